@@ -1,0 +1,507 @@
+// api.cu -- the C ABI of include/cbev.h: engine lifetime, uploads, reset / step orchestration.
+#include <cuda.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "engine.h"
+
+static thread_local char g_err[512] = "";
+
+void cbev_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define CU_TRY(expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      cbev_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CBEV_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+namespace {
+
+// CBEV_DEBUG_SYNC=1: synchronise after every kernel and report which one faulted
+int debug_sync(const char* what, cudaStream_t s) {
+  static const bool on = getenv("CBEV_DEBUG_SYNC") != nullptr;
+  if (!on) return CBEV_OK;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cbev_set_error("kernel %s failed: %s", what, cudaGetErrorString(e));
+    return CBEV_ERR_CUDA;
+  }
+  return CBEV_OK;
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) {
+    cbev_set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return CBEV_ERR_NOMEM;
+  }
+  return cudaMemset(*p, 0, n * sizeof(T)) == cudaSuccess ? CBEV_OK : CBEV_ERR_CUDA;
+}
+
+template <typename T>
+int dev_upload(T** p, const T* host, size_t n) {
+  int rc = dev_alloc(p, n);
+  if (rc) return rc;
+  if (n && host) {
+    if (cudaMemcpy(*p, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cbev_set_error("cudaMemcpy H2D failed");
+      return CBEV_ERR_CUDA;
+    }
+  }
+  return CBEV_OK;
+}
+
+template <typename T>
+void dev_free(T*& p) {
+  if (p) cudaFree((void*)p);
+  p = nullptr;
+}
+
+void free_pool(PoolDev& p) {
+  dev_free(p.ego_state0); dev_free(p.ego_target_speed); dev_free(p.len_ego_route); dev_free(p.ego_tidx0);
+  dev_free(p.num_vehicles); dev_free(p.ego_off); dev_free(p.rew_off); dev_free(p.actor_off); dev_free(p.tl_off);
+  dev_free(p.ego_cx); dev_free(p.ego_cy); dev_free(p.ego_cyaw); dev_free(p.rew_rx); dev_free(p.rew_ry);
+  dev_free(p.rew_cum); dev_free(p.act_kind); dev_free(p.act_beh); dev_free(p.act_state0); dev_free(p.act_cruise_px);
+  dev_free(p.act_cruise_mps); dev_free(p.act_beh_p); dev_free(p.act_tidx0); dev_free(p.act_route_off);
+  dev_free(p.act_raw_off); dev_free(p.act_retreat_slot); dev_free(p.act_cx); dev_free(p.act_cy); dev_free(p.act_cyaw);
+  dev_free(p.act_raw_x); dev_free(p.act_raw_y); dev_free(p.tl_rect); dev_free(p.tl_color); dev_free(p.sg_mat);
+  p = PoolDev();
+}
+
+void free_state(EnvState& s) {
+  dev_free(s.scene); dev_free(s.episode); dev_free(s.done); dev_free(s.ego); dev_free(s.ego2); dev_free(s.egoi);
+  dev_free(s.tgt_vis); dev_free(s.stats); dev_free(s.ax); dev_free(s.ay); dev_free(s.ayaw); dev_free(s.av);
+  dev_free(s.atarget_mps); dev_free(s.aelapsed); dev_free(s.astate_elapsed); dev_free(s.atidx); dev_free(s.arxlen);
+  dev_free(s.aflags); dev_free(s.retreat); dev_free(s.retreat_n);
+  s = EnvState();
+}
+
+int channels_of(int mask_mode) {
+  static const int ch[6] = {1, 2, 4, 5, 6, 7};
+  return (mask_mode >= 0 && mask_mode < 6) ? ch[mask_mode] : -1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int build_tensor_map(cbev_engine* e) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+    cbev_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return CBEV_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)e->map_w, (cuuint64_t)e->map_h};
+  cuuint64_t strides[1] = {(cuuint64_t)e->map_w};
+  cuuint32_t box[2] = {(cuuint32_t)e->box_w, (cuuint32_t)e->crop};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((EncodeTiledFn)fn)(reinterpret_cast<CUtensorMap*>(e->tmap), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, e->map,
+                                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cbev_set_error("cuTensorMapEncodeTiled failed with CUresult %d (map %dx%d, box %dx%d)", (int)r, e->map_w, e->map_h,
+                   e->box_w, e->crop);
+    return CBEV_ERR_CUDA;
+  }
+  return CBEV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cbev_version(void) { return CBEV_VERSION; }
+const char* cbev_last_error(void) { return g_err; }
+
+int cbev_create(const cbev_config* cfg, cbev_handle* out) {
+  if (!cfg || !out) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  *out = nullptr;
+  if (cfg->num_envs < 1) { cbev_set_error("num_envs must be >= 1"); return CBEV_ERR_ARG; }
+  if (cfg->fov_size != 128) { cbev_set_error("only size=128 (Town01-128 map scale) is implemented, got %d", cfg->fov_size); return CBEV_ERR_ARG; }
+  if (cfg->obs_mode < 0 || cfg->obs_mode > 2) { cbev_set_error("bad obs_mode %d", cfg->obs_mode); return CBEV_ERR_ARG; }
+  if (cfg->obs_mode != CBEV_OBS_RGB && (cfg->obs_h != 96 || cfg->obs_w != 96)) {
+    cbev_set_error("only obs_size=(96, 96) is implemented (cv2 INTER_AREA 128->96), got (%d, %d)", cfg->obs_h, cfg->obs_w);
+    return CBEV_ERR_ARG;
+  }
+  if (cfg->obs_mode == CBEV_OBS_SEMANTIC && channels_of(cfg->mask_mode) < 0) { cbev_set_error("bad mask_mode %d", cfg->mask_mode); return CBEV_ERR_ARG; }
+  if (cfg->frame_stack < 1) { cbev_set_error("frame_stack must be >= 1"); return CBEV_ERR_ARG; }
+  if (!(cfg->anchor_x_frac >= 0.0 && cfg->anchor_x_frac <= 1.0 && cfg->anchor_y_frac >= 0.0 && cfg->anchor_y_frac <= 1.0)) {
+    cbev_set_error("ego anchor fractions must be within [0, 1]");
+    return CBEV_ERR_ARG;
+  }
+  const int F = cfg->obs_mode == CBEV_OBS_RGB ? 1 : cfg->frame_stack;
+  if (F > 1 && cfg->ring_slots < 2 * F - 1) { cbev_set_error("ring_slots must be >= 2*frame_stack-1 (%d), got %d", 2 * F - 1, cfg->ring_slots); return CBEV_ERR_ARG; }
+  if (F == 1 && cfg->ring_slots < 1) { cbev_set_error("ring_slots must be >= 1"); return CBEV_ERR_ARG; }
+  if (cfg->action_mode == CBEV_ACTION_DISCRETE && (cfg->n_discrete < 1 || cfg->n_discrete > 16)) { cbev_set_error("n_discrete must be in [1, 16]"); return CBEV_ERR_ARG; }
+  if (cfg->max_actors < 0) { cbev_set_error("max_actors must be >= 0"); return CBEV_ERR_ARG; }
+
+  cbev_engine* e = new (std::nothrow) cbev_engine();
+  if (!e) return CBEV_ERR_NOMEM;
+  e->cfg = *cfg;
+  e->cfg.frame_stack = F;
+  if (F == 1) e->cfg.ring_slots = 1;
+  e->N = cfg->num_envs;
+  cudaGetDevice(&e->device);
+  // FovRenderer constants (envs/fov.py:30-44); padding = crop_size (envs/world.py:69-78)
+  const int m = cfg->fov_size - 1;
+  int ax = (int)nearbyint((double)m * cfg->anchor_x_frac), ay = (int)nearbyint((double)m * cfg->anchor_y_frac);
+  ax = ax < 0 ? 0 : (ax > m ? m : ax);
+  ay = ay < 0 ? 0 : (ay > m ? m : ay);
+  e->anchor_x = ax;
+  e->anchor_y = ay;
+  int mx = ax > m - ax ? ax : m - ax, my = ay > m - ay ? ay : m - ay;
+  int crop = (int)ceil(2.0 * hypot((double)mx, (double)my));
+  if (crop < cfg->fov_size) crop = cfg->fov_size;
+  if (crop > 241) { delete e; cbev_set_error("crop size %d exceeds the 256-texel TMA box (crop + 15 alignment slack)", crop); return CBEV_ERR_ARG; }
+  e->crop = crop;
+  e->pad = crop;
+  e->box_w = ((crop + 15 + 15) / 16) * 16;  // aligned superset of any 16-byte-unaligned crop origin
+  e->channels = cfg->obs_mode == CBEV_OBS_SEMANTIC ? channels_of(cfg->mask_mode) : 1;
+  if (cfg->obs_mode == CBEV_OBS_SEMANTIC) e->frame_bytes = (int64_t)e->channels * cfg->obs_h * cfg->obs_w * 4;
+  else if (cfg->obs_mode == CBEV_OBS_GRAY) e->frame_bytes = (int64_t)cfg->obs_h * cfg->obs_w;
+  else e->frame_bytes = (int64_t)cfg->fov_size * cfg->fov_size * 3;
+
+  const size_t N = (size_t)e->N, A = (size_t)(cfg->max_actors > 0 ? cfg->max_actors : 1);
+  int rc = 0;
+  rc |= dev_alloc(&e->st.scene, N);
+  rc |= dev_alloc(&e->st.episode, N);
+  rc |= dev_alloc(&e->st.done, N);
+  rc |= dev_alloc(&e->st.ego, N * 24);
+  rc |= dev_alloc(&e->st.egoi, N * 8);
+  rc |= dev_alloc(&e->st.tgt_vis, N);
+  rc |= dev_alloc(&e->st.stats, N * 12);
+  rc |= dev_alloc(&e->st.ax, N * A);
+  rc |= dev_alloc(&e->st.ay, N * A);
+  rc |= dev_alloc(&e->st.ayaw, N * A);
+  rc |= dev_alloc(&e->st.av, N * A);
+  rc |= dev_alloc(&e->st.atarget_mps, N * A);
+  rc |= dev_alloc(&e->st.aelapsed, N * A);
+  rc |= dev_alloc(&e->st.astate_elapsed, N * A);
+  rc |= dev_alloc(&e->st.atidx, N * A);
+  rc |= dev_alloc(&e->st.arxlen, N * A);
+  rc |= dev_alloc(&e->st.aflags, N * A);
+  rc |= dev_alloc(&e->desc, N * CBEV_DESC_WORDS);
+  rc |= dev_alloc(&e->fov, N * (size_t)cfg->fov_size * cfg->fov_size);
+  rc |= dev_alloc(&e->gstats, (size_t)CBEV_STATS_FIELDS);
+  rc |= dev_alloc(&e->h_reward_dev, N);
+  rc |= dev_alloc(&e->h_term_dev, N);
+  rc |= dev_alloc(&e->h_trunc_dev, N);
+  rc |= dev_alloc((uint8_t**)&e->h_actions_dev, N * 16);
+  if (rc) { cbev_destroy(e); return rc; }
+  cudaMemset(e->st.scene, 0xff, N * sizeof(int32_t));
+  *out = e;
+  return CBEV_OK;
+}
+
+int cbev_destroy(cbev_handle e) {
+  if (!e) return CBEV_OK;
+  free_pool(e->pool);
+  free_state(e->st);
+  dev_free(e->map); dev_free(e->desc); dev_free(e->rects); dev_free(e->fov); dev_free(e->gstats);
+  dev_free(e->h_reward_dev); dev_free(e->h_term_dev); dev_free(e->h_trunc_dev);
+  { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }
+  dev_free(e->all_scene_ids);
+  delete e;
+  return CBEV_OK;
+}
+
+int cbev_upload_map(cbev_handle e, const uint8_t* cls_host, int32_t w, int32_t h_px) {
+  if (!e || !cls_host) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  if (w < 16 || h_px < 16 || (w % 16) != 0) { cbev_set_error("map width must be a multiple of 16 (TMA row pitch), got %dx%d", w, h_px); return CBEV_ERR_ARG; }
+  for (size_t i = 0; i < (size_t)w * h_px; ++i)
+    if (cls_host[i] > 2) { cbev_set_error("map classes must be 0 (non-drivable), 1 (drivable) or 2 (sidewalk)"); return CBEV_ERR_ARG; }
+  dev_free(e->map);
+  int rc = dev_upload(&e->map, cls_host, (size_t)w * h_px);
+  if (rc) return rc;
+  e->map_w = w;
+  e->map_h = h_px;
+  rc = build_tensor_map(e);
+  if (rc) return rc;
+  e->has_map = true;
+  return CBEV_OK;
+}
+
+int cbev_upload_scene_pool(cbev_handle e, const cbev_pool_desc* p) {
+  if (!e || !p) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  if (p->n_scenes < 1) { cbev_set_error("scene pool is empty"); return CBEV_ERR_ARG; }
+  const int n = p->n_scenes;
+  // ---- validate (the reference raises on malformed scenes at reset; here at upload) ----
+  int max_actors = 0, max_targets = 0, max_tl = 0, max_retreat = 0;
+  std::vector<int32_t> slots((size_t)(p->n_actors_total > 0 ? p->n_actors_total : 1), -1);
+  for (int s = 0; s < n; ++s) {
+    int nt = p->ego_off[s + 1] - p->ego_off[s];
+    if (nt < 2 || nt > CBEV_MAX_TARGETS) { cbev_set_error("scene %d: ego route has %d points, supported range is [2, %d]", s, nt, CBEV_MAX_TARGETS); return CBEV_ERR_ARG; }
+    if (p->ego_tidx0[s] < 0 || p->ego_tidx0[s] >= nt) { cbev_set_error("scene %d: ego target index out of range", s); return CBEV_ERR_ARG; }
+    int a0 = p->actor_off[s], a1 = p->actor_off[s + 1];
+    if (a1 < a0 || a1 > p->n_actors_total) { cbev_set_error("scene %d: bad actor offsets", s); return CBEV_ERR_ARG; }
+    int nret = 0;
+    bool seen_ped = false;
+    for (int a = a0; a < a1; ++a) {
+      if (p->act_kind[a] > 1) { cbev_set_error("scene %d: bad actor kind", s); return CBEV_ERR_ARG; }
+      if (p->act_kind[a] == 1) seen_ped = true;
+      else if (seen_ped) { cbev_set_error("scene %d: vehicles must precede pedestrians (draw / collision order)", s); return CBEV_ERR_ARG; }
+      int np = p->act_route_off[a + 1] - p->act_route_off[a];
+      if (np < 2) { cbev_set_error("scene %d: actor route needs >= 2 points", s); return CBEV_ERR_ARG; }
+      if (p->act_beh[a] > CBEV_BEH_STOP_RETURN) { cbev_set_error("scene %d: unknown behaviour id %d", s, p->act_beh[a]); return CBEV_ERR_ARG; }
+      if (p->act_beh[a] == CBEV_BEH_STOP_RETURN) {
+        if (!p->sg_mat) { cbev_set_error("scene %d: StopReturn behaviour needs sg_mat (retreat smoothing operators)", s); return CBEV_ERR_ARG; }
+        int nr = p->act_raw_off[a + 1] - p->act_raw_off[a];
+        if (nr + 1 > CBEV_SG_MAX) { cbev_set_error("scene %d: retreat route of %d points exceeds CBEV_SG_MAX", s, nr + 1); return CBEV_ERR_ARG; }
+        slots[a] = nret++;
+      }
+    }
+    if (a1 - a0 > max_actors) max_actors = a1 - a0;
+    if (nt > max_targets) max_targets = nt;
+    int ntl = p->tl_off[s + 1] - p->tl_off[s];
+    if (ntl > max_tl) max_tl = ntl;
+    if (nret > max_retreat) max_retreat = nret;
+  }
+  if (max_actors > e->cfg.max_actors) { cbev_set_error("pool has scenes with %d actors but the engine was created with max_actors=%d", max_actors, e->cfg.max_actors); return CBEV_ERR_ARG; }
+
+  free_pool(e->pool);
+  PoolDev& d = e->pool;
+  d.n_scenes = n;
+  d.n_actors_total = p->n_actors_total;
+  d.max_actors = max_actors;
+  d.max_targets = max_targets;
+  d.max_tl = max_tl;
+  d.max_retreat = max_retreat;
+  const size_t na = (size_t)p->n_actors_total, nr = (size_t)p->ego_off[n], nq = (size_t)p->rew_off[n];
+  const size_t npts = na ? (size_t)p->act_route_off[na] : 0, nraw = na ? (size_t)p->act_raw_off[na] : 0;
+  const size_t ntl = (size_t)p->tl_off[n];
+  int rc = 0;
+  rc |= dev_upload(&d.ego_state0, p->ego_state0, (size_t)n * 4);
+  rc |= dev_upload(&d.ego_target_speed, p->ego_target_speed, (size_t)n);
+  rc |= dev_upload(&d.len_ego_route, p->len_ego_route, (size_t)n);
+  rc |= dev_upload(&d.ego_tidx0, p->ego_tidx0, (size_t)n);
+  rc |= dev_upload(&d.num_vehicles, p->num_vehicles, (size_t)n);
+  rc |= dev_upload(&d.ego_off, p->ego_off, (size_t)n + 1);
+  rc |= dev_upload(&d.rew_off, p->rew_off, (size_t)n + 1);
+  rc |= dev_upload(&d.actor_off, p->actor_off, (size_t)n + 1);
+  rc |= dev_upload(&d.tl_off, p->tl_off, (size_t)n + 1);
+  rc |= dev_upload(&d.ego_cx, p->ego_cx, nr);
+  rc |= dev_upload(&d.ego_cy, p->ego_cy, nr);
+  rc |= dev_upload(&d.ego_cyaw, p->ego_cyaw, nr);
+  rc |= dev_upload(&d.rew_rx, p->rew_rx, nq);
+  rc |= dev_upload(&d.rew_ry, p->rew_ry, nq);
+  rc |= dev_upload(&d.rew_cum, p->rew_cum, nq);
+  rc |= dev_upload(&d.act_kind, p->act_kind, na);
+  rc |= dev_upload(&d.act_beh, p->act_beh, na);
+  rc |= dev_upload(&d.act_state0, p->act_state0, na * 4);
+  rc |= dev_upload(&d.act_cruise_px, p->act_cruise_px, na);
+  rc |= dev_upload(&d.act_cruise_mps, p->act_cruise_mps, na);
+  rc |= dev_upload(&d.act_beh_p, p->act_beh_p, na * 4);
+  rc |= dev_upload(&d.act_tidx0, p->act_tidx0, na);
+  rc |= dev_upload(&d.act_route_off, p->act_route_off, na + 1);
+  rc |= dev_upload(&d.act_raw_off, p->act_raw_off, na + 1);
+  rc |= dev_upload(&d.act_retreat_slot, slots.data(), na ? na : 1);
+  rc |= dev_upload(&d.act_cx, p->act_cx, npts);
+  rc |= dev_upload(&d.act_cy, p->act_cy, npts);
+  rc |= dev_upload(&d.act_cyaw, p->act_cyaw, npts);
+  rc |= dev_upload(&d.act_raw_x, p->act_raw_x, nraw);
+  rc |= dev_upload(&d.act_raw_y, p->act_raw_y, nraw);
+  rc |= dev_upload(&d.tl_rect, p->tl_rect, ntl * 4);
+  rc |= dev_upload(&d.tl_color, p->tl_color, ntl);
+  if (p->sg_mat) rc |= dev_upload(&d.sg_mat, p->sg_mat, (size_t)(CBEV_SG_MAX + 1) * CBEV_SG_MAX * CBEV_SG_MAX);
+  if (rc) return rc;
+  // per-env buffers that depend on the pool
+  dev_free(e->rects);
+  dev_free(e->st.retreat);
+  dev_free(e->st.retreat_n);
+  e->max_rects = e->cfg.max_actors + CBEV_MAX_TARGETS + max_tl + 1;
+  rc |= dev_alloc(&e->rects, (size_t)e->N * e->max_rects);
+  rc |= dev_alloc(&e->st.retreat, (size_t)e->N * (max_retreat ? max_retreat : 1) * 3 * CBEV_SG_MAX);
+  rc |= dev_alloc(&e->st.retreat_n, (size_t)e->N * (max_retreat ? max_retreat : 1));
+  if (rc) return rc;
+  e->has_pool = true;
+  return CBEV_OK;
+}
+
+int64_t cbev_frame_bytes(cbev_handle e) { return e ? e->frame_bytes : -1; }
+
+int cbev_bind_obs_ring(cbev_handle e, void* ring_dev, int64_t bytes) {
+  if (!e || !ring_dev) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  int64_t need = (int64_t)e->N * e->cfg.ring_slots * e->frame_bytes;
+  if (bytes < need) { cbev_set_error("observation ring needs %lld bytes, got %lld", (long long)need, (long long)bytes); return CBEV_ERR_ARG; }
+  if (((uintptr_t)ring_dev & 15) != 0) { cbev_set_error("observation ring must be 16-byte aligned"); return CBEV_ERR_ARG; }
+  e->ring = ring_dev;
+  e->ring_bytes = bytes;
+  return CBEV_OK;
+}
+
+static int check_ready(cbev_handle e, bool need_reset) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  if (!e->has_map) { cbev_set_error("no map uploaded (cbev_upload_map)"); return CBEV_ERR_STATE; }
+  if (!e->has_pool) { cbev_set_error("no scene pool uploaded (cbev_upload_scene_pool)"); return CBEV_ERR_STATE; }
+  if (!e->ring) { cbev_set_error("no observation ring bound (cbev_bind_obs_ring)"); return CBEV_ERR_STATE; }
+  if (need_reset && !e->was_reset) { cbev_set_error("step() called before reset()"); return CBEV_ERR_STATE; }
+  return CBEV_OK;
+}
+
+int cbev_reset(cbev_handle e, const uint8_t* mask_dev, const int32_t* scene_ids_dev, void* stream) {
+  int rc = check_ready(e, false);
+  if (rc) return rc;
+  if (!scene_ids_dev) { cbev_set_error("scene_ids is required"); return CBEV_ERR_ARG; }
+  if (mask_dev && !e->was_reset) { cbev_set_error("the first reset must cover every env (mask = NULL)"); return CBEV_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int F = e->cfg.frame_stack, L = e->cfg.ring_slots;
+  if (e->head < 0) e->head = F - 1;
+  cbev_launch_reset(e, mask_dev, scene_ids_dev, s);
+  if ((rc = debug_sync("k_reset", s))) return rc;
+  if (cbev_launch_render(e, e->head, F > 1 ? L - F + 1 : 0, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
+  if ((rc = debug_sync("k_render (reset frame)", s))) return rc;
+  CU_TRY(cudaGetLastError());
+  e->was_reset = true;
+  return CBEV_OK;
+}
+
+int cbev_step(cbev_handle e, const void* actions_dev, const cbev_step_out* out, void* stream) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!actions_dev || !out || !out->reward || !out->terminated || !out->truncated) { cbev_set_error("actions, reward, terminated and truncated are required"); return CBEV_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int F = e->cfg.frame_stack, L = e->cfg.ring_slots;
+  int head = e->head + 1;
+  if (head >= L) head = F - 1;
+  cbev_launch_sim(e, actions_dev, out, s);
+  if ((rc = debug_sync("k_sim", s))) return rc;
+  if (cbev_launch_render(e, head, F > 1 ? L - F + 1 : 0, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
+  if ((rc = debug_sync("k_render", s))) return rc;
+  CU_TRY(cudaGetLastError());
+  e->head = head;
+  e->steps += 1;
+  return CBEV_OK;
+}
+
+int cbev_step_host(cbev_handle e, const void* actions_host, double* reward_host, uint8_t* terminated_host,
+                   uint8_t* truncated_host, void* stream) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!actions_host || !reward_host || !terminated_host || !truncated_host) { cbev_set_error("null host buffer"); return CBEV_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = (size_t)e->N;
+  const size_t abytes = e->cfg.action_mode == CBEV_ACTION_DISCRETE ? N * 8 : N * 12;
+  CU_TRY(cudaMemcpyAsync(e->h_actions_dev, actions_host, abytes, cudaMemcpyHostToDevice, s));
+  cbev_step_out out;
+  memset(&out, 0, sizeof(out));
+  out.reward = e->h_reward_dev;
+  out.terminated = e->h_term_dev;
+  out.truncated = e->h_trunc_dev;
+  rc = cbev_step(e, e->h_actions_dev, &out, stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(reward_host, e->h_reward_dev, N * 8, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(terminated_host, e->h_term_dev, N, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(truncated_host, e->h_trunc_dev, N, cudaMemcpyDeviceToHost, s));
+  return CBEV_OK;
+}
+
+int cbev_obs_head(cbev_handle e, int32_t* head) {
+  if (!e || !head) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  *head = e->head;
+  return CBEV_OK;
+}
+
+int cbev_get_state(cbev_handle e, double* ego_host, double* actors_host) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  CU_TRY(cudaDeviceSynchronize());
+  const size_t N = (size_t)e->N, A = (size_t)(e->cfg.max_actors > 0 ? e->cfg.max_actors : 1);
+  if (ego_host) {
+    std::vector<double> eg(N * 24);
+    std::vector<int32_t> ei(N * 8);
+    std::vector<unsigned long long> tv(N);
+    CU_TRY(cudaMemcpy(eg.data(), e->st.ego, N * 24 * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ei.data(), e->st.egoi, N * 8 * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(tv.data(), e->st.tgt_vis, N * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < N; ++i) {
+      double* o = ego_host + i * 16;
+      for (int k = 0; k < 9; ++k) o[k] = eg[i * 24 + k];  // x,y,yaw,v,x1,y1,yaw1,v1,acc
+      o[9] = (double)ei[i * 8 + 0];                        // tidx
+      o[10] = eg[i * 24 + 9];                              // t
+      o[11] = eg[i * 24 + 10];                             // dist2goal
+      o[12] = eg[i * 24 + 11];                             // dist2goal_1
+      o[13] = eg[i * 24 + 12];                             // s_prev
+      o[14] = (double)(uint32_t)(tv[i] & 0xffffffffull);
+      o[15] = (double)(uint32_t)(tv[i] >> 32);
+    }
+  }
+  if (actors_host) {
+    std::vector<double> x(N * A), y(N * A), yaw(N * A), v(N * A), tm(N * A);
+    std::vector<int32_t> ti(N * A);
+    std::vector<uint8_t> fl(N * A);
+    CU_TRY(cudaMemcpy(x.data(), e->st.ax, N * A * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(y.data(), e->st.ay, N * A * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(yaw.data(), e->st.ayaw, N * A * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(v.data(), e->st.av, N * A * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(tm.data(), e->st.atarget_mps, N * A * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ti.data(), e->st.atidx, N * A * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(fl.data(), e->st.aflags, N * A, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < N * A; ++i) {
+      double* o = actors_host + i * 8;
+      o[0] = x[i]; o[1] = y[i]; o[2] = yaw[i]; o[3] = v[i]; o[4] = (double)ti[i]; o[5] = (double)(fl[i] & 15);
+      o[6] = tm[i]; o[7] = (double)fl[i];
+    }
+  }
+  return CBEV_OK;
+}
+
+int cbev_set_ego_state(cbev_handle e, const double* ego_host) {
+  if (!e || !ego_host) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  CU_TRY(cudaDeviceSynchronize());
+  const size_t N = (size_t)e->N;
+  std::vector<double> eg(N * 24);
+  std::vector<int32_t> ei(N * 8);
+  CU_TRY(cudaMemcpy(eg.data(), e->st.ego, N * 24 * 8, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(ei.data(), e->st.egoi, N * 8 * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < N; ++i) {
+    const double* o = ego_host + i * 16;
+    for (int k = 0; k < 9; ++k) eg[i * 24 + k] = o[k];
+    ei[i * 8 + 0] = (int32_t)o[9];
+  }
+  CU_TRY(cudaMemcpy(e->st.ego, eg.data(), N * 24 * 8, cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(e->st.egoi, ei.data(), N * 8 * 4, cudaMemcpyHostToDevice));
+  return CBEV_OK;
+}
+
+int cbev_copy_fov(cbev_handle e, uint8_t* fov_dev, void* stream) {
+  if (!e || !fov_dev) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  size_t bytes = (size_t)e->N * e->cfg.fov_size * e->cfg.fov_size;
+  CU_TRY(cudaMemcpyAsync(fov_dev, e->fov, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return CBEV_OK;
+}
+
+int cbev_read_stats(cbev_handle e, double* stats_dev, int32_t reset_after, void* stream) {
+  if (!e || !stats_dev) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(cudaMemcpyAsync(stats_dev, e->gstats, CBEV_STATS_FIELDS * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  double steps = (double)e->steps * (double)e->N;
+  CU_TRY(cudaMemcpyAsync(stats_dev + CBEV_S_STEPS, &steps, sizeof(double), cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaStreamSynchronize(s));  // `steps` lives on this stack frame
+  if (reset_after) {
+    CU_TRY(cudaMemsetAsync(e->gstats, 0, CBEV_STATS_FIELDS * sizeof(double), s));
+    e->steps = 0;
+  }
+  return CBEV_OK;
+}
+
+int64_t cbev_launch_count(cbev_handle e) { return e ? e->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// engine.h -- internal layout of the CarlaBEV B200 engine (not part of the C ABI).
+//
+// HBM layout (all struct-of-arrays):
+//   * PoolDev   : read-only scene pool, flat arrays + offset tables (one copy per GPU)
+//   * EnvState  : per-env mutable state, env-major; actor arrays are [N][max_actors]
+//   * RenderDesc: per-env render descriptor written by the sim kernel, read by the raster kernel
+//   * obs ring  : caller-owned, [N][ring_slots][frame]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cbev.h"
+
+#define CBEV_MAX_TARGETS 64   // ego route points (targets) per scene, one visibility bit each
+#define CBEV_DESC_WORDS 16    // ints per render-descriptor header
+#define CBEV_WARPS_PER_BLOCK 4
+
+// render descriptor header words
+enum {
+  RD_OX = 0,   // crop origin in MAP coordinates (xmin - pad), may be negative (TMA zero-fills = NON_DRIVABLE)
+  RD_OY,
+  RD_MODE,     // 0: exact 90-degree turns, 1: 16.16 fixed-point walk
+  RD_TURNS,
+  RD_NX, RD_NY, RD_ISIN, RD_ICOS, RD_AX, RD_AY, RD_XD, RD_YD, RD_CY,
+  RD_NRECTS,
+  RD_FLAGS,    // bit0: reset frame (fill every window slot)
+  RD_PAD
+};
+
+struct PoolDev {
+  int32_t n_scenes = 0, n_actors_total = 0, max_actors = 0, max_targets = 0, max_tl = 0, max_retreat = 0;
+  double *ego_state0 = nullptr, *ego_target_speed = nullptr, *len_ego_route = nullptr;
+  int32_t *ego_tidx0 = nullptr, *num_vehicles = nullptr;
+  int32_t *ego_off = nullptr, *rew_off = nullptr, *actor_off = nullptr, *tl_off = nullptr;
+  double *ego_cx = nullptr, *ego_cy = nullptr, *ego_cyaw = nullptr;
+  int32_t *rew_rx = nullptr, *rew_ry = nullptr;
+  double* rew_cum = nullptr;
+  uint8_t *act_kind = nullptr, *act_beh = nullptr;
+  double *act_state0 = nullptr, *act_cruise_px = nullptr, *act_cruise_mps = nullptr, *act_beh_p = nullptr;
+  int32_t *act_tidx0 = nullptr, *act_route_off = nullptr, *act_raw_off = nullptr;
+  int32_t* act_retreat_slot = nullptr;  // per actor: slot in the per-env retreat-route buffer or -1
+  double *act_cx = nullptr, *act_cy = nullptr, *act_cyaw = nullptr, *act_raw_x = nullptr, *act_raw_y = nullptr;
+  int32_t* tl_rect = nullptr;
+  uint8_t* tl_color = nullptr;
+  double* sg_mat = nullptr;
+};
+
+struct EnvState {
+  int32_t* scene = nullptr;        // [N] pool index, -1 before the first reset
+  int32_t* episode = nullptr;      // [N] episodes finished by this env
+  uint8_t* done = nullptr;         // [N] last step was terminal (needs reset)
+  double* ego = nullptr;           // [N][16]: x,y,yaw,v,x1,y1,yaw1,v1,acc,t,dist2goal,dist2goal_1,s_prev,last_dyaw,pc0..1 (see sim.cu)
+  double* ego2 = nullptr;          // [N][4]: prev comfort yaw_rate, spare
+  int32_t* egoi = nullptr;         // [N][8]: tidx, flags(bit0 comfort valid, bit1 s_prev valid), k, consecutive_offroad, spare
+  unsigned long long* tgt_vis = nullptr;  // [N]
+  double* stats = nullptr;         // [N][12]: return, length, sum speed, sum |comfort| x6, viol, harsh, cause
+  // actors [N][max_actors]
+  double *ax = nullptr, *ay = nullptr, *ayaw = nullptr, *av = nullptr, *atarget_mps = nullptr;
+  double *aelapsed = nullptr, *astate_elapsed = nullptr;
+  int32_t *atidx = nullptr, *arxlen = nullptr;
+  uint8_t* aflags = nullptr;       // bits0-3 fsm, bit4 braking, bit5 on retreat route
+  // retreat routes [N][max_retreat][CBEV_SG_MAX][3] + lengths [N][max_retreat]
+  double* retreat = nullptr;
+  int32_t* retreat_n = nullptr;
+};
+
+struct SimParams {
+  int32_t N, max_actors, max_rects, max_retreat;
+  int32_t map_w, map_h, fov, crop, pad, anchor_x, anchor_y;
+  int32_t action_mode, n_discrete, reward_mode, autoreset;
+  uint64_t seed;
+  const uint8_t* map;
+  float discrete_table[16 * 3];
+  cbev_config cfg;  // reward parameters
+};
+
+struct cbev_engine {
+  cbev_config cfg;
+  int device = 0;
+  int32_t N = 0, crop = 0, pad = 0, anchor_x = 0, anchor_y = 0, box_w = 0;
+  int32_t map_w = 0, map_h = 0;
+  uint8_t* map = nullptr;
+  alignas(64) unsigned char tmap[128];  // CUtensorMap of the class map
+  bool has_map = false, has_pool = false, was_reset = false;
+  PoolDev pool;
+  EnvState st;
+  int32_t max_rects = 0;
+  int32_t* desc = nullptr;         // [N][CBEV_DESC_WORDS]
+  uint32_t* rects = nullptr;       // [N][max_rects]
+  uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)
+  void* ring = nullptr;
+  int64_t ring_bytes = 0, frame_bytes = 0;
+  int32_t channels = 0;
+  int32_t head = -1;
+  double* gstats = nullptr;        // [CBEV_STATS_FIELDS]
+  // staging for cbev_step_host
+  void* h_actions_dev = nullptr;
+  double* h_reward_dev = nullptr;
+  uint8_t *h_term_dev = nullptr, *h_trunc_dev = nullptr;
+  int32_t* all_scene_ids = nullptr;
+  int64_t launches = 0;
+  int64_t steps = 0;
+};
+
+// kernels (sim.cu / render.cu)
+void cbev_launch_reset(cbev_engine* e, const uint8_t* mask, const int32_t* scene_ids, cudaStream_t s);
+void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, cudaStream_t s);
+int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, cudaStream_t s);
+void cbev_set_error(const char* fmt, ...);

@@ -1,0 +1,392 @@
+// render.cu -- BEV rasteriser + observation writer (one CTA per environment).
+//
+// Restates, for the GPU, the reference's per-step image path:
+//   Scene._scene_step map blit + ActorManager.draw_all (src/scenes/scene.py:93-95,
+//   src/managers/actor_manager.py:121-132) -> FovRenderer crop / pygame.transform.rotate /
+//   compose (envs/fov.py:70-94, envs/world.py:137-157) -> Hero.draw (src/actors/hero.py:26-32)
+//   -> CarlaBEV.render (envs/carlabev.py:233-236) -> ResizeObservation (cv2 INTER_AREA 128->96)
+//   -> SemanticMaskWrapper / GrayscaleObservation -> FrameStackObservation
+//   (envs/__init__.py:62-83, wrappers/rgb_to_semantic.py:65-142).
+//
+// Pipeline inside one CTA (all on-chip between the map read and the observation write):
+//   1. TMA 2-D tile load of the class-map crop (16-byte aligned superset) into shared memory.  Out-of-map texels are
+//      zero-filled by the TMA unit = class 0 = NON_DRIVABLE, which is exactly the padded render
+//      surface of the reference (envs/world.py:80-87), so no padded copy of the map exists.
+//   2. the sim kernel's clipped draw list is painted over the tile in draw order.
+//   3. every FOV pixel is inverse-mapped through pygame's 16.16 fixed-point rotate walk
+//      (or the exact 90-degree permutation) into the tile -> 128x128 palette-index image.
+//   4. 2x2 area taps (weights in 1/16, round-half-even == cv2 INTER_AREA for 128->96) and exact
+//      colour equality give one channel bitmask per 96x96 pixel.
+//   5. masks are expanded to float32 planes and streamed to HBM with coalesced 16-byte stores,
+//      once per ring slot the frame belongs to.
+#include <cuda.h>
+
+#include "engine.h"
+
+namespace {
+
+constexpr int RT = 256;  // threads per CTA
+
+__constant__ uint32_t c_pal_rg[CBEV_PAL_COUNT];   // R | G << 16
+__constant__ uint32_t c_pal_b[CBEV_PAL_COUNT];
+__constant__ uint32_t c_pal_key[CBEV_PAL_COUNT];  // R | G << 8 | B << 16
+__constant__ uint8_t c_chan_mask[6][CBEV_PAL_COUNT + 1];  // [mask mode][palette index or NONE] -> channel bits
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_u4(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+struct RenderParams {
+  int32_t N, fov, crop, box_w, anchor_x, anchor_y;
+  int32_t frame_stack, ring_slots, head, mirror;  // mirror = slot offset (L - F + 1)
+  int64_t frame_bytes;
+  int32_t tile_bytes, pad0;
+  const int32_t* desc;
+  const uint32_t* rects;
+  int32_t max_rects;
+  uint8_t* fov_out;  // [N][S][S] palette-index frames (nullable)
+  void* ring;
+};
+
+// cv2 INTER_AREA 128 -> 96: dst pixel d covers src taps s0 = floor(4d/3), s0+1 with weights
+// (3-ph, 1+ph)/4, ph = d % 3.  Product weights are in 1/16 units; sums are exact.
+__device__ __forceinline__ uint32_t round_half_even_16(uint32_t s) {
+  uint32_t q = s >> 4, r = s & 15u;
+  return q + ((r > 8u) || (r == 8u && (q & 1u)));
+}
+
+// resolve the resized pixel: returns palette index (exact colour equality) or CBEV_PAL_COUNT (no class)
+__device__ __forceinline__ uint32_t blend_rgb(uint32_t c00, uint32_t c01, uint32_t c10, uint32_t c11, uint32_t wx0,
+                                              uint32_t wx1, uint32_t wy0, uint32_t wy1, const uint32_t* s_rg,
+                                              const uint32_t* s_b) {
+  uint32_t rg = wy0 * (wx0 * s_rg[c00] + wx1 * s_rg[c01]) + wy1 * (wx0 * s_rg[c10] + wx1 * s_rg[c11]);
+  uint32_t b = wy0 * (wx0 * s_b[c00] + wx1 * s_b[c01]) + wy1 * (wx0 * s_b[c10] + wx1 * s_b[c11]);
+  uint32_t R = round_half_even_16(rg & 0xffffu), G = round_half_even_16(rg >> 16), B = round_half_even_16(b);
+  return R | (G << 8) | (B << 16);
+}
+
+template <int OBS_MODE, int CHANNELS>
+__global__ void __launch_bounds__(RT, 3)
+k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: [tile: crop rows x box_w] (re-used as the 96x96 mask image / RGB staging) | fov 128x128 | tables | mbar
+  const int S = P.fov;
+  const int crop = P.crop, pitch = P.box_w;
+  const int tile_bytes = P.tile_bytes;
+  uint8_t* s_tile = smem;
+  uint8_t* const s_region = smem;  // start of the tile region (16-byte aligned), re-used after the rotate
+  uint8_t* s_fov = smem + tile_bytes;
+  uint32_t* s_rg = (uint32_t*)(s_fov + S * S);
+  uint32_t* s_b = s_rg + 16;
+  uint32_t* s_key = s_b + 16;
+  int32_t* s_desc = (int32_t*)(s_key + 16);
+  uint64_t* s_bar = (uint64_t*)(s_desc + CBEV_DESC_WORDS);
+  uint8_t* s_cm = (uint8_t*)(s_bar + 2);  // channel bits per palette index for this mask mode
+
+  const int env = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
+  const int flags = d[RD_FLAGS];
+  if (flags & 2) return;  // masked-out env of a partial reset
+
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(s_bar, (uint32_t)(crop * pitch));
+    // the TMA unit needs a 16-byte aligned inner coordinate (measured on B200: an unaligned x raises
+    // "illegal instruction"), so fetch the aligned superset [ox & ~15, +box_w) and index it with +shift
+    tma_load_2d(s_tile, &tmap, d[RD_OX] & ~15, d[RD_OY], s_bar);
+  }
+  if (tid < CBEV_DESC_WORDS) s_desc[tid] = d[tid];
+  if (tid < CBEV_PAL_COUNT) {
+    s_rg[tid] = c_pal_rg[tid];
+    s_b[tid] = c_pal_b[tid];
+    s_key[tid] = c_pal_key[tid];
+  }
+  if (tid <= CBEV_PAL_COUNT) s_cm[tid] = c_chan_mask[mask_mode][tid];
+  __syncthreads();
+  mbar_wait(s_bar, 0);
+  s_tile += s_desc[RD_OX] & 15;  // crop pixel (x, y) lives at s_tile[y * pitch + x]
+
+  // ---- 2. draw list, in order (later rects overwrite earlier ones) ----
+  const int nrects = s_desc[RD_NRECTS];
+  if (tid < 32 && nrects > 0) {
+    const uint32_t* rl = P.rects + (size_t)env * P.max_rects;
+    for (int r = 0; r < nrects; ++r) {
+      uint32_t pk = rl[r];
+      int x0 = pk & 255, y0 = (pk >> 8) & 255, w = ((pk >> 16) & 63) + 1, h = ((pk >> 22) & 63) + 1;
+      uint8_t pal = (uint8_t)(pk >> 28);
+      for (int i = tid; i < w * h; i += 32) s_tile[(y0 + i / w) * pitch + x0 + i % w] = pal;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. rotate + compose + ego square -> 128x128 palette-index FOV ----
+  {
+    const int mode = s_desc[RD_MODE], turns = s_desc[RD_TURNS];
+    const int nx = s_desc[RD_NX], ny = s_desc[RD_NY];
+    const int isin = s_desc[RD_ISIN], icos = s_desc[RD_ICOS];
+    const int rax = s_desc[RD_AX] + s_desc[RD_XD], ray = s_desc[RD_AY] + s_desc[RD_YD], rcy = s_desc[RD_CY];
+    const int left = P.anchor_x - (nx >> 1), top = P.anchor_y - (ny >> 1);  // get_rect(center=anchor)
+    const int lim = (crop << 16) - 1;
+    const uint8_t bg = s_tile[0];  // transform.rotate background = source's first pixel
+    const int ex0 = P.anchor_x - 2, ey0 = P.anchor_y - 2;
+    for (int u = tid; u < S * S / 4; u += RT) {
+      const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+      const int ryp = oy - top;
+      const bool row_in = ryp >= 0 && ryp < ny;
+      const int bx = rax + isin * (rcy - ryp);
+      const int by = ray - icos * (rcy - ryp);
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ox = ox0 + k;
+        const int rxp = ox - left;
+        uint32_t v = CBEV_PAL_BLACK;
+        if (row_in && rxp >= 0 && rxp < nx) {
+          if (mode == 0) {
+            int sx, sy;
+            if (turns == 0) { sx = rxp; sy = ryp; }
+            else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
+            else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
+            else { sx = ryp; sy = crop - 1 - rxp; }
+            v = s_tile[sy * pitch + sx];
+          } else {
+            int dx = bx + rxp * icos, dy = by + rxp * isin;
+            if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
+            else v = s_tile[(dy >> 16) * pitch + (dx >> 16)];
+          }
+        }
+        if (ox >= ex0 && ox < ex0 + 4 && oy >= ey0 && oy < ey0 + 4) v = CBEV_PAL_BLACK;  // Hero.draw
+        packed |= v << (8 * k);
+      }
+      ((uint32_t*)s_fov)[u] = packed;
+    }
+  }
+  __syncthreads();
+  if (P.fov_out != nullptr) {
+    uint4* dst = (uint4*)(P.fov_out + (size_t)env * S * S);
+    for (int u = tid; u < S * S / 16; u += RT) dst[u] = ((const uint4*)s_fov)[u];
+  }
+
+  // which ring slots receive this frame: the head slot, or every window slot for a reset frame,
+  // each mirrored to slot - mirror when that lands in [0, F-2] (keeps the F-window contiguous)
+  const int F = P.frame_stack;
+  const int first = (flags & 1) ? P.head - F + 1 : P.head;
+
+  if (OBS_MODE == CBEV_OBS_RGB) {
+    // raw render(): (S, S, 3) uint8, staged through shared memory for 16-byte coalesced stores
+    uint8_t* s_rgb = s_region;
+    for (int p = tid; p < S * S; p += RT) {
+      uint32_t key = s_key[s_fov[p]];
+      s_rgb[3 * p + 0] = (uint8_t)key;
+      s_rgb[3 * p + 1] = (uint8_t)(key >> 8);
+      s_rgb[3 * p + 2] = (uint8_t)(key >> 16);
+    }
+    __syncthreads();
+    uint8_t* dst = (uint8_t*)P.ring + (size_t)env * P.ring_slots * P.frame_bytes + (size_t)P.head * P.frame_bytes;
+    for (int u = tid; u < S * S * 3 / 16; u += RT) st_u4(dst + 16 * u, ((const uint4*)s_rgb)[u]);
+    return;
+  }
+
+  // ---- 4. area resize 128 -> 96 + colour equality -> one byte per output pixel ----
+  constexpr int O = 96;
+  uint8_t* s_out = s_region;  // 96x96 bytes: channel bitmask (semantic) or gray level
+  const uint8_t* cm = s_cm;
+  for (int u = tid; u < O * (O / 12); u += RT) {
+    const int dy = u / (O / 12), j = u % (O / 12);
+    const int sy0 = (dy * 4) / 3, phy = dy % 3;
+    const uint32_t wy0 = 3 - phy, wy1 = 1 + phy;
+    const uint4 r0 = *(const uint4*)(s_fov + sy0 * S + 16 * j);
+    const uint4 r1 = *(const uint4*)(s_fov + (sy0 + 1) * S + 16 * j);
+    const uint32_t a[4] = {r0.x, r0.y, r0.z, r0.w}, b[4] = {r1.x, r1.y, r1.z, r1.w};
+    uint32_t outw[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int sx = (k * 4) / 3, ph = k % 3;
+      const uint32_t wx0 = 3 - ph, wx1 = 1 + ph;
+      const uint32_t c00 = (a[sx >> 2] >> (8 * (sx & 3))) & 255u, c01 = (a[(sx + 1) >> 2] >> (8 * ((sx + 1) & 3))) & 255u;
+      const uint32_t c10 = (b[sx >> 2] >> (8 * (sx & 3))) & 255u, c11 = (b[(sx + 1) >> 2] >> (8 * ((sx + 1) & 3))) & 255u;
+      uint32_t res;
+      if (OBS_MODE == CBEV_OBS_SEMANTIC) {
+        uint32_t cls;
+        if (c00 == c01 && c00 == c10 && c00 == c11) {
+          cls = c00;
+        } else {
+          uint32_t key = blend_rgb(c00, c01, c10, c11, wx0, wx1, wy0, wy1, s_rg, s_b);
+          cls = CBEV_PAL_COUNT;
+#pragma unroll
+          for (int q = 0; q < CBEV_PAL_TL_YELLOW; ++q) cls = (key == s_key[q]) ? q : cls;
+        }
+        res = cm[cls];
+      } else {
+        uint32_t key = (c00 == c01 && c00 == c10 && c00 == c11)
+                           ? s_key[c00]
+                           : blend_rgb(c00, c01, c10, c11, wx0, wx1, wy0, wy1, s_rg, s_b);
+        // GrayscaleObservation: sum(rgb * [0.2125, 0.7154, 0.0721]).astype(uint8), float64 left-to-right
+        double g = __dadd_rn(__dadd_rn(__dmul_rn((double)(key & 255u), 0.2125),
+                                       __dmul_rn((double)((key >> 8) & 255u), 0.7154)),
+                             __dmul_rn((double)(key >> 16), 0.0721));
+        res = (uint32_t)(int)g & 255u;
+      }
+      outw[k >> 2] |= res << (8 * (k & 3));
+    }
+    uint32_t* o = (uint32_t*)(s_out + dy * O + 12 * j);
+    o[0] = outw[0]; o[1] = outw[1]; o[2] = outw[2];
+  }
+  __syncthreads();
+
+  // ---- 5. expand + stream out ----
+  for (int slot = first; slot <= P.head; ++slot) {
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+      int sl = slot;
+      if (rep == 1) {
+        sl = slot - P.mirror;
+        if (P.mirror <= 0 || sl < 0) break;
+      }
+      uint8_t* base = (uint8_t*)P.ring + ((size_t)env * P.ring_slots + sl) * P.frame_bytes;
+      if (OBS_MODE == CBEV_OBS_SEMANTIC) {
+        float* fb = (float*)base;
+        for (int q = tid; q < O * O / 4; q += RT) {
+          const uint32_t m4 = ((const uint32_t*)s_out)[q];
+#pragma unroll
+          for (int c = 0; c < CHANNELS; ++c) {
+            const uint32_t t = (m4 >> c) & 0x01010101u;  // bit c of each of the 4 pixels; 1.0f = 0x3f800000
+            st_f4(fb + c * (O * O) + 4 * q, __uint_as_float((t & 1u) * 0x3f800000u),
+                  __uint_as_float(((t >> 8) & 1u) * 0x3f800000u), __uint_as_float(((t >> 16) & 1u) * 0x3f800000u),
+                  __uint_as_float((t >> 24) * 0x3f800000u));
+          }
+        }
+      } else {
+        for (int q = tid; q < O * O / 16; q += RT) st_u4(base + 16 * q, ((const uint4*)s_out)[q]);
+      }
+    }
+  }
+}
+
+bool g_tables_ready = false;
+
+void upload_tables() {
+  static const uint8_t pal[CBEV_PAL_COUNT][3] = {{150, 150, 150}, {255, 255, 255}, {220, 220, 220}, {0, 7, 175},
+                                                 {255, 0, 0},     {0, 255, 0},     {255, 64, 64},    {255, 255, 0},
+                                                 {0, 0, 0},       {100, 100, 100}};  // semantics.py:19-28
+  uint32_t rg[CBEV_PAL_COUNT], b[CBEV_PAL_COUNT], key[CBEV_PAL_COUNT];
+  for (int i = 0; i < CBEV_PAL_COUNT; ++i) {
+    rg[i] = pal[i][0] | ((uint32_t)pal[i][1] << 16);
+    b[i] = pal[i][2];
+    key[i] = pal[i][0] | ((uint32_t)pal[i][1] << 8) | ((uint32_t)pal[i][2] << 16);
+  }
+  // channel membership per mask mode (wrappers/rgb_to_semantic.py:6-42); "drivable" = white or green
+  uint8_t cm[6][CBEV_PAL_COUNT + 1] = {};
+  const int ND = CBEV_PAL_NON_DRIVABLE, DR = CBEV_PAL_DRIVABLE, SW = CBEV_PAL_SIDEWALK, VE = CBEV_PAL_VEHICLE,
+            PE = CBEV_PAL_PEDESTRIAN, RO = CBEV_PAL_ROUTE, TL = CBEV_PAL_TL_RED;
+  cm[CBEV_MASK_BINARY][DR] = 1; cm[CBEV_MASK_BINARY][RO] = 1;
+  cm[CBEV_MASK_2][DR] = 1; cm[CBEV_MASK_2][RO] = 1 | 2;
+  cm[CBEV_MASK_4][DR] = 1; cm[CBEV_MASK_4][VE] = 2; cm[CBEV_MASK_4][PE] = 4; cm[CBEV_MASK_4][RO] = 1 | 8;
+  cm[CBEV_MASK_5][DR] = 1; cm[CBEV_MASK_5][SW] = 2; cm[CBEV_MASK_5][VE] = 4; cm[CBEV_MASK_5][PE] = 8;
+  cm[CBEV_MASK_5][RO] = 1 | 16;
+  for (int m = CBEV_MASK_6; m <= CBEV_MASK_7; ++m) {
+    cm[m][ND] = 1; cm[m][DR] = 2; cm[m][SW] = 4; cm[m][VE] = 8; cm[m][PE] = 16; cm[m][RO] = 2 | 32;
+  }
+  cm[CBEV_MASK_7][TL] = 64;
+  cudaMemcpyToSymbol(c_pal_rg, rg, sizeof(rg));
+  cudaMemcpyToSymbol(c_pal_b, b, sizeof(b));
+  cudaMemcpyToSymbol(c_pal_key, key, sizeof(key));
+  cudaMemcpyToSymbol(c_chan_mask, cm, sizeof(cm));
+}
+
+template <int MODE, int CH>
+int launch(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
+  auto kern = k_render<MODE, CH>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return 1;
+    attr_done = true;
+  }
+  kern<<<P.N, RT, smem, s>>>(P, *reinterpret_cast<const CUtensorMap*>(e->tmap), e->cfg.mask_mode);
+  return 0;
+}
+
+}  // namespace
+
+int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, cudaStream_t s) {
+  if (!g_tables_ready) {
+    upload_tables();
+    g_tables_ready = true;
+  }
+  RenderParams P;
+  P.N = e->N;
+  P.fov = e->cfg.fov_size;
+  P.crop = e->crop;
+  P.box_w = e->box_w;
+  P.anchor_x = e->anchor_x;
+  P.anchor_y = e->anchor_y;
+  P.frame_stack = e->cfg.frame_stack;
+  P.ring_slots = e->cfg.ring_slots;
+  P.head = head;
+  P.mirror = mirror;
+  P.frame_bytes = e->frame_bytes;
+  P.desc = e->desc;
+  P.rects = e->rects;
+  P.max_rects = e->max_rects;
+  P.fov_out = e->fov;
+  P.ring = e->ring;
+  const int S = P.fov;
+  size_t tile = (size_t)P.crop * P.box_w;
+  if (e->cfg.obs_mode == CBEV_OBS_RGB && tile < (size_t)S * S * 3) tile = (size_t)S * S * 3;  // RGB staging
+  tile = ((tile + 127) / 128) * 128;
+  P.tile_bytes = (int32_t)tile;
+  P.pad0 = 0;
+  size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16;
+  int rc = 1;
+  if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, s);
+  else if (e->cfg.obs_mode == CBEV_OBS_GRAY) rc = launch<CBEV_OBS_GRAY, 1>(e, P, smem, s);
+  else {
+    switch (e->channels) {
+      case 1: rc = launch<CBEV_OBS_SEMANTIC, 1>(e, P, smem, s); break;
+      case 2: rc = launch<CBEV_OBS_SEMANTIC, 2>(e, P, smem, s); break;
+      case 4: rc = launch<CBEV_OBS_SEMANTIC, 4>(e, P, smem, s); break;
+      case 5: rc = launch<CBEV_OBS_SEMANTIC, 5>(e, P, smem, s); break;
+      case 6: rc = launch<CBEV_OBS_SEMANTIC, 6>(e, P, smem, s); break;
+      case 7: rc = launch<CBEV_OBS_SEMANTIC, 7>(e, P, smem, s); break;
+      default: rc = 1;
+    }
+  }
+  if (rc == 0) e->launches += 1;
+  return rc;
+}

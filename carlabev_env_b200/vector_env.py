@@ -1,0 +1,271 @@
+"""Drop-in vectorised CarlaBEV environment on top of the CUDA engine.
+
+Surface kept from the reference (`CarlaBEV.envs.make_env` -> gymnasium SyncVectorEnv of wrapped
+CarlaBEV envs; envs/__init__.py:40-120, envs/carlabev.py:36-258):
+
+    envs = make_env(cfg)                      # RunConfig | EnvConfig | legacy attribute bag
+    envs.num_envs, envs.single_observation_space, envs.single_action_space
+    obs, infos = envs.reset(seed=None, options={"scene": ..., "level": ..., "scene_seed": ...,
+                                                "reset_mask": bool[N]})
+    obs, rewards, terminations, truncations, infos = envs.step(actions)
+    envs.close()
+
+Differences that follow from the design:
+  * observations / rewards / flags are torch CUDA tensors (the step never leaves the GPU);
+    `to_numpy=True` returns NumPy copies with the reference's dtypes.
+  * scenes come from a host-generated, device-resident pool; `reset(options=...)` selects or
+    extends it.  `autoreset="next_step"` turns on device auto-reset from that pool.
+  * `infos` carries the reference's terminal keys (`episode_info`, `episode`) as dict-of-arrays
+    with `_key` masks, plus the per-step `hero` comfort signals the reference documents
+    (docs/control_and_actions.md:102) as a batched tensor.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import engine as E
+from . import scenes as S
+from .config import (ACTION_PROFILES, CARL_DEFAULTS, SHAPING_DEFAULTS, EnvConfig, RunConfig, get_action_profile_spec,
+                     get_difficulty_spec, get_reward_profile_spec, validate_run_config)
+from .pool import load_pool, pack_pool
+from .spaces import Box, Discrete
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_town01_map() -> np.ndarray:
+    """Class map of Town01 at size=128 (1280 x 1024; 0 non-drivable, 1 drivable, 2 sidewalk), derived
+    from the reference's Town01-128-sem.png by oracle/gen_golden.py:dump_map (envs/utils.py:49-62)."""
+    with np.load(os.path.join(HERE, "assets", "town01_128_cls.npz")) as z:
+        return np.ascontiguousarray(z["cls"], dtype=np.uint8)
+
+
+class CarlaBEVVectorEnv:
+    metadata = {"render_modes": ["rgb_array"], "render_fps": 60, "autoreset_mode": "Disabled"}
+
+    def __init__(self, cfg: RunConfig, *, scenes=None, autoreset: str = "disabled", device=None, ring_slots=None,
+                 ring_budget_bytes=None, to_numpy: bool = False, raw_rgb: bool = False, seed=None):
+        import torch
+
+        self.torch = torch
+        self.cfg = cfg
+        env = cfg.env
+        self.env_cfg = env
+        self.num_envs = int(cfg.num_envs)
+        self.to_numpy = to_numpy
+        self.autoreset = autoreset
+        if env.temporal_fusion_mode != "stack":
+            raise NotImplementedError("temporal_fusion_mode != 'stack' is a SURVEY.md §8(f1) 'next' row")
+        if env.fov_masked:
+            raise NotImplementedError("fov_masked is a SURVEY.md §8(f1) 'next' row")
+        aspec = get_action_profile_spec(env.action_profile_id)
+        rspec = get_reward_profile_spec(env.reward_profile_id)
+        if env.obs_mode == "bev_semantic":
+            obs_mode = E.OBS_SEMANTIC
+        elif raw_rgb:
+            obs_mode = E.OBS_RGB
+        else:
+            obs_mode = E.OBS_GRAY  # wrap_env: bev_rgb -> GrayscaleObservation (envs/__init__.py:70)
+        self._scenes = list(scenes) if scenes is not None else []
+        max_actors = max([len(s["act_kind"]) for s in self._scenes] + [env.max_vehicles + 2])
+        params = dict(rspec["parameters"])
+        if env.reward_mode == "shaping":
+            params.setdefault("max_actions", SHAPING_DEFAULTS["max_actions"])  # cfg.max_actions is never passed
+        self.engine = E.Engine(
+            self.num_envs, obs_mode=obs_mode, mask_mode=env.semantic_mask_ch, frame_stack=env.frame_stack,
+            ring_slots=ring_slots, ring_budget_bytes=ring_budget_bytes,
+            action_mode=E.ACTION_DISCRETE if env.action_mode == "discrete" else E.ACTION_CONTINUOUS,
+            discrete_table=aspec.get("discrete_actions"),
+            reward_mode=E.REWARD_CARL if env.reward_mode == "carl" else E.REWARD_SHAPING, reward_params=params,
+            autoreset=E.AUTORESET_NEXT_STEP if autoreset == "next_step" else E.AUTORESET_DISABLED,
+            anchor=(env.ego_anchor_x_frac, env.ego_anchor_y_frac), max_actors=max_actors,
+            seed=cfg.seed if seed is None else seed, device=device, size=env.size, obs_size=env.obs_size)
+        self.device = self.engine.device
+        self.cls_map = load_town01_map()
+        self.engine.upload_map(self.cls_map)
+        self.pad = self._crop_size(env)
+        if self._scenes:
+            self.engine.upload_pool(pack_pool(self._scenes))
+        # spaces (envs/spaces.py:27-61 + wrappers)
+        if env.action_mode == "discrete":
+            self.single_action_space = Discrete(len(aspec["discrete_actions"]))
+        else:
+            self.single_action_space = Box(np.asarray(aspec["low"], np.float32), np.asarray(aspec["high"], np.float32),
+                                           dtype=np.float32)
+        F = env.frame_stack
+        if obs_mode == E.OBS_SEMANTIC:
+            C = E.MASK_CHANNELS[env.semantic_mask_ch]
+            self.single_observation_space = Box(0.0, 1.0, (F * C, *env.obs_size), np.float32)
+        elif obs_mode == E.OBS_GRAY:
+            self.single_observation_space = Box(0, 255, (F, *env.obs_size), np.uint8)
+        else:
+            self.single_observation_space = Box(0, 255, (env.size, env.size, 3), np.uint8)
+        self.single_action_space.seed(cfg.seed)
+        self._ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        self._ep_len = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+        self._needs_reset = np.ones(self.num_envs, dtype=bool)
+        self._scene_of_env = np.zeros(self.num_envs, dtype=np.int64)
+        self.current_hero = None
+
+    @staticmethod
+    def _crop_size(env) -> int:
+        import math
+
+        m = env.size - 1
+        ax = max(0, min(m, int(round(m * env.ego_anchor_x_frac))))
+        ay = max(0, min(m, int(round(m * env.ego_anchor_y_frac))))
+        return max(env.size, int(math.ceil(2.0 * math.hypot(max(ax, m - ax), max(ay, m - ay)))))
+
+    # ---------------------------------------------------------------- pool
+    def set_scene_pool(self, scenes):
+        """Replace the device-resident pool (list of scene dicts, see pool.py)."""
+        self._scenes = list(scenes)
+        self.engine.upload_pool(pack_pool(self._scenes))
+
+    def _scenes_from_options(self, options, mask):
+        """Resolve reset options to pool indices, generating scripted scenes on the host if needed
+        (the reference builds the scene inside reset: carlabev.py:96-148)."""
+        n = self.num_envs
+        if "scene_ids" in options:
+            ids = np.broadcast_to(np.asarray(options["scene_ids"], dtype=np.int64), (n,)).copy()
+            if ids.min() < 0 or ids.max() >= len(self._scenes):
+                raise ValueError("scene_ids outside the scene pool")
+            return ids
+        scene = options.get("scene")
+        if scene is None or scene == "pool":
+            if not self._scenes:
+                raise RuntimeError("no scene pool: pass scenes=... / call set_scene_pool(), or reset with "
+                                   "options={'scene': 'lead_brake' | 'jaywalk', ...}")
+            base = int(options.get("scene_seed", self.env_cfg.seed))
+            return (base + np.arange(n)) % len(self._scenes)
+        if scene in ("lead_brake", "jaywalk"):
+            # SyncVectorEnv passes the same options to every env, so every masked env gets the
+            # same (scene, level, scene_seed) -- identical scene per env, like the reference.
+            seed = int(options.get("scene_seed", self.env_cfg.seed))
+            level = options.get("level")
+            key = (scene, level, seed)
+            cache = getattr(self, "_scripted_cache", {})
+            if key not in cache:
+                sc = S.build_scripted_scene(scene, seed, level=level, cls_map=self.cls_map, pad=self.pad,
+                                            max_reset_attempts=options.get("max_reset_attempts", 10))
+                self._scenes.append(sc)
+                cache[key] = len(self._scenes) - 1
+                self._scripted_cache = cache
+                self.engine.upload_pool(pack_pool(self._scenes))
+            return np.full(n, cache[key], dtype=np.int64)
+        if scene in ("rdm", "red_light_runner") or str(scene).endswith(".json"):
+            raise NotImplementedError(
+                f"scene={scene!r} needs the reference's lane graphs / authored files on the host; export a pool with "
+                "oracle/gen_golden.py:extract_scene and pass it via scenes=... (DESIGN.md, out of scope rows)")
+        raise KeyError(f"Unknown scenario '{scene}'")
+
+    # ---------------------------------------------------------------- gym surface
+    def reset(self, *, seed=None, options=None):
+        t = self.torch
+        options = {} if options is None else dict(options)
+        mask = options.pop("reset_mask", None)
+        if mask is not None:
+            mask = np.asarray(mask)
+            assert mask.dtype == np.bool_ and mask.shape == (self.num_envs,) and mask.any(), \
+                "reset_mask must be a bool array of shape (num_envs,) with at least one True"
+        if seed is not None and "scene_seed" not in options:
+            options["scene_seed"] = int(seed)  # CarlaBEV._resolve_rng_bundle, carlabev.py:83-94
+        ids = self._scenes_from_options(options, mask)
+        first = bool(self._needs_reset.all()) and self.engine.head < 0
+        if first and mask is not None and not mask.all():
+            raise RuntimeError("the first reset must cover every env")
+        m = None if (mask is None or mask.all()) else mask
+        obs = self.engine.reset(ids, m)
+        sel = slice(None) if m is None else t.as_tensor(m, device=self.device)
+        self._ep_return[sel] = 0.0
+        self._ep_len[sel] = 0
+        if m is None:
+            self._needs_reset[:] = False
+            self._scene_of_env[:] = ids
+        else:
+            self._needs_reset[m] = False
+            self._scene_of_env[m] = ids[m]
+        infos = {}
+        return self._out_obs(obs), infos
+
+    def step(self, actions):
+        t = self.torch
+        if self.autoreset == "disabled" and self._needs_reset.any():
+            # gymnasium SyncVectorEnv(AutoresetMode.DISABLED) asserts on this
+            raise AssertionError(f"step() on terminated envs {np.flatnonzero(self._needs_reset).tolist()}; "
+                                 "call reset(options={'reset_mask': ...}) first")
+        if self.env_cfg.action_mode == "discrete":
+            a = t.as_tensor(actions, device=self.device).to(t.int64).contiguous().view(self.num_envs)
+        else:
+            a = t.as_tensor(actions, device=self.device).to(t.float32).contiguous().view(self.num_envs, 3)
+        eng = self.engine
+        eng.step(a)
+        obs = eng.obs()
+        rew, term, trunc = eng.reward, eng.terminated.bool(), eng.truncated.bool()
+        self._ep_return += rew
+        self._ep_len += 1
+        self.current_hero = eng.hero
+        infos = {"hero": eng.hero, "cause": eng.cause}
+        done = term | trunc
+        done_host = done.cpu().numpy()  # one small D2H per step: the reference's terminal info is host data
+        if done_host.any():
+            infos.update(self._terminal_infos(done_host))
+            if self.autoreset == "disabled":
+                self._needs_reset |= done_host
+            d = t.as_tensor(done_host, device=self.device)
+            self._ep_return[d] = 0.0
+            self._ep_len[d] = 0
+        if self.to_numpy:
+            return (self._out_obs(obs), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy(), infos)
+        return obs, rew, term, trunc, infos
+
+    def _terminal_infos(self, done_host):
+        """episode_info (stats.py:127-148 + carlabev.py:177-185) and RecordEpisodeStatistics' `episode`."""
+        idx = np.flatnonzero(done_host)
+        ep = self.engine.episode[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
+        n = self.num_envs
+        info = {k: np.zeros(n, dtype=np.float64) for k in E.EPISODE_FIELDS if k not in ("cause",)}
+        term = np.full(n, None, dtype=object)
+        for j, i in enumerate(idx):
+            for k, name in enumerate(E.EPISODE_FIELDS):
+                if name == "cause":
+                    term[i] = E.CAUSE_NAMES[int(ep[j, k])]
+                else:
+                    info[name][i] = ep[j, k]
+        info["termination"] = term
+        info["length"] = info["length"].astype(np.int64)
+        mask = done_host.copy()
+        episode_info = {}
+        for k, v in info.items():
+            episode_info[k] = v
+            episode_info[f"_{k}"] = mask
+        r = np.zeros(n)
+        ln = np.zeros(n, dtype=np.int64)
+        r[idx] = self._ep_return[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
+        ln[idx] = self._ep_len[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
+        return {"episode_info": episode_info, "_episode_info": mask,
+                "episode": {"r": r, "_r": mask, "l": ln, "_l": mask}, "_episode": mask}
+
+    def _out_obs(self, obs):
+        return obs.cpu().numpy() if self.to_numpy else obs
+
+    def episode_statistics(self, reset=False):
+        """Device-accumulated episode statistics (CBEV_S_* of include/cbev.h) as a CUDA float64 tensor.
+        This vector is the only thing ranks exchange (carlabev_env_b200.distributed.allreduce_stats)."""
+        return self.engine.read_stats(reset)
+
+    def close(self):
+        self.engine.close()
+
+
+def make_env(cfg=None, eval: bool = False, **engine_kwargs) -> CarlaBEVVectorEnv:  # noqa: A002
+    """envs/__init__.py:108-120."""
+    if cfg is None:
+        cfg = RunConfig()
+    if not hasattr(cfg, "env") and not (isinstance(cfg, dict) and "env" in cfg):
+        cfg = validate_run_config({"env": cfg})
+    else:
+        cfg = validate_run_config(cfg)
+    return CarlaBEVVectorEnv(cfg, **engine_kwargs)
