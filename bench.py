@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the CarlaBEV batched stepping hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA engine (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port) on host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- 4096 envs per GPU, `lead_brake` scenes
+(levels 1..3 round-robin, scene_seed = i), continuous actions U([0,1]x[-1,1]x[0,1]) from a seeded
+generator, 6-class semantic-mask observations with a 4-frame stack, device auto-reset from the pool.
+A "step" is one pass of the hot path over all envs of the rank: sim kernel + raster/obs kernel.
+Multi-GPU (torchrun, one rank per GPU): envs shard independently, weak scaling, no data-path
+collective; the timed region is bracketed by a barrier + synchronize and the max over ranks is taken.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (obs+reward+done) at N envs, 1/2/4/8 B200; % HBM roofline"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 4096
+POOL_SCENES = 4096
+FRAME_BYTES = 6 * 96 * 96 * 4          # one new 6-class float32 frame
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ scene pool
+def _pool_worker(indices):
+    from carlabev_env_b200.scenes import build_scripted_scene
+    from carlabev_env_b200.vector_env import load_town01_map
+
+    cls = load_town01_map()
+    return [build_scripted_scene("lead_brake", i, level=1 + i % 3, cls_map=cls) for i in indices]
+
+
+def build_pool(n_scenes, cache=True):
+    """lead_brake pool: level = 1 + i % 3, scene_seed = i (host generator, carlabev_env_b200/scenes.py)."""
+    from carlabev_env_b200.pool import load_pool, save_pool
+    path = os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else ".",
+                        f".pool_lead_brake_{n_scenes}.npz")
+    if cache and os.path.exists(path):
+        try:
+            return load_pool(path)
+        except Exception:  # noqa: BLE001
+            pass
+    workers = min(os.cpu_count() or 1, 32)
+    if n_scenes >= 512 and workers > 1:
+        import multiprocessing as mp
+
+        chunks = [list(range(w, n_scenes, workers)) for w in range(workers)]
+        with mp.get_context("spawn").Pool(workers) as pool:
+            parts = pool.map(_pool_worker, chunks)
+        scenes = [None] * n_scenes
+        for idx, part in zip(chunks, parts):
+            for i, sc in zip(idx, part):
+                scenes[i] = sc
+    else:
+        scenes = _pool_worker(list(range(n_scenes)))
+    if cache:
+        try:
+            save_pool(path, scenes)
+        except Exception:  # noqa: BLE001
+            pass
+    return scenes
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
+                "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def _cpu_worker(args):
+    """Step `n_envs` oracle envs for `steps` steps each (masked reset from the pool on termination)."""
+    wid, n_envs, steps, seed = args
+    from carlabev_env_b200.scenes import build_scripted_scene
+    from carlabev_env_b200.vector_env import load_town01_map
+    from oracle.env import OracleEnv
+
+    cls = load_town01_map()
+    rng = np.random.default_rng(seed + wid)
+    scenes = [build_scripted_scene("lead_brake", wid * 64 + i, level=1 + i % 3, cls_map=cls) for i in range(8)]
+    envs = [OracleEnv(cls, obs_mode="bev_semantic", semantic_mask_ch="6-class", frame_stack=4,
+                      action_mode="continuous") for _ in range(n_envs)]
+    for i, e in enumerate(envs):
+        e.reset(scenes[i % len(scenes)])
+    t0 = time.perf_counter()
+    n = 0
+    k = 0
+    for _ in range(steps):
+        for e in envs:
+            a = np.array([rng.uniform(0, 1), rng.uniform(-1, 1), rng.uniform(0, 1)], dtype=np.float32)
+            _, _, term, trunc, _ = e.step(a)
+            n += 1
+            if term or trunc:
+                k += 1
+                e.reset(scenes[(k + wid) % len(scenes)])
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(steps_per_env=150, envs_per_worker=1, max_workers=None):
+    """Reference CPU path (oracle port of the reference's step) on all host cores."""
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    workers = min(cores, max_workers or 64)
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, [(w, envs_per_worker, steps_per_env, 1234) for w in range(workers)])
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return {"value": total / slowest, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": f"{workers} worker processes x {envs_per_worker} env x {steps_per_env} steps of the same lead_brake "
+                      f"workload through oracle/ (NumPy port of the reference step incl. render/resize/masks/stack); "
+                      f"throughput = steps / slowest worker's stepping time ({slowest:.1f}s; wall incl. spawn {wall:.1f}s); "
+                      f"host has {cores} cores"}
+
+
+# ------------------------------------------------------------------------------------ arms
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps_per_env = max(20, min(400, args.steps * 4))
+    cb = cpu_baseline(steps_per_env=steps_per_env)
+    n_env = cb["cores"]
+    line = {
+        "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * n_env / cb["value"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "configs[1] bounded sample: lead_brake, continuous actions, 6-class semantic F=4; "
+                               f"{n_env} CPU envs (one per worker process)", "envs": n_env},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import pack_pool
+    from carlabev_env_b200.vector_env import load_town01_map
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    N = args.envs
+    scenes = build_pool(args.pool)
+    a_mean = float(np.mean([len(s["act_kind"]) for s in scenes]))
+    eng = E.Engine(N, obs_mode=E.OBS_SEMANTIC, mask_mode="6-class", frame_stack=4, action_mode=E.ACTION_CONTINUOUS,
+                   reward_mode=E.REWARD_CARL, autoreset=E.AUTORESET_NEXT_STEP, max_actors=4, seed=rank, device=local,
+                   ring_slots=args.ring_slots)
+    eng.upload_map(load_town01_map())
+    eng.upload_pool(pack_pool(scenes))
+    ids = (torch.arange(N, dtype=torch.int32) + rank * N) % len(scenes)
+    eng.reset(ids)
+    gen = torch.Generator(device="cpu").manual_seed(0 + rank)
+    bank = 16
+    lo = torch.tensor([0.0, -1.0, 0.0])
+    hi = torch.tensor([1.0, 1.0, 1.0])
+    acts_host = [(lo + (hi - lo) * torch.rand(N, 3, generator=gen)).float().pin_memory() for _ in range(bank)]
+    acts_dev = [a.to(dev) for a in acts_host]
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") ----
+    for i in range(args.warmup):
+        eng.step(acts_dev[i % bank])
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    eng.profile(True)
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        eng.step(acts_dev[i % bank])
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - l0
+    sim_ms, render_ms, prof_steps = eng.profile_read()
+    eng.profile(False)
+    clock_info = clocks.stop() if clocks else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * N * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers (H2D actions, D2H reward/flags every step) ----
+    rew_h = torch.zeros(N, dtype=torch.float64).pin_memory()
+    term_h = torch.zeros(N, dtype=torch.uint8).pin_memory()
+    trunc_h = torch.zeros(N, dtype=torch.uint8).pin_memory()
+    e2e_steps = args.steps
+    for i in range(min(3, args.warmup)):
+        eng.step_host(acts_host[i % bank], rew_h, term_h, trunc_h)
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    chk = 0.0
+    for i in range(e2e_steps):
+        eng.step_host(acts_host[i % bank], rew_h, term_h, trunc_h)
+        stream.synchronize()  # the host consumes reward / done before it can act again
+        chk += float(rew_h[0])
+    ev3.record(stream)
+    barrier()
+    t2 = torch.tensor([ev2.elapsed_time(ev3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / (float(t2.item()) * 1e-3)
+
+    # ---- episode statistics: the only collective (all-reduce of a 21-double vector over NCCL) ----
+    from carlabev_env_b200.distributed import allreduce_stats, summarize_stats
+
+    stats = summarize_stats(allreduce_stats(eng.read_stats().clone()))
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        render_avg_ms = render_ms / max(prof_steps, 1)
+        sim_avg_ms = sim_ms / max(prof_steps, 1)
+        alg_bytes = N * FRAME_BYTES
+        achieved = alg_bytes / (render_avg_ms * 1e-3) / 1e9 if render_avg_ms > 0 else 0.0
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(steps_per_env=args.cpu_steps)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "render_traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"configs[1]: {N} envs/GPU lead_brake (levels 1-3, pool of {len(scenes)} seeded scenes), "
+                            "continuous actions, 6-class semantic masks 96x96 float32, frame_stack 4, CaRL reward, "
+                            "device auto-reset (next-step) from the pool",
+                "envs_per_gpu": N, "envs_total": world * N, "ring_slots": eng.L,
+                "l2": f"each step writes {alg_bytes / 1e6:.0f} MB of observations per GPU (> 126 MB L2), no flush needed",
+                "mean_actors_per_scene": a_mean,
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "kernel": "k_render",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": render_avg_ms, "sim_kernel_ms": sim_avg_ms, "profiled_steps": prof_steps,
+                         "step_fraction_render": render_avg_ms / (ms / args.steps) if ms else None},
+            "cpu_baseline": cb,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 12, "d2h_bytes_per_step": N * 10,
+                    "note": "cbev_step_host: pinned host actions in, reward/terminated/truncated out, stream sync "
+                            "every step; observations stay device resident (ring view)"},
+            "gpu_launches": int(launches),
+            "clocks": clock_info,
+            "episode_stats": stats,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--pool", type=int, default=POOL_SCENES)
+    ap.add_argument("--ring-slots", type=int, default=None)
+    ap.add_argument("--cpu-steps", type=int, default=150)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -220,6 +220,10 @@ int cbev_destroy(cbev_handle e) {
   dev_free(e->h_reward_dev); dev_free(e->h_term_dev); dev_free(e->h_trunc_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }
   dev_free(e->all_scene_ids);
+  if (e->prof_ev) {
+    for (int i = 0; i < 3 * CBEV_PROF_MAX; ++i) cudaEventDestroy(e->prof_ev[i]);
+    delete[] e->prof_ev;
+  }
   delete e;
   return CBEV_OK;
 }
@@ -382,9 +386,13 @@ int cbev_step(cbev_handle e, const void* actions_dev, const cbev_step_out* out, 
   const int F = e->cfg.frame_stack, L = e->cfg.ring_slots;
   int head = e->head + 1;
   if (head >= L) head = F - 1;
+  const bool prof = e->profiling && e->prof_n < CBEV_PROF_MAX;
+  if (prof) cudaEventRecord(e->prof_ev[3 * e->prof_n + 0], s);
   cbev_launch_sim(e, actions_dev, out, s);
+  if (prof) cudaEventRecord(e->prof_ev[3 * e->prof_n + 1], s);
   if ((rc = debug_sync("k_sim", s))) return rc;
   if (cbev_launch_render(e, head, F > 1 ? L - F + 1 : 0, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
+  if (prof) { cudaEventRecord(e->prof_ev[3 * e->prof_n + 2], s); e->prof_n += 1; }
   if ((rc = debug_sync("k_render", s))) return rc;
   CU_TRY(cudaGetLastError());
   e->head = head;
@@ -503,5 +511,42 @@ int cbev_read_stats(cbev_handle e, double* stats_dev, int32_t reset_after, void*
 }
 
 int64_t cbev_launch_count(cbev_handle e) { return e ? e->launches : -1; }
+
+int cbev_profile_enable(cbev_handle e, int32_t on) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  if (on && !e->prof_ev) {
+    e->prof_ev = new (std::nothrow) cudaEvent_t[3 * CBEV_PROF_MAX];
+    if (!e->prof_ev) return CBEV_ERR_NOMEM;
+    for (int i = 0; i < 3 * CBEV_PROF_MAX; ++i) CU_TRY(cudaEventCreate(&e->prof_ev[i]));
+  }
+  e->profiling = on != 0;
+  e->prof_n = 0;
+  return CBEV_OK;
+}
+
+int cbev_profile_read(cbev_handle e, double* sim_ms, double* render_ms, int64_t* steps) {
+  if (!e || !sim_ms || !render_ms || !steps) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  double a = 0.0, b = 0.0;
+  if (e->prof_n > 0) CU_TRY(cudaEventSynchronize(e->prof_ev[3 * (e->prof_n - 1) + 2]));
+  for (int i = 0; i < e->prof_n; ++i) {
+    float t0 = 0.f, t1 = 0.f;
+    CU_TRY(cudaEventElapsedTime(&t0, e->prof_ev[3 * i + 0], e->prof_ev[3 * i + 1]));
+    CU_TRY(cudaEventElapsedTime(&t1, e->prof_ev[3 * i + 1], e->prof_ev[3 * i + 2]));
+    a += t0;
+    b += t1;
+  }
+  *sim_ms = a;
+  *render_ms = b;
+  *steps = e->prof_n;
+  e->prof_n = 0;
+  return CBEV_OK;
+}
+
+int cbev_abi_sizes(int32_t* config_bytes, int32_t* pool_desc_bytes, int32_t* step_out_bytes) {
+  if (config_bytes) *config_bytes = (int32_t)sizeof(cbev_config);
+  if (pool_desc_bytes) *pool_desc_bytes = (int32_t)sizeof(cbev_pool_desc);
+  if (step_out_bytes) *step_out_bytes = (int32_t)sizeof(cbev_step_out);
+  return CBEV_OK;
+}
 
 }  // extern "C"

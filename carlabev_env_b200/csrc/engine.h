@@ -14,6 +14,7 @@
 #define CBEV_MAX_TARGETS 64   // ego route points (targets) per scene, one visibility bit each
 #define CBEV_DESC_WORDS 16    // ints per render-descriptor header
 #define CBEV_WARPS_PER_BLOCK 4
+#define CBEV_PROF_MAX 2048
 
 // render descriptor header words
 enum {
@@ -100,6 +101,10 @@ struct cbev_engine {
   int32_t* all_scene_ids = nullptr;
   int64_t launches = 0;
   int64_t steps = 0;
+  // per-kernel profiling (cbev_profile_enable)
+  bool profiling = false;
+  cudaEvent_t* prof_ev = nullptr;  // [CBEV_PROF_MAX][3]
+  int32_t prof_n = 0;
 };
 
 // kernels (sim.cu / render.cu)

@@ -37,7 +37,7 @@ SG_MAX = 12
 EXPORTS = ("cbev_version", "cbev_last_error", "cbev_create", "cbev_destroy", "cbev_upload_map",
            "cbev_upload_scene_pool", "cbev_frame_bytes", "cbev_bind_obs_ring", "cbev_reset", "cbev_step",
            "cbev_step_host", "cbev_obs_head", "cbev_get_state", "cbev_set_ego_state", "cbev_copy_fov",
-           "cbev_read_stats", "cbev_launch_count")
+           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes")
 
 
 class CbevConfig(C.Structure):
@@ -115,6 +115,14 @@ def load_library(build_if_missing: bool = True):
     lib.cbev_set_ego_state.argtypes = [_P, _P]
     lib.cbev_copy_fov.argtypes = [_P, _P, _P]
     lib.cbev_read_stats.argtypes = [_P, _P, C.c_int32, _P]
+    lib.cbev_profile_enable.argtypes = [_P, C.c_int32]
+    lib.cbev_profile_read.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.cbev_abi_sizes.argtypes = [C.POINTER(C.c_int32)] * 3
+    sizes = [C.c_int32(), C.c_int32(), C.c_int32()]
+    lib.cbev_abi_sizes(*[C.byref(v) for v in sizes])
+    expect = (C.sizeof(CbevConfig), C.sizeof(CbevPoolDesc), C.sizeof(CbevStepOut))
+    if tuple(v.value for v in sizes) != expect:
+        raise CbevError(f"ABI mismatch between include/cbev.h and engine.py: {[v.value for v in sizes]} vs {expect}")
     _lib = lib
     return lib
 
@@ -338,6 +346,15 @@ class Engine:
     def read_stats(self, reset=False):
         _check(self.lib, self.lib.cbev_read_stats(self.handle, self.stats_buf.data_ptr(), int(reset), self._stream()))
         return self.stats_buf
+
+    def profile(self, on: bool):
+        _check(self.lib, self.lib.cbev_profile_enable(self.handle, int(on)))
+
+    def profile_read(self):
+        """(sim_ms, render_ms, steps) summed over the profiled steps since the last read."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _check(self.lib, self.lib.cbev_profile_read(self.handle, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     @property
     def launches(self) -> int:

@@ -251,6 +251,15 @@ int cbev_read_stats(cbev_handle h, double* stats_dev, int32_t reset_after, void*
 /* Number of kernel launches issued by the engine so far. */
 int64_t cbev_launch_count(cbev_handle h);
 
+/* Per-kernel device timing: when enabled, cbev_step records CUDA events on `stream` before the sim
+ * kernel, between the two kernels and after the raster kernel (up to 2048 steps are kept).
+ * cbev_profile_read synchronises and returns the summed durations in milliseconds. */
+int cbev_profile_enable(cbev_handle h, int32_t on);
+int cbev_profile_read(cbev_handle h, double* sim_ms, double* render_ms, int64_t* steps);
+
+/* ABI self-check: sizeof(cbev_config), sizeof(cbev_pool_desc), sizeof(cbev_step_out). */
+int cbev_abi_sizes(int32_t* config_bytes, int32_t* pool_desc_bytes, int32_t* step_out_bytes);
+
 #ifdef __cplusplus
 }
 #endif
