@@ -489,8 +489,15 @@ int cbev_set_ego_state(cbev_handle e, const double* ego_host) {
   return CBEV_OK;
 }
 
+int cbev_keep_fov(cbev_handle e, int32_t on) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  e->keep_fov = on != 0;
+  return CBEV_OK;
+}
+
 int cbev_copy_fov(cbev_handle e, uint8_t* fov_dev, void* stream) {
   if (!e || !fov_dev) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  if (!e->keep_fov) { cbev_set_error("palette frames are not kept: call cbev_keep_fov(h, 1) before stepping"); return CBEV_ERR_STATE; }
   size_t bytes = (size_t)e->N * e->cfg.fov_size * e->cfg.fov_size;
   CU_TRY(cudaMemcpyAsync(fov_dev, e->fov, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CBEV_OK;

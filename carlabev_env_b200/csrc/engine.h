@@ -82,7 +82,7 @@ struct cbev_engine {
   int32_t map_w = 0, map_h = 0;
   uint8_t* map = nullptr;
   alignas(64) unsigned char tmap[128];  // CUtensorMap of the class map
-  bool has_map = false, has_pool = false, was_reset = false;
+  bool has_map = false, has_pool = false, was_reset = false, keep_fov = false;
   PoolDev pool;
   EnvState st;
   int32_t max_rects = 0;

@@ -97,12 +97,37 @@ __device__ __forceinline__ uint32_t blend_rgb(uint32_t c00, uint32_t c01, uint32
   return R | (G << 8) | (B << 16);
 }
 
+// one output byte of the 96x96 image from its 2x2 taps: channel bitmask (semantic) or gray level
+template <int OBS_MODE>
+__device__ __forceinline__ uint32_t resolve_px(uint32_t c00, uint32_t c01, uint32_t c10, uint32_t c11, uint32_t wx0,
+                                               uint32_t wx1, uint32_t wy0, uint32_t wy1, const uint32_t* s_rg,
+                                               const uint32_t* s_b, const uint32_t* s_key, const uint8_t* s_cm) {
+  const bool same = c00 == c01 && c00 == c10 && c00 == c11;
+  if (OBS_MODE == CBEV_OBS_SEMANTIC) {
+    uint32_t cls = c00;
+    if (!same) {
+      const uint32_t key = blend_rgb(c00, c01, c10, c11, wx0, wx1, wy0, wy1, s_rg, s_b);
+      cls = CBEV_PAL_COUNT;
+#pragma unroll
+      for (int q = 0; q < CBEV_PAL_TL_YELLOW; ++q) cls = (key == s_key[q]) ? q : cls;
+    }
+    return s_cm[cls];
+  }
+  const uint32_t key = same ? s_key[c00] : blend_rgb(c00, c01, c10, c11, wx0, wx1, wy0, wy1, s_rg, s_b);
+  // GrayscaleObservation: sum(rgb * [0.2125, 0.7154, 0.0721]).astype(uint8), float64 left-to-right
+  const double g = __dadd_rn(__dadd_rn(__dmul_rn((double)(key & 255u), 0.2125),
+                                       __dmul_rn((double)((key >> 8) & 255u), 0.7154)),
+                             __dmul_rn((double)(key >> 16), 0.0721));
+  return (uint32_t)(int)g & 255u;
+}
+
 template <int OBS_MODE, int CHANNELS>
 __global__ void __launch_bounds__(RT, 3)
 k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [tile: crop rows x box_w] (re-used as the 96x96 mask image / RGB staging) | fov 128x128 | tables | mbar
-  const int S = P.fov;
+  // layout: [tile: crop rows x box_w | re-used as: 96x96 output bytes + mixed-block worklist / RGB staging]
+  //         [fov 128x128] [tables] [mbar]
+  constexpr int S = 128;
   const int crop = P.crop, pitch = P.box_w;
   const int tile_bytes = P.tile_bytes;
   uint8_t* s_tile = smem;
@@ -113,7 +138,9 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   uint32_t* s_key = s_b + 16;
   int32_t* s_desc = (int32_t*)(s_key + 16);
   uint64_t* s_bar = (uint64_t*)(s_desc + CBEV_DESC_WORDS);
-  uint8_t* s_cm = (uint8_t*)(s_bar + 2);  // channel bits per palette index for this mask mode
+  uint8_t* s_cm = (uint8_t*)(s_bar + 2);     // channel bits per palette index for this mask mode
+  float4* s_lut = (float4*)(s_cm + 16);      // 16 x float4: 4 mask bits -> four 0.0f / 1.0f values
+  int* s_count = (int*)(s_lut + 16);
 
   const int env = blockIdx.x;
   const int tid = threadIdx.x;
@@ -124,11 +151,11 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(s_bar, (uint32_t)(crop * pitch));
     // the TMA unit needs a 16-byte aligned inner coordinate (measured on B200: an unaligned x raises
     // "illegal instruction"), so fetch the aligned superset [ox & ~15, +box_w) and index it with +shift
     tma_load_2d(s_tile, &tmap, d[RD_OX] & ~15, d[RD_OY], s_bar);
+    *s_count = 0;
   }
   if (tid < CBEV_DESC_WORDS) s_desc[tid] = d[tid];
   if (tid < CBEV_PAL_COUNT) {
@@ -137,23 +164,28 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     s_key[tid] = c_pal_key[tid];
   }
   if (tid <= CBEV_PAL_COUNT) s_cm[tid] = c_chan_mask[mask_mode][tid];
+  if (tid < 16)
+    s_lut[tid] = make_float4((tid & 1) ? 1.0f : 0.0f, (tid & 2) ? 1.0f : 0.0f, (tid & 4) ? 1.0f : 0.0f,
+                             (tid & 8) ? 1.0f : 0.0f);
   __syncthreads();
   mbar_wait(s_bar, 0);
   s_tile += s_desc[RD_OX] & 15;  // crop pixel (x, y) lives at s_tile[y * pitch + x]
 
   // ---- 2. draw list, in order (later rects overwrite earlier ones) ----
   const int nrects = s_desc[RD_NRECTS];
-  if (tid < 32 && nrects > 0) {
-    const uint32_t* rl = P.rects + (size_t)env * P.max_rects;
-    for (int r = 0; r < nrects; ++r) {
-      uint32_t pk = rl[r];
-      int x0 = pk & 255, y0 = (pk >> 8) & 255, w = ((pk >> 16) & 63) + 1, h = ((pk >> 22) & 63) + 1;
-      uint8_t pal = (uint8_t)(pk >> 28);
-      for (int i = tid; i < w * h; i += 32) s_tile[(y0 + i / w) * pitch + x0 + i % w] = pal;
-      __syncwarp();
+  if (nrects > 0) {
+    if (tid < 32) {
+      const uint32_t* rl = P.rects + (size_t)env * P.max_rects;
+      for (int r = 0; r < nrects; ++r) {
+        uint32_t pk = rl[r];
+        int x0 = pk & 255, y0 = (pk >> 8) & 255, w = ((pk >> 16) & 63) + 1, h = ((pk >> 22) & 63) + 1;
+        uint8_t pal = (uint8_t)(pk >> 28);
+        for (int i = tid; i < w * h; i += 32) s_tile[(y0 + i / w) * pitch + x0 + i % w] = pal;
+        __syncwarp();
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- 3. rotate + compose + ego square -> 128x128 palette-index FOV ----
   {
@@ -165,36 +197,83 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     const int lim = (crop << 16) - 1;
     const uint8_t bg = s_tile[0];  // transform.rotate background = source's first pixel
     const int ex0 = P.anchor_x - 2, ey0 = P.anchor_y - 2;
-    for (int u = tid; u < S * S / 4; u += RT) {
-      const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
-      const int ryp = oy - top;
-      const bool row_in = ryp >= 0 && ryp < ny;
-      const int bx = rax + isin * (rcy - ryp);
-      const int by = ray - icos * (rcy - ryp);
-      uint32_t packed = 0;
+    // The crop is sized so that the 128x128 window normally lies inside the rotated surface and inside the
+    // source range of the fixed-point walk.  Both facts are linear in (x, y): checking the four window corners
+    // proves them for every pixel, which removes all per-pixel range tests (the generic loop remains for the rest).
+    bool fast = left <= 0 && top <= 0 && left + nx >= S && top + ny >= S;
+    if (mode == 1 && fast) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ox = ox0 + k;
-        const int rxp = ox - left;
-        uint32_t v = CBEV_PAL_BLACK;
-        if (row_in && rxp >= 0 && rxp < nx) {
-          if (mode == 0) {
-            int sx, sy;
-            if (turns == 0) { sx = rxp; sy = ryp; }
-            else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
-            else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
-            else { sx = ryp; sy = crop - 1 - rxp; }
-            v = s_tile[sy * pitch + sx];
-          } else {
-            int dx = bx + rxp * icos, dy = by + rxp * isin;
-            if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
-            else v = s_tile[(dy >> 16) * pitch + (dx >> 16)];
-          }
-        }
-        if (ox >= ex0 && ox < ex0 + 4 && oy >= ey0 && oy < ey0 + 4) v = CBEV_PAL_BLACK;  // Hero.draw
-        packed |= v << (8 * k);
+      for (int c = 0; c < 4; ++c) {
+        const int rxp = ((c & 1) ? S - 1 : 0) - left, ryp = ((c & 2) ? S - 1 : 0) - top;
+        const int dx = rax + isin * (rcy - ryp) + rxp * icos, dy = ray - icos * (rcy - ryp) + rxp * isin;
+        fast = fast && dx >= 0 && dy >= 0 && dx <= lim && dy <= lim;
       }
-      ((uint32_t*)s_fov)[u] = packed;
+    }
+    if (fast && mode == 1) {
+      for (int u = tid; u < S * S / 4; u += RT) {
+        const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+        const int ryp = oy - top, rxp = ox0 - left;
+        int dx = rax + isin * (rcy - ryp) + rxp * icos;
+        int dy = ray - icos * (rcy - ryp) + rxp * isin;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          packed |= (uint32_t)s_tile[(dy >> 16) * pitch + (dx >> 16)] << (8 * k);
+          dx += icos;
+          dy += isin;
+        }
+        ((uint32_t*)s_fov)[u] = packed;
+      }
+    } else if (fast) {
+      // exact 90-degree turns (rotate90): src = base + x * step_x + y * step_y
+      int base, stepx, stepy;
+      if (turns == 0) { base = 0; stepx = 1; stepy = pitch; }
+      else if (turns == 1) { base = crop - 1; stepx = pitch; stepy = -1; }
+      else if (turns == 2) { base = (crop - 1) * pitch + crop - 1; stepx = -1; stepy = -pitch; }
+      else { base = (crop - 1) * pitch; stepx = -pitch; stepy = 1; }
+      base += -left * stepx - top * stepy;
+      for (int u = tid; u < S * S / 4; u += RT) {
+        const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+        const int a = base + ox0 * stepx + oy * stepy;
+        ((uint32_t*)s_fov)[u] = (uint32_t)s_tile[a] | ((uint32_t)s_tile[a + stepx] << 8) |
+                                ((uint32_t)s_tile[a + 2 * stepx] << 16) | ((uint32_t)s_tile[a + 3 * stepx] << 24);
+      }
+    } else {
+      for (int u = tid; u < S * S / 4; u += RT) {
+        const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+        const int ryp = oy - top;
+        const bool row_in = ryp >= 0 && ryp < ny;
+        const int bx = rax + isin * (rcy - ryp);
+        const int by = ray - icos * (rcy - ryp);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rxp = ox0 + k - left;
+          uint32_t v = CBEV_PAL_BLACK;
+          if (row_in && rxp >= 0 && rxp < nx) {
+            if (mode == 0) {
+              int sx, sy;
+              if (turns == 0) { sx = rxp; sy = ryp; }
+              else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
+              else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
+              else { sx = ryp; sy = crop - 1 - rxp; }
+              v = s_tile[sy * pitch + sx];
+            } else {
+              int dx = bx + rxp * icos, dy = by + rxp * isin;
+              if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
+              else v = s_tile[(dy >> 16) * pitch + (dx >> 16)];
+            }
+          }
+          packed |= v << (8 * k);
+        }
+        ((uint32_t*)s_fov)[u] = packed;
+      }
+    }
+    __syncthreads();
+    // Hero.draw: 4x4 black square centred on the anchor (hero.py:26-32), clipped to the surface
+    if (tid < 16) {
+      const int x = ex0 + (tid & 3), y = ey0 + (tid >> 2);
+      if (x >= 0 && x < S && y >= 0 && y < S) s_fov[y * S + x] = CBEV_PAL_BLACK;
     }
   }
   __syncthreads();
@@ -224,49 +303,61 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   }
 
   // ---- 4. area resize 128 -> 96 + colour equality -> one byte per output pixel ----
+  // Every 4x4 source block maps to a 3x3 output block (period of the 4/3 scale on both axes).
+  // Pass A: a block whose 16 texels are equal resolves to one table lookup for all 9 outputs; the other
+  // blocks go to a worklist.  Pass B: the worklist is processed one output pixel per thread (no divergence).
   constexpr int O = 96;
-  uint8_t* s_out = s_region;  // 96x96 bytes: channel bitmask (semantic) or gray level
-  const uint8_t* cm = s_cm;
-  for (int u = tid; u < O * (O / 12); u += RT) {
-    const int dy = u / (O / 12), j = u % (O / 12);
-    const int sy0 = (dy * 4) / 3, phy = dy % 3;
-    const uint32_t wy0 = 3 - phy, wy1 = 1 + phy;
-    const uint4 r0 = *(const uint4*)(s_fov + sy0 * S + 16 * j);
-    const uint4 r1 = *(const uint4*)(s_fov + (sy0 + 1) * S + 16 * j);
-    const uint32_t a[4] = {r0.x, r0.y, r0.z, r0.w}, b[4] = {r1.x, r1.y, r1.z, r1.w};
-    uint32_t outw[3] = {0, 0, 0};
+  uint8_t* s_out = s_region;                        // 96x96 bytes: channel bitmask (semantic) or gray level
+  uint16_t* s_list = (uint16_t*)(s_region + O * O);  // up to 32*32 mixed blocks
+  {
+    const int br = tid >> 3, j = tid & 7;  // 32 block rows x 8 strips of 4 blocks (RT == 256)
+    uint4 R[4];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const int sx = (k * 4) / 3, ph = k % 3;
-      const uint32_t wx0 = 3 - ph, wx1 = 1 + ph;
-      const uint32_t c00 = (a[sx >> 2] >> (8 * (sx & 3))) & 255u, c01 = (a[(sx + 1) >> 2] >> (8 * ((sx + 1) & 3))) & 255u;
-      const uint32_t c10 = (b[sx >> 2] >> (8 * (sx & 3))) & 255u, c11 = (b[(sx + 1) >> 2] >> (8 * ((sx + 1) & 3))) & 255u;
-      uint32_t res;
-      if (OBS_MODE == CBEV_OBS_SEMANTIC) {
-        uint32_t cls;
-        if (c00 == c01 && c00 == c10 && c00 == c11) {
-          cls = c00;
-        } else {
-          uint32_t key = blend_rgb(c00, c01, c10, c11, wx0, wx1, wy0, wy1, s_rg, s_b);
-          cls = CBEV_PAL_COUNT;
+    for (int i = 0; i < 4; ++i) R[i] = *(const uint4*)(s_fov + (4 * br + i) * S + 16 * j);
+    uint32_t m[4];
+    uint32_t mixed = 0;
 #pragma unroll
-          for (int q = 0; q < CBEV_PAL_TL_YELLOW; ++q) cls = (key == s_key[q]) ? q : cls;
-        }
-        res = cm[cls];
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t w0 = (&R[0].x)[b], w1 = (&R[1].x)[b], w2 = (&R[2].x)[b], w3 = (&R[3].x)[b];
+      const uint32_t c = w0 & 255u;
+      const bool uni = w0 == w1 && w0 == w2 && w0 == w3 && w0 == c * 0x01010101u;
+      m[b] = 0;
+      if (uni) {
+        if (OBS_MODE == CBEV_OBS_SEMANTIC) m[b] = s_cm[c];
+        else m[b] = resolve_px<OBS_MODE>(c, c, c, c, 2, 2, 2, 2, s_rg, s_b, s_key, s_cm);
       } else {
-        uint32_t key = (c00 == c01 && c00 == c10 && c00 == c11)
-                           ? s_key[c00]
-                           : blend_rgb(c00, c01, c10, c11, wx0, wx1, wy0, wy1, s_rg, s_b);
-        // GrayscaleObservation: sum(rgb * [0.2125, 0.7154, 0.0721]).astype(uint8), float64 left-to-right
-        double g = __dadd_rn(__dadd_rn(__dmul_rn((double)(key & 255u), 0.2125),
-                                       __dmul_rn((double)((key >> 8) & 255u), 0.7154)),
-                             __dmul_rn((double)(key >> 16), 0.0721));
-        res = (uint32_t)(int)g & 255u;
+        mixed |= 1u << b;
       }
-      outw[k >> 2] |= res << (8 * (k & 3));
     }
-    uint32_t* o = (uint32_t*)(s_out + dy * O + 12 * j);
-    o[0] = outw[0]; o[1] = outw[1]; o[2] = outw[2];
+    // 12 output bytes per row: m0 m0 m0 m1 | m1 m1 m2 m2 | m2 m3 m3 m3 (same for the 3 rows of the block row)
+    const uint32_t o0 = m[0] | (m[0] << 8) | (m[0] << 16) | (m[1] << 24);
+    const uint32_t o1 = m[1] | (m[1] << 8) | (m[2] << 16) | (m[2] << 24);
+    const uint32_t o2 = m[2] | (m[3] << 8) | (m[3] << 16) | (m[3] << 24);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      uint32_t* o = (uint32_t*)(s_out + (3 * br + i) * O + 12 * j);
+      o[0] = o0; o[1] = o1; o[2] = o2;
+    }
+    if (mixed) {
+      const int n = __popc(mixed);
+      int pos = atomicAdd(s_count, n);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (mixed & (1u << b)) s_list[pos++] = (uint16_t)(br * 32 + j * 4 + b);
+    }
+  }
+  __syncthreads();
+  {
+    const int n9 = *s_count * 9;
+    for (int idx = tid; idx < n9; idx += RT) {
+      const int blk = s_list[idx / 9], px = idx % 9;
+      const int i = px / 3, jj = px % 3;
+      const int bry = blk >> 5, bcx = blk & 31;
+      const uint8_t* src = s_fov + (4 * bry + i) * S + 4 * bcx + jj;
+      const uint32_t res = resolve_px<OBS_MODE>(src[0], src[1], src[S], src[S + 1], 3 - jj, 1 + jj, 3 - i, 1 + i, s_rg,
+                                                s_b, s_key, s_cm);
+      s_out[(3 * bry + i) * O + 3 * bcx + jj] = (uint8_t)res;
+    }
   }
   __syncthreads();
 
@@ -286,10 +377,10 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
           const uint32_t m4 = ((const uint32_t*)s_out)[q];
 #pragma unroll
           for (int c = 0; c < CHANNELS; ++c) {
-            const uint32_t t = (m4 >> c) & 0x01010101u;  // bit c of each of the 4 pixels; 1.0f = 0x3f800000
-            st_f4(fb + c * (O * O) + 4 * q, __uint_as_float((t & 1u) * 0x3f800000u),
-                  __uint_as_float(((t >> 8) & 1u) * 0x3f800000u), __uint_as_float(((t >> 16) & 1u) * 0x3f800000u),
-                  __uint_as_float((t >> 24) * 0x3f800000u));
+            // bit c of each of the 4 pixels -> 4-bit index (multiply gathers the bits into the top byte)
+            const uint32_t t = (m4 >> c) & 0x01010101u;
+            const float4 v = s_lut[(t * 0x01020408u) >> 24];
+            st_f4(fb + c * (O * O) + 4 * q, v.x, v.y, v.z, v.w);
           }
         }
       } else {
@@ -364,15 +455,16 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, cudaStream_
   P.desc = e->desc;
   P.rects = e->rects;
   P.max_rects = e->max_rects;
-  P.fov_out = e->fov;
+  P.fov_out = e->keep_fov ? e->fov : nullptr;
   P.ring = e->ring;
   const int S = P.fov;
   size_t tile = (size_t)P.crop * P.box_w;
   if (e->cfg.obs_mode == CBEV_OBS_RGB && tile < (size_t)S * S * 3) tile = (size_t)S * S * 3;  // RGB staging
+  if (tile < 96 * 96 + 2 * 1024 + 64) tile = 96 * 96 + 2 * 1024 + 64;  // output bytes + mixed-block worklist
   tile = ((tile + 127) / 128) * 128;
   P.tile_bytes = (int32_t)tile;
   P.pad0 = 0;
-  size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16;
+  size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16;
   int rc = 1;
   if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, s);
   else if (e->cfg.obs_mode == CBEV_OBS_GRAY) rc = launch<CBEV_OBS_GRAY, 1>(e, P, smem, s);

@@ -37,7 +37,7 @@ SG_MAX = 12
 EXPORTS = ("cbev_version", "cbev_last_error", "cbev_create", "cbev_destroy", "cbev_upload_map",
            "cbev_upload_scene_pool", "cbev_frame_bytes", "cbev_bind_obs_ring", "cbev_reset", "cbev_step",
            "cbev_step_host", "cbev_obs_head", "cbev_get_state", "cbev_set_ego_state", "cbev_copy_fov",
-           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes")
+           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov")
 
 
 class CbevConfig(C.Structure):
@@ -114,6 +114,7 @@ def load_library(build_if_missing: bool = True):
     lib.cbev_get_state.argtypes = [_P, _P, _P]
     lib.cbev_set_ego_state.argtypes = [_P, _P]
     lib.cbev_copy_fov.argtypes = [_P, _P, _P]
+    lib.cbev_keep_fov.argtypes = [_P, C.c_int32]
     lib.cbev_read_stats.argtypes = [_P, _P, C.c_int32, _P]
     lib.cbev_profile_enable.argtypes = [_P, C.c_int32]
     lib.cbev_profile_read.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -327,8 +328,11 @@ class Engine:
             return ring[:, head - F + 1: head + 1]
         return self.ring.view(N, self.size, self.size, 3)
 
+    def keep_fov(self, on=True):
+        _check(self.lib, self.lib.cbev_keep_fov(self.handle, int(on)))
+
     def fov(self):
-        """Last rendered palette-index frames, uint8 [N, S, S]."""
+        """Last rendered palette-index frames, uint8 [N, S, S] (needs keep_fov(True) before the step)."""
         out = self.torch.empty(self.N, self.size, self.size, dtype=self.torch.uint8, device=self.device)
         _check(self.lib, self.lib.cbev_copy_fov(self.handle, out.data_ptr(), self._stream()))
         return out

@@ -241,7 +241,9 @@ int cbev_obs_head(cbev_handle h, int32_t* head);
 int cbev_get_state(cbev_handle h, double* ego_host, double* actors_host);
 int cbev_set_ego_state(cbev_handle h, const double* ego_host);
 
-/* Last rendered 128x128 palette-index frame of every env (uint8 [N][S][S], device pointer). */
+/* Debug / parity: keep the 128x128 palette-index frame of every env (one extra 16 KB store per env-step
+ * while on), and copy the last one out (uint8 [N][S][S], device pointer). */
+int cbev_keep_fov(cbev_handle h, int32_t on);
 int cbev_copy_fov(cbev_handle h, uint8_t* fov_dev, void* stream);
 
 /* Global episode statistics accumulated on device (CBEV_STATS_FIELDS doubles, device pointer).

@@ -35,6 +35,7 @@ def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb
     )
     eng.upload_map(load_map())
     eng.upload_pool(g.pool)
+    eng.keep_fov(True)
     return eng
 
 
