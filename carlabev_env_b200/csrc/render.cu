@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t resolve_px(uint32_t c00, uint32_t c01, uint3
 }
 
 template <int OBS_MODE, int CHANNELS>
-__global__ void __launch_bounds__(RT, 3)
+__global__ void __launch_bounds__(RT, 4)
 k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
   extern __shared__ __align__(128) uint8_t smem[];
   // layout: [tile: crop rows x box_w | re-used as: 96x96 output bytes + mixed-block worklist / RGB staging]

@@ -18,6 +18,10 @@
 
 #include "engine.h"
 
+#ifndef CBEV_SIM_BLOCKS_PER_SM
+#define CBEV_SIM_BLOCKS_PER_SM 7  // 7 x 4 warps/SM: 4096 envs fit in one wave on 148 SMs (<= 73 registers)
+#endif
+
 namespace {
 
 constexpr double DT = 0.1;                       // stanley_controller.py:22
@@ -338,7 +342,7 @@ __device__ void start_retreat(const PoolDev& pool, double* rbuf, int32_t* rn, in
 }
 
 // ---- the step kernel ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, CBEV_SIM_BLOCKS_PER_SM)
 k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, cbev_step_out out,
       int32_t* __restrict__ desc, uint32_t* __restrict__ rects, double* __restrict__ gstats) {
   __shared__ double s_hero[CBEV_WARPS_PER_BLOCK][CBEV_HERO_FIELDS];
