@@ -1,0 +1,259 @@
+"""GPU tests of the engine beyond golden replay: batched parity with the oracle on fresh scenes, the
+observation ring (wrap + mirror), masked reset, device auto-reset, the VectorEnv surface, error paths and
+size-independent properties at the benchmark size (4096 envs)."""
+import numpy as np
+import pytest
+
+from golden_util import Golden, load_map
+
+pytestmark = pytest.mark.gpu
+
+
+def _scenes(kinds, seed0=500):
+    from carlabev_env_b200.scenes import build_scripted_scene
+
+    cls = load_map()
+    return [build_scripted_scene(k, seed0 + i, level=lv, cls_map=cls) for i, (k, lv) in enumerate(kinds)]
+
+
+def _engine(n, scenes, **kw):
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import pack_pool
+
+    args = dict(obs_mode=E.OBS_SEMANTIC, mask_mode="6-class", frame_stack=4, action_mode=E.ACTION_CONTINUOUS,
+                max_actors=4, ring_budget_bytes=64 << 20)
+    args.update(kw)
+    eng = E.Engine(n, **args)
+    eng.upload_map(load_map())
+    eng.upload_pool(pack_pool(scenes))
+    return eng
+
+
+def _rand_actions(rng, n):
+    return np.stack([rng.uniform(0, 1, n), rng.uniform(-1, 1, n), rng.uniform(0, 1, n)], axis=1).astype(np.float32)
+
+
+def _check_env(t, i, hero, rew, term, obs, oracle, out):
+    o, r, te, tr, _ = out
+    e = oracle.sim.ego
+    assert np.allclose(hero[:4], [e.x, e.y, e.yaw, e.v], rtol=1e-9, atol=1e-9), (t, i, "pose")
+    assert abs(r - rew) < 1e-9, (t, i, "reward", r, rew)
+    assert te == term, (t, i, "terminated")
+    assert np.array_equal(obs, o), (t, i, "observation")
+
+
+def test_batched_parity_with_masked_resets():
+    import torch
+
+    from oracle.env import OracleEnv
+
+    kinds = [("lead_brake", 1 + i % 3) for i in range(10)] + [("jaywalk", 1 + i % 4) for i in range(10)]
+    scenes = _scenes(kinds)
+    n = len(scenes)
+    eng = _engine(n, scenes)
+    oracles = [OracleEnv(load_map(), action_mode="continuous") for _ in range(n)]
+    scene_of = np.arange(n)
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i]))
+    rng = np.random.default_rng(1)
+    n_resets = 0
+    for t in range(60):
+        a = _rand_actions(rng, n)
+        if t < 25:
+            a[n // 2:, 0] *= 0.2  # let the pedestrians' FSM play out for part of the batch
+        eng.step(torch.from_numpy(a).cuda())
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, hero = eng.terminated.cpu().numpy().astype(bool), eng.hero.cpu().numpy()
+        for i in range(n):
+            _check_env(t, i, hero[i], rew[i], term[i], obs[i], oracles[i], oracles[i].step(a[i]))
+        if term.any():  # SyncVectorEnv-style masked reset with a new scene for the finished envs
+            scene_of[term] = (scene_of[term] + 7) % n
+            obs = eng.reset(torch.from_numpy(scene_of.astype(np.int32)), term).cpu().numpy()
+            for i in np.flatnonzero(term):
+                assert np.array_equal(obs[i], oracles[i].reset(scenes[scene_of[i]])), (t, i, "masked reset obs")
+                n_resets += 1
+            for i in np.flatnonzero(~term):  # untouched envs keep their window
+                assert np.array_equal(obs[i], oracles[i]._stacked()), (t, i, "window of a non-reset env")
+    assert n_resets > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("ring_slots", [7, 9])
+def test_ring_wrap_keeps_the_frame_stack(ring_slots):
+    import torch
+
+    from oracle.env import OracleEnv
+
+    scenes = _scenes([("jaywalk", 2), ("jaywalk", 1), ("lead_brake", 2)], seed0=900)
+    eng = _engine(3, scenes, ring_slots=ring_slots)
+    oracles = [OracleEnv(load_map(), action_mode="continuous") for _ in range(3)]
+    eng.reset(torch.arange(3, dtype=torch.int32))
+    for i in range(3):
+        oracles[i].reset(scenes[i])
+    alive = np.ones(3, bool)
+    for t in range(3 * ring_slots + 2):
+        a = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (3, 1))  # brake: long episodes
+        eng.step(torch.from_numpy(a).cuda())
+        obs = eng.obs().cpu().numpy()
+        for i in range(3):
+            if alive[i]:
+                o, _, te, _, _ = oracles[i].step(a[i])
+                assert np.array_equal(obs[i], o), (t, i, eng.head)
+                alive[i] = not te
+    assert alive.any()
+    eng.close()
+
+
+def _splitmix64(z):
+    m = (1 << 64) - 1
+    z = (z + 0x9E3779B97F4A7C15) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+
+def test_device_autoreset_next_step():
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from oracle.env import OracleEnv
+
+    kinds = [("lead_brake", 1 + i % 3) for i in range(12)]
+    scenes = _scenes(kinds, seed0=300)
+    n, seed = 12, 5
+    eng = _engine(n, scenes, autoreset=E.AUTORESET_NEXT_STEP, seed=seed)
+    oracles = [OracleEnv(load_map(), action_mode="continuous") for _ in range(n)]
+    eng.reset(torch.arange(n, dtype=torch.int32))
+    for i in range(n):
+        oracles[i].reset(scenes[i])
+    done = np.zeros(n, bool)
+    episodes = np.zeros(n, dtype=np.int64)
+    rng = np.random.default_rng(2)
+    n_auto = 0
+    m = (1 << 64) - 1
+    for t in range(70):
+        a = _rand_actions(rng, n)
+        a[:, 0] = np.clip(a[:, 0] + 0.3, 0, 1)
+        eng.step(torch.from_numpy(a).cuda())
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, hero = eng.terminated.cpu().numpy().astype(bool), eng.hero.cpu().numpy()
+        for i in range(n):
+            if done[i]:  # gymnasium NEXT_STEP: this step resets, ignores the action, reward 0, not terminated
+                h = _splitmix64((seed + i * 0x9E3779B97F4A7C15 + int(episodes[i]) * 0xD1B54A32D192ED03) & m)
+                sc = h % len(scenes)
+                assert int(hero[i][E.HERO_FIELDS.index("scene")]) == sc, (t, i)
+                assert rew[i] == 0.0 and not term[i]
+                assert np.array_equal(obs[i], oracles[i].reset(scenes[sc])), (t, i, "auto-reset obs")
+                done[i] = False
+                n_auto += 1
+            else:
+                _check_env(t, i, hero[i], rew[i], term[i], obs[i], oracles[i], oracles[i].step(a[i]))
+                if term[i]:
+                    done[i] = True
+                    episodes[i] += 1
+    assert n_auto > 3
+    stats = eng.read_stats().cpu().numpy()
+    assert stats[0] == episodes.sum() and stats[-1] == 70 * n
+    eng.close()
+
+
+def test_vector_env_surface_and_infos():
+    import torch
+
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+
+    scenes = _scenes([("lead_brake", 1 + i % 3) for i in range(6)], seed0=40)
+    cfg = RunConfig(env=EnvConfig(action_mode="continuous"), num_envs=6)
+    envs = make_env(cfg, scenes=scenes, ring_budget_bytes=64 << 20)
+    assert envs.num_envs == 6 and envs.single_observation_space.shape == (24, 96, 96)
+    assert envs.single_action_space.shape == (3,)
+    obs, infos = envs.reset(options={"scene_ids": np.arange(6)})
+    assert obs.shape == (6, 24, 96, 96) and obs.dtype == torch.float32 and infos == {}
+    with pytest.raises(AssertionError):
+        envs.reset(options={"reset_mask": np.zeros(6, bool)})
+    finished = None
+    for t in range(80):
+        a = np.tile(np.array([[1.0, 0.3, 0.0]], np.float32), (6, 1))
+        obs, rew, term, trunc, infos = envs.step(a)
+        assert rew.dtype == torch.float64 and term.dtype == torch.bool and infos["hero"].shape == (6, 32)
+        if bool((term | trunc).any()):
+            finished = (term | trunc).cpu().numpy()
+            ei = infos["episode_info"]
+            assert np.array_equal(infos["_episode_info"], finished)
+            i = int(np.flatnonzero(finished)[0])
+            assert ei["termination"][i] in ("collision", "success", "out_of_bounds")
+            assert ei["length"][i] == infos["episode"]["l"][i] == t + 1
+            assert abs(ei["return"][i] - infos["episode"]["r"][i]) < 1e-9
+            break
+    assert finished is not None
+    with pytest.raises(AssertionError):  # SyncVectorEnv(AutoresetMode.DISABLED) refuses to step finished envs
+        envs.step(np.zeros((6, 3), np.float32))
+    obs, _ = envs.reset(options={"scene_ids": np.arange(6), "reset_mask": finished})
+    envs.step(np.zeros((6, 3), np.float32))
+    # scripted scene built on the host at reset time, like the reference's reset(options={"scene": ...})
+    obs, _ = envs.reset(options={"scene": "jaywalk", "level": 3, "scene_seed": 11})
+    assert obs.shape == (6, 24, 96, 96)
+    with pytest.raises(NotImplementedError):
+        envs.reset(options={"scene": "rdm"})
+    envs.close()
+
+
+def test_error_paths():
+    import torch
+
+    from carlabev_env_b200 import engine as E
+
+    scenes = _scenes([("lead_brake", 1)])
+    with pytest.raises(E.CbevError, match="ring_slots"):
+        _engine(2, scenes, ring_slots=4)
+    eng = _engine(2, scenes)
+    with pytest.raises(E.CbevError, match="before reset"):
+        eng.step(torch.zeros(2, 3, device="cuda"))
+    with pytest.raises(E.CbevError, match="first reset"):
+        eng.reset(torch.zeros(2, dtype=torch.int32), np.array([True, False]))
+    big = _scenes([("lead_brake", 3)])
+    small = E.Engine(1, action_mode=E.ACTION_CONTINUOUS, max_actors=1, ring_budget_bytes=32 << 20)
+    from carlabev_env_b200.pool import pack_pool
+
+    with pytest.raises(E.CbevError, match="max_actors"):
+        small.upload_pool(pack_pool(big))
+    eng.close()
+    small.close()
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (4096 envs): determinism, mask structure and the frame-stack shift property."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+
+    scenes = _scenes([("lead_brake", 1 + i % 3) for i in range(64)], seed0=2000)
+    n = 4096
+
+    def run():
+        eng = _engine(n, scenes, autoreset=E.AUTORESET_NEXT_STEP, seed=9, ring_budget_bytes=12 << 30)
+        eng.reset(torch.arange(n, dtype=torch.int32) % len(scenes))
+        g = torch.Generator(device="cpu").manual_seed(0)
+        prev, sums = None, []
+        for t in range(12):
+            a = torch.rand(n, 3, generator=g)
+            a[:, 1] = a[:, 1] * 2 - 1
+            eng.step(a.cuda())
+            obs = eng.obs()
+            assert obs.shape == (n, 24, 96, 96)
+            assert bool(((obs == 0) | (obs == 1)).all())
+            new = obs[:, 18:]
+            excl = new[:, 0] + new[:, 1] + new[:, 2] + new[:, 3] + new[:, 4]  # one base class per pixel at most
+            assert float(excl.max()) <= 1.0
+            assert bool((new[:, 5] <= new[:, 1]).all())                       # route pixels count as drivable
+            if prev is not None:
+                keep = ~was_done                                               # noqa: F821
+                assert bool((obs[keep, :18] == prev[keep, 6:]).all())          # stack shifts by one frame
+            prev = obs.clone()
+            was_done = eng.terminated.bool().clone()                           # these envs auto-reset next step
+            sums.append(float(obs.sum()) + float(eng.reward.sum()))
+        eng.close()
+        return sums
+
+    assert run() == run()

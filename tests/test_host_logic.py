@@ -1,0 +1,158 @@
+"""Host-side logic that needs no GPU: configuration surface, scene generators, pool container, the C-ABI
+library (loads + exports every declared symbol) and the multi-rank statistics reduction (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from golden_util import ROOT, Golden, load_map
+
+
+# ---- configuration (modelled on the reference's tests/test_public_config.py) ----------------------------
+def test_env_config_defaults_and_legacy_fields():
+    from carlabev_env_b200 import EnvConfig, validate_env_config
+
+    c = EnvConfig()
+    assert (c.size, c.obs_size, c.obs_mode, c.semantic_mask_ch, c.frame_stack) == (128, (96, 96), "bev_semantic", "6-class", 4)
+    assert c.action_profile_id == "discrete9_v1" and c.reward_profile_id == "carl_base_v1" and c.masked
+    legacy = validate_env_config({"masked": False, "action_space": "continuous", "reward_type": "shaping"})
+    assert legacy.obs_mode == "bev_rgb" and legacy.action_mode == "continuous" and legacy.reward_mode == "shaping"
+    assert legacy.action_profile_id == "continuous_gsb_v1" and legacy.reward_profile_id == "shaping_base_v1"
+
+
+def test_env_config_validation_errors():
+    from carlabev_env_b200 import EnvConfig, RunConfig, validate_run_config
+
+    with pytest.raises(ValueError):
+        EnvConfig(frame_stack=0)
+    with pytest.raises(ValueError):
+        EnvConfig(ego_anchor_y_frac=1.5)
+    with pytest.raises(ValueError):
+        EnvConfig(action_mode="continuous", action_profile_id="discrete9_v1")
+    with pytest.raises(ValueError):
+        EnvConfig(temporal_fusion_mode="vehicle_temporal", frame_stack=2)
+    with pytest.raises(KeyError):
+        EnvConfig(action_profile_id="nope")
+    with pytest.raises(ValueError):
+        validate_run_config(RunConfig(env=EnvConfig(obs_mode="vector")))
+    with pytest.raises(ValueError):
+        RunConfig(num_envs=0)
+
+
+def test_engine_construction_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+    from carlabev_env_b200.engine import CbevError
+
+    with pytest.raises(CbevError):
+        make_env(RunConfig(env=EnvConfig(), num_envs=2))
+
+
+# ---- scene generators / pool ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,kind,seed0,nlev", [("lead_brake_continuous", "lead_brake", 0, 3),
+                                                  ("jaywalk_levels", "jaywalk", 100, 4),
+                                                  ("jaywalk_drive", "jaywalk", 200, 4)])
+def test_host_scene_generators_match_reference_snapshots(case, kind, seed0, nlev):
+    from carlabev_env_b200.pool import unpack_pool
+    from carlabev_env_b200.scenes import build_scripted_scene
+
+    cls = load_map()
+    for ep, ref in enumerate(unpack_pool(Golden(case).pool)):
+        mine = build_scripted_scene(kind, seed0 + ep, level=1 + ep % nlev, cls_map=cls)
+        for k, v in ref.items():
+            a, b = np.asarray(v), np.asarray(mine[k])
+            assert a.shape == b.shape, (k, a.shape, b.shape)
+            if a.dtype.kind == "f":
+                assert np.allclose(a, b, rtol=1e-12, atol=1e-12), k
+            else:
+                assert np.array_equal(a, b), k
+
+
+def test_pool_pack_roundtrip():
+    from carlabev_env_b200.pool import pack_pool, unpack_pool
+
+    scenes = unpack_pool(Golden("rdm_rgb_lookahead").pool) + unpack_pool(Golden("jaywalk_levels").pool)
+    again = unpack_pool(pack_pool(scenes))
+    assert len(again) == len(scenes)
+    for a, b in zip(scenes, again):
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+def test_derived_seeds_match_reference_formula():
+    from carlabev_env_b200.scenes import derive_seed
+
+    # randomness.py:13-16: sha256(f"{seed}:{part}")[:16] mod (2^31 - 1); values recorded from the reference
+    assert derive_seed(0, "route") == int(__import__("hashlib").sha256(b"0:route").hexdigest()[:16], 16) % (2**31 - 1)
+    assert derive_seed(7, "scenario") != derive_seed(7, "traffic")
+
+
+# ---- C ABI ---------------------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    from carlabev_env_b200 import engine
+
+    lib = engine.load_library()
+    header = open(os.path.join(ROOT, "include", "cbev.h")).read()
+    declared = set(re.findall(r"\b(cbev_[a-z_0-9]+)\s*\(", header))
+    declared -= {"cbev_config", "cbev_pool_desc", "cbev_step_out"}
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/cbev.h but not exported"
+    assert set(engine.EXPORTS) == declared
+    assert lib.cbev_version() == 100
+    # struct layouts agree between the header (compiled) and the ctypes mirror
+    sizes = [ctypes.c_int32() for _ in range(3)]
+    lib.cbev_abi_sizes(*[ctypes.byref(s) for s in sizes])
+    assert [s.value for s in sizes] == [ctypes.sizeof(engine.CbevConfig), ctypes.sizeof(engine.CbevPoolDesc),
+                                        ctypes.sizeof(engine.CbevStepOut)]
+    # argument validation happens before any CUDA call
+    cfg = engine.CbevConfig()
+    h = ctypes.c_void_p()
+    assert lib.cbev_create(ctypes.byref(cfg), ctypes.byref(h)) == 1
+    assert b"num_envs" in lib.cbev_last_error()
+
+
+# ---- multi-rank statistics (the only exchange) ---------------------------------------------------------------------
+def _stats_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from carlabev_env_b200.distributed import allreduce_stats, shard_range, summarize_stats
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(64, rank, world)
+    stats = torch.zeros(21, dtype=torch.float64)
+    stats[0] = hi - lo            # episodes
+    stats[1] = float(rank + 1)    # return sum
+    stats[4 + 2] = 3.0            # collisions
+    stats[-1] = 10.0 * (hi - lo)  # env steps
+    out = summarize_stats(allreduce_stats(stats))
+    dist.destroy_process_group()
+    q.put((rank, lo, hi, out))
+
+
+def test_stats_allreduce_gloo_world2():
+    import multiprocessing as mp
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stats_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [(r[1], r[2]) for r in res] == [(0, 32), (32, 64)]
+    for _, _, _, out in res:
+        assert out["episodes"] == 64 and out["env_steps"] == 640
+        assert abs(out["mean_return"] - 3.0 / 64) < 1e-12 and abs(out["rate_collision"] - 6.0 / 64) < 1e-12
