@@ -66,7 +66,7 @@ struct EnvState {
 };
 
 struct SimParams {
-  int32_t N, max_actors, max_rects, max_retreat;
+  int32_t N, env_lo, env_hi, max_actors, max_rects, max_retreat;
   int32_t map_w, map_h, fov, crop, pad, anchor_x, anchor_y;
   int32_t action_mode, n_discrete, reward_mode, autoreset;
   uint64_t seed;
@@ -109,6 +109,6 @@ struct cbev_engine {
 
 // kernels (sim.cu / render.cu)
 void cbev_launch_reset(cbev_engine* e, const uint8_t* mask, const int32_t* scene_ids, cudaStream_t s);
-void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, cudaStream_t s);
-int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, cudaStream_t s);
+void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, int lo, int hi, cudaStream_t s);
+int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int hi, cudaStream_t s);
 void cbev_set_error(const char* fmt, ...);

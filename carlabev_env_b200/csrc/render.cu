@@ -69,7 +69,7 @@ __device__ __forceinline__ void st_u4(void* p, uint4 v) {
 }
 
 struct RenderParams {
-  int32_t N, fov, crop, box_w, anchor_x, anchor_y;
+  int32_t N, env_lo, fov, crop, box_w, anchor_x, anchor_y;
   int32_t frame_stack, ring_slots, head, mirror;  // mirror = slot offset (L - F + 1)
   int64_t frame_bytes;
   int32_t tile_bytes, pad0;
@@ -142,7 +142,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   float4* s_lut = (float4*)(s_cm + 16);      // 16 x float4: 4 mask bits -> four 0.0f / 1.0f values
   int* s_count = (int*)(s_lut + 16);
 
-  const int env = blockIdx.x;
+  const int env = P.env_lo + blockIdx.x;
   const int tid = threadIdx.x;
   const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
   const int flags = d[RD_FLAGS];
@@ -435,13 +435,14 @@ int launch(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
 
 }  // namespace
 
-int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, cudaStream_t s) {
+int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int hi, cudaStream_t s) {
   if (!g_tables_ready) {
     upload_tables();
     g_tables_ready = true;
   }
   RenderParams P;
-  P.N = e->N;
+  P.N = hi - lo;
+  P.env_lo = lo;
   P.fov = e->cfg.fov_size;
   P.crop = e->crop;
   P.box_w = e->box_w;

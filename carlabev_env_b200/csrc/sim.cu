@@ -347,9 +347,9 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
       int32_t* __restrict__ desc, uint32_t* __restrict__ rects, double* __restrict__ gstats) {
   __shared__ double s_hero[CBEV_WARPS_PER_BLOCK][CBEV_HERO_FIELDS];
   const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * CBEV_WARPS_PER_BLOCK + warp;
+  const int env = P.env_lo + blockIdx.x * CBEV_WARPS_PER_BLOCK + warp;
   const int lane = threadIdx.x & 31;
-  if (env >= P.N) return;
+  if (env >= P.env_hi) return;
   int32_t* d = desc + (size_t)env * CBEV_DESC_WORDS;
   uint32_t* rl = rects + (size_t)env * P.max_rects;
 
@@ -937,6 +937,8 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
 static SimParams make_params(cbev_engine* e) {
   SimParams P;
   P.N = e->N;
+  P.env_lo = 0;
+  P.env_hi = e->N;
   P.max_actors = e->cfg.max_actors;
   P.max_rects = e->max_rects;
   P.max_retreat = e->pool.max_retreat;
@@ -965,9 +967,11 @@ void cbev_launch_reset(cbev_engine* e, const uint8_t* mask, const int32_t* scene
   e->launches += 1;
 }
 
-void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, cudaStream_t s) {
+void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, int lo, int hi, cudaStream_t s) {
   SimParams P = make_params(e);
-  int blocks = (e->N + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
+  P.env_lo = lo;
+  P.env_hi = hi;
+  int blocks = (hi - lo + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
   k_sim<<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->gstats);
   e->launches += 1;
 }
