@@ -189,11 +189,46 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+WORKLOADS = {
+    # name: BASELINE.json config it restates; c2 is the bench line, the others are reported extras
+    "c2": dict(desc="configs[1]: {N} envs/GPU lead_brake (levels 1-3, pool of {K} seeded scenes), continuous actions, "
+                    "6-class semantic masks 96x96 float32, frame_stack 4, CaRL reward, device auto-reset (next-step) "
+                    "from the pool", envs=4096, obs="semantic", actions="continuous", anchor=(0.5, 0.5)),
+    "c3": dict(desc="configs[2]: {N} envs/GPU rdm rt_hard_v1 (25 vehicles, shipped pool of {K} reference scenes), "
+                    "discrete9 actions, 6-class semantic F=4, auto-reset", envs=8192, obs="semantic",
+               actions="discrete", anchor=(0.5, 0.5), pool="rdm_rt_hard_v1"),
+    "c4": dict(desc="configs[3]: {N} envs/GPU 50/50 jaywalk (levels 1-4) / red_light_runner, continuous actions, "
+                    "6-class semantic F=4, auto-reset from a pool of {K} scenes", envs=8192, obs="semantic",
+               actions="continuous", anchor=(0.5, 0.5), pool="mixed_edge"),
+    "c5": dict(desc="configs[4]: {N} envs/GPU raw RGB (128,128,3) uint8 obs, lookahead_75 camera, rdm with 50 vehicles "
+                    "(shipped pool of {K} reference scenes), continuous actions, auto-reset", envs=8192, obs="rgb",
+               actions="continuous", anchor=(0.5, 0.75), pool="rdm_dense_50"),
+}
+
+
+def workload_pool(name, args):
+    from carlabev_env_b200.pool import load_shipped_pool
+
+    w = WORKLOADS[name]
+    if name == "c2":
+        return build_pool(args.pool)
+    if w["pool"] == "mixed_edge":
+        from carlabev_env_b200.scenes import build_scripted_scene
+        from carlabev_env_b200.vector_env import load_town01_map
+
+        cls = load_town01_map()
+        jay = [build_scripted_scene("jaywalk", i, level=1 + i % 4, cls_map=cls) for i in range(256)]
+        rl = load_shipped_pool("red_light_runner")
+        return [jay[i // 2] if i % 2 == 0 else rl[(i // 2) % len(rl)] for i in range(512)]
+    return load_shipped_pool(w["pool"])
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.config import ACTION_PROFILES
     from carlabev_env_b200.pool import pack_pool
     from carlabev_env_b200.vector_env import load_town01_map
 
@@ -204,21 +239,30 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    N = args.envs
-    scenes = build_pool(args.pool)
+    W = WORKLOADS[args.workload]
+    N = args.envs or W["envs"]
+    scenes = workload_pool(args.workload, args)
     a_mean = float(np.mean([len(s["act_kind"]) for s in scenes]))
-    eng = E.Engine(N, obs_mode=E.OBS_SEMANTIC, mask_mode="6-class", frame_stack=4, action_mode=E.ACTION_CONTINUOUS,
-                   reward_mode=E.REWARD_CARL, autoreset=E.AUTORESET_NEXT_STEP, max_actors=4, seed=rank, device=local,
-                   ring_slots=args.ring_slots)
+    a_max = int(max(len(s["act_kind"]) for s in scenes))
+    discrete = W["actions"] == "discrete"
+    eng = E.Engine(N, obs_mode=E.OBS_SEMANTIC if W["obs"] == "semantic" else E.OBS_RGB, mask_mode="6-class",
+                   frame_stack=4, action_mode=E.ACTION_DISCRETE if discrete else E.ACTION_CONTINUOUS,
+                   discrete_table=ACTION_PROFILES["discrete9_v1"]["discrete_actions"],
+                   reward_mode=E.REWARD_CARL, autoreset=E.AUTORESET_NEXT_STEP, max_actors=max(a_max, 1), seed=rank,
+                   device=local, ring_slots=args.ring_slots, anchor=W["anchor"])
+    frame_bytes = eng.frame_bytes
     eng.upload_map(load_town01_map())
     eng.upload_pool(pack_pool(scenes))
     ids = (torch.arange(N, dtype=torch.int32) + rank * N) % len(scenes)
     eng.reset(ids)
     gen = torch.Generator(device="cpu").manual_seed(0 + rank)
     bank = 16
-    lo = torch.tensor([0.0, -1.0, 0.0])
-    hi = torch.tensor([1.0, 1.0, 1.0])
-    acts_host = [(lo + (hi - lo) * torch.rand(N, 3, generator=gen)).float().pin_memory() for _ in range(bank)]
+    if discrete:
+        acts_host = [torch.randint(0, 9, (N,), generator=gen, dtype=torch.int64).pin_memory() for _ in range(bank)]
+    else:
+        lo = torch.tensor([0.0, -1.0, 0.0])
+        hi = torch.tensor([1.0, 1.0, 1.0])
+        acts_host = [(lo + (hi - lo) * torch.rand(N, 3, generator=gen)).float().pin_memory() for _ in range(bank)]
     acts_dev = [a.to(dev) for a in acts_host]
     stream = torch.cuda.current_stream(dev)
 
@@ -286,7 +330,7 @@ def run_ours(args):
         n_prof_steps = max(prof_steps // pairs_per_step, 1)
         render_avg_ms = render_ms / n_prof_steps
         sim_avg_ms = sim_ms / n_prof_steps
-        alg_bytes = N * FRAME_BYTES
+        alg_bytes = N * frame_bytes
         achieved = alg_bytes / (render_avg_ms * 1e-3) / 1e9 if render_avg_ms > 0 else 0.0
         cb = None
         if world == 1 and not args.no_cpu_baseline:
@@ -304,9 +348,7 @@ def run_ours(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"configs[1]: {N} envs/GPU lead_brake (levels 1-3, pool of {len(scenes)} seeded scenes), "
-                            "continuous actions, 6-class semantic masks 96x96 float32, frame_stack 4, CaRL reward, "
-                            "device auto-reset (next-step) from the pool",
+                "workload": W["desc"].format(N=N, K=len(scenes)),
                 "envs_per_gpu": N, "envs_total": world * N, "ring_slots": eng.L,
                 "l2": f"each step writes {alg_bytes / 1e6:.0f} MB of observations per GPU (> 126 MB L2), no flush needed",
                 "mean_actors_per_scene": a_mean,
@@ -318,7 +360,8 @@ def run_ours(args):
                          "launches_per_step": 2 * pairs_per_step,
                          "step_fraction_render": render_avg_ms / (ms / args.steps) if ms else None},
             "cpu_baseline": cb,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 12, "d2h_bytes_per_step": N * 10,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * (8 if discrete else 12),
+                    "d2h_bytes_per_step": N * 10,
                     "note": "cbev_step_host: pinned host actions in, reward/terminated/truncated out, stream sync "
                             "every step; observations stay device resident (ring view)"},
             "gpu_launches": int(launches),
@@ -337,7 +380,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config; c2 is the bench line")
     ap.add_argument("--pool", type=int, default=POOL_SCENES)
     ap.add_argument("--ring-slots", type=int, default=None)
     ap.add_argument("--cpu-steps", type=int, default=150)

@@ -134,3 +134,35 @@ def save_pool(path, scenes: list[dict]) -> None:
 def load_pool(path) -> list[dict]:
     with np.load(path) as z:
         return unpack_pool(z)
+
+
+# ---- pools shipped with the package (exported from the reference by oracle/export_pools.py) -------------
+SHIPPED_POOLS = {
+    # name: (file, reset options the entries were generated with; entry i has scene_seed = i)
+    "rdm_rt_hard_v1": dict(scene="rdm", difficulty_id="rt_hard_v1", num_vehicles=25, route_dist_range=(50, 130)),
+    "rdm_rt_medium_v1": dict(scene="rdm", difficulty_id="rt_medium_v1", num_vehicles=16, route_dist_range=(40, 100)),
+    "rdm_dense_50": dict(scene="rdm", num_vehicles=50, route_dist_range=(30, 130)),
+    "red_light_runner": dict(scene="red_light_runner"),
+}
+
+
+def load_shipped_pool(name: str) -> list[dict]:
+    import os
+
+    if name not in SHIPPED_POOLS:
+        raise KeyError(f"Unknown shipped pool {name!r}. Available: {', '.join(sorted(SHIPPED_POOLS))}")
+    return load_pool(os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "pools", f"{name}.npz"))
+
+
+def shipped_pool_for(options: dict) -> str | None:
+    """Name of the shipped pool generated with these reset options, if any."""
+    scene = options.get("scene", "rdm")
+    if scene == "red_light_runner":
+        return "red_light_runner"
+    if scene == "rdm":
+        diff = options.get("difficulty_id")
+        if diff in ("rt_hard_v1", "rt_medium_v1"):
+            return f"rdm_{diff}"
+        if options.get("num_vehicles") == 50:
+            return "rdm_dense_50"
+    return None

@@ -29,7 +29,7 @@ from . import engine as E
 from . import scenes as S
 from .config import (ACTION_PROFILES, CARL_DEFAULTS, SHAPING_DEFAULTS, EnvConfig, RunConfig, get_action_profile_spec,
                      get_difficulty_spec, get_reward_profile_spec, validate_run_config)
-from .pool import load_pool, pack_pool
+from .pool import load_shipped_pool, pack_pool, shipped_pool_for
 from .spaces import Box, Discrete
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -155,6 +155,23 @@ class CarlaBEVVectorEnv:
                 self._scripted_cache = cache
                 self.engine.upload_pool(pack_pool(self._scenes))
             return np.full(n, cache[key], dtype=np.int64)
+        if scene in ("rdm", "red_light_runner"):
+            # generated by the reference from its lane graphs; a pool exported with exactly these options ships
+            # with the package (entry i == the reference's scene for scene_seed = i)
+            name = shipped_pool_for(options)
+            if name is not None:
+                cache = getattr(self, "_shipped_cache", {})
+                if name not in cache:
+                    sc = load_shipped_pool(name)
+                    cache[name] = (len(self._scenes), len(sc))
+                    self._scenes.extend(sc)
+                    self._shipped_cache = cache
+                    self.engine.upload_pool(pack_pool(self._scenes))
+                base, count = cache[name]
+                seed = int(options.get("scene_seed", self.env_cfg.seed))
+                if not 0 <= seed < count:
+                    raise ValueError(f"shipped pool {name!r} covers scene_seed 0..{count - 1}, got {seed}")
+                return np.full(n, base + seed, dtype=np.int64)
         if scene in ("rdm", "red_light_runner") or str(scene).endswith(".json"):
             raise NotImplementedError(
                 f"scene={scene!r} needs the reference's lane graphs / authored files on the host; export a pool with "

@@ -1,0 +1,63 @@
+"""Export scene pools that need the reference's lane graphs (rdm, red_light_runner) by resetting the
+UNMODIFIED reference (under oracle/shims) and snapshotting its objects (oracle/gen_golden.py:extract_scene).
+
+TEST / DATA INFRASTRUCTURE, run in the build container only:  python oracle/export_pools.py
+Writes carlabev_env_b200/assets/pools/*.npz (packed pools, carlabev_env_b200/pool.py)."""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.gen_golden import extract_scene  # noqa: E402  (loads the reference)
+from CarlaBEV.config import EnvConfig, RunConfig  # noqa: E402
+from CarlaBEV.envs import make_env  # noqa: E402
+
+from carlabev_env_b200.pool import save_pool  # noqa: E402
+
+OUT = os.path.join(ROOT, "carlabev_env_b200", "assets", "pools")
+
+
+def export(name, n, options_of, env_kwargs=None):
+    cfg = RunConfig(env=EnvConfig(render_mode="rgb_array", **(env_kwargs or {})), num_envs=1)
+    envs = make_env(cfg)
+    base = envs.envs[0].unwrapped
+    scenes = []
+    t0 = time.time()
+    for i in range(n):
+        opts = options_of(i)
+        envs.reset(options={**opts, "reset_mask": np.array([True])})
+        scenes.append(extract_scene(base, opts))
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, f"{name}.npz")
+    save_pool(path, scenes)
+    acts = [len(s["act_kind"]) for s in scenes]
+    print(f"{name}: {n} scenes, actors {min(acts)}..{max(acts)}, ego route {min(len(s['ego_cx']) for s in scenes)}.."
+          f"{max(len(s['ego_cx']) for s in scenes)} pts, {os.path.getsize(path) / 1e6:.2f} MB, {time.time() - t0:.0f}s")
+    envs.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else ""
+    if which in ("", "rdm_hard"):
+        # BASELINE configs[2]: rdm rt_hard_v1 (25 vehicles, routes 50-130 m), scene_seed = i
+        export("rdm_rt_hard_v1", 96, lambda i: dict(scene="rdm", difficulty_id="rt_hard_v1", num_vehicles=25,
+                                                    route_dist_range=(50, 130), scene_seed=i))
+    if which in ("", "rdm_medium"):
+        # BASELINE configs[0]: rdm rt_medium_v1 (16 vehicles, routes 40-100 m)
+        export("rdm_rt_medium_v1", 32, lambda i: dict(scene="rdm", difficulty_id="rt_medium_v1", num_vehicles=16,
+                                                      route_dist_range=(40, 100), scene_seed=i))
+    if which in ("", "rdm_dense"):
+        # BASELINE configs[4]: max actor density (num_vehicles = max_vehicles = 50), lookahead_75 camera
+        export("rdm_dense_50", 48, lambda i: dict(scene="rdm", num_vehicles=50, route_dist_range=(30, 130), scene_seed=i),
+               env_kwargs=dict(ego_anchor_x_frac=0.5, ego_anchor_y_frac=0.75))
+    if which in ("", "red_light"):
+        # BASELINE configs[3]: red_light_runner (first valid 4-way intersection); the adversary's start jitter is
+        # unseeded in the reference (quirk C-10), so these are snapshots, not re-derivable from the seed
+        export("red_light_runner", 32, lambda i: dict(scene="red_light_runner", scene_seed=i))

@@ -195,7 +195,7 @@ def test_vector_env_surface_and_infos():
     obs, _ = envs.reset(options={"scene": "jaywalk", "level": 3, "scene_seed": 11})
     assert obs.shape == (6, 24, 96, 96)
     with pytest.raises(NotImplementedError):
-        envs.reset(options={"scene": "rdm"})
+        envs.reset(options={"scene": "rdm", "num_vehicles": 3})
     envs.close()
 
 
@@ -257,3 +257,85 @@ def test_full_size_properties():
         return sums
 
     assert run() == run()
+
+
+def test_rdm_and_red_light_pools_discrete_parity():
+    """Scenes exported from the reference's graph-based generators (shipped pools): 25-vehicle random traffic and
+    red_light_runner (traffic-light strips), discrete9 actions, 7-class masks."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.config import ACTION_PROFILES
+    from carlabev_env_b200.pool import load_shipped_pool, pack_pool
+    from oracle.env import OracleEnv
+
+    scenes = load_shipped_pool("rdm_rt_hard_v1")[:10] + load_shipped_pool("red_light_runner")[:2]
+    n = len(scenes)
+    eng = E.Engine(n, obs_mode=E.OBS_SEMANTIC, mask_mode="7-class", frame_stack=4, action_mode=E.ACTION_DISCRETE,
+                   discrete_table=ACTION_PROFILES["discrete9_v1"]["discrete_actions"], max_actors=25,
+                   ring_budget_bytes=64 << 20)
+    eng.upload_map(load_map())
+    eng.upload_pool(pack_pool(scenes))
+    oracles = [OracleEnv(load_map(), semantic_mask_ch="7-class") for _ in range(n)]
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i]))
+    rng = np.random.default_rng(4)
+    alive = np.ones(n, bool)
+    for t in range(90):
+        a = rng.choice([1, 1, 1, 3, 4, 0, 5, 6], size=n)  # mostly throttle, some steering
+        eng.step(torch.from_numpy(a).cuda())
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, hero = eng.terminated.cpu().numpy().astype(bool), eng.hero.cpu().numpy()
+        ego, act = eng.get_state(25)
+        for i in range(n):
+            if not alive[i]:
+                continue
+            _check_env(t, i, hero[i], rew[i], term[i], obs[i], oracles[i], oracles[i].step(a[i]))
+            ref = np.array([[b.x, b.y, b.yaw, b.v] for b in oracles[i].sim.actors])
+            assert np.allclose(act[i, :len(ref), :4], ref, rtol=1e-9, atol=1e-9), (t, i, "actors")
+            alive[i] = not term[i]
+        if not alive.any():
+            break
+    assert t > 20
+    eng.close()
+
+
+def test_raw_rgb_lookahead_dense_traffic():
+    """BASELINE configs[4] shape: raw (128, 128, 3) uint8 frames, lookahead_75 camera, 50 vehicles, continuous."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import load_shipped_pool, pack_pool
+    from oracle.env import OracleEnv
+
+    scenes = load_shipped_pool("rdm_dense_50")[:8]
+    n = len(scenes)
+    eng = E.Engine(n, obs_mode=E.OBS_RGB, action_mode=E.ACTION_CONTINUOUS, max_actors=50, anchor=(0.5, 0.75))
+    eng.upload_map(load_map())
+    eng.upload_pool(pack_pool(scenes))
+    oracles = [OracleEnv(load_map(), obs_mode="bev_raw", frame_stack=1, action_mode="continuous", anchor=(0.5, 0.75))
+               for _ in range(n)]
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    assert obs.shape == (n, 128, 128, 3) and obs.dtype == np.uint8
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i])[0])
+    rng = np.random.default_rng(6)
+    alive = np.ones(n, bool)
+    for t in range(50):
+        a = _rand_actions(rng, n)
+        a[:, 0] = np.clip(a[:, 0] + 0.3, 0, 1)
+        a[:, 2] *= 0.2
+        eng.step(torch.from_numpy(a).cuda())
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, hero = eng.terminated.cpu().numpy().astype(bool), eng.hero.cpu().numpy()
+        for i in range(n):
+            if not alive[i]:
+                continue
+            o, r, te, tr, _ = oracles[i].step(a[i])
+            e = oracles[i].sim.ego
+            assert np.allclose(hero[i][:4], [e.x, e.y, e.yaw, e.v], rtol=1e-9, atol=1e-9), (t, i)
+            assert abs(r - rew[i]) < 1e-9 and te == term[i], (t, i)
+            assert np.array_equal(obs[i], o[0]), (t, i, "rgb frame")   # bar: within 1 LSB; we get exact
+            alive[i] = not te
+    eng.close()
