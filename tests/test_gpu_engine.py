@@ -339,3 +339,67 @@ def test_raw_rgb_lookahead_dense_traffic():
             assert np.array_equal(obs[i], o[0]), (t, i, "rgb frame")   # bar: within 1 LSB; we get exact
             alive[i] = not te
     eng.close()
+
+
+def test_pose_drift_over_1000_steps():
+    """BASELINE north_star: poses within 1e-5 relative after 1000 steps on identical seeds and actions.
+    A route-following policy (Stanley steering + speed hold, computed on the oracle state) keeps three
+    16-vehicle random-traffic episodes alive for up to 1000 steps; the engine is free-running."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import load_shipped_pool, pack_pool
+    from oracle.env import OracleEnv
+
+    pool = load_shipped_pool("rdm_rt_medium_v1")
+    scenes = [pool[16], pool[19], pool[8]]
+    n = len(scenes)
+    eng = E.Engine(n, obs_mode=E.OBS_SEMANTIC, mask_mode="6-class", frame_stack=4, action_mode=E.ACTION_CONTINUOUS,
+                   max_actors=16, ring_budget_bytes=64 << 20)
+    eng.upload_map(load_map())
+    eng.upload_pool(pack_pool(scenes))
+    eng.keep_fov(True)
+    eng.reset(torch.arange(n, dtype=torch.int32))
+    oracles = [OracleEnv(load_map(), action_mode="continuous", obs_mode="bev_raw", frame_stack=1) for _ in range(n)]
+    for o, s in zip(oracles, scenes):
+        o.reset(s)
+
+    def policy(env, vt=2.8):
+        e = env.sim.ego
+        delta, _ = e.stanley()
+        steer_deg = float(np.clip(18.0 / (1.0 + 0.35 * abs(e.v)), 8.0, 18.0))
+        return np.array([np.clip(0.6 * (vt - e.v), 0, 1), np.clip(float(delta) / np.radians(steer_deg), -1, 1),
+                         np.clip(0.3 * (e.v - vt - 0.5), 0, 1)], dtype=np.float32)
+
+    alive = np.ones(n, bool)
+    worst = 0.0
+    steps_alive = np.zeros(n, int)
+    for t in range(1000):
+        a = np.stack([policy(o) if alive[i] else np.zeros(3, np.float32) for i, o in enumerate(oracles)])
+        eng.step(torch.from_numpy(a).cuda())
+        hero = eng.hero.cpu().numpy()
+        term = eng.terminated.cpu().numpy().astype(bool)
+        rew = eng.reward.cpu().numpy()
+        for i in range(n):
+            if not alive[i]:
+                continue
+            _, r, te, _, _ = oracles[i].step(a[i])
+            e = oracles[i].sim.ego
+            ref = np.array([e.x, e.y, e.yaw, e.v], dtype=np.float64)
+            rel = np.abs(hero[i, :4] - ref) / np.maximum(np.abs(ref), 1.0)
+            worst = max(worst, float(rel.max()))
+            assert rel.max() < 1e-7, (t, i, hero[i, :4], ref)
+            assert te == term[i] and abs(r - rew[i]) < 1e-9, (t, i)
+            steps_alive[i] += 1
+            alive[i] = not te
+        if t in (250, 999):
+            ego, act = eng.get_state(16)
+            fov = eng.fov().cpu().numpy()
+            for i in range(n):
+                if alive[i]:
+                    ref = np.array([[b.x, b.y, b.yaw, b.v] for b in oracles[i].sim.actors])
+                    assert np.allclose(act[i, :len(ref), :4], ref, rtol=1e-7, atol=1e-7), (t, i, "actors")
+                    assert np.array_equal(fov[i], oracles[i].render_index()), (t, i, "frame")
+    assert steps_alive.max() == 1000 and (steps_alive >= 900).sum() >= 2, steps_alive
+    print(f"max relative pose deviation over {steps_alive.tolist()} steps: {worst:.3e}")
+    eng.close()
