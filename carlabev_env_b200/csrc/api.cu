@@ -216,6 +216,7 @@ int cbev_destroy(cbev_handle e) {
   if (!e) return CBEV_OK;
   free_pool(e->pool);
   free_state(e->st);
+  dev_free(e->fov_mask);
   dev_free(e->map); dev_free(e->desc); dev_free(e->rects); dev_free(e->fov); dev_free(e->gstats);
   dev_free(e->h_reward_dev); dev_free(e->h_term_dev); dev_free(e->h_trunc_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }
@@ -423,6 +424,32 @@ int cbev_step_host(cbev_handle e, const void* actions_host, double* reward_host,
   CU_TRY(cudaMemcpyAsync(reward_host, e->h_reward_dev, N * 8, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaMemcpyAsync(terminated_host, e->h_term_dev, N, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaMemcpyAsync(truncated_host, e->h_trunc_dev, N, cudaMemcpyDeviceToHost, s));
+  return CBEV_OK;
+}
+
+int cbev_upload_fov_mask(cbev_handle e, const uint8_t* mask_host) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  CU_TRY(cudaDeviceSynchronize());
+  dev_free(e->fov_mask);
+  if (!mask_host) return CBEV_OK;
+  const size_t n = (size_t)e->cfg.fov_size * e->cfg.fov_size;
+  std::vector<uint8_t> m(n);
+  for (size_t i = 0; i < n; ++i) m[i] = mask_host[i] ? 0xff : 0x00;
+  return dev_upload(&e->fov_mask, m.data(), n);
+}
+
+int cbev_fuse(cbev_handle e, int32_t mode, float* out_dev, void* stream) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  if (!out_dev) { cbev_set_error("null output"); return CBEV_ERR_ARG; }
+  if (mode != CBEV_FUSE_VEHICLE_TEMPORAL && mode != CBEV_FUSE_VEHICLE_WEIGHTED) { cbev_set_error("bad fusion mode %d", mode); return CBEV_ERR_ARG; }
+  if (e->cfg.obs_mode != CBEV_OBS_SEMANTIC) { cbev_set_error("temporal_fusion_mode requires obs_mode='bev_semantic'"); return CBEV_ERR_ARG; }
+  if (e->cfg.frame_stack < 3) { cbev_set_error("temporal_fusion_mode requires frame_stack >= 3"); return CBEV_ERR_ARG; }
+  if (cbev_launch_fuse(e, mode, out_dev, (cudaStream_t)stream)) {
+    cbev_set_error("temporal_fusion_mode requires a semantic_mask_ch with a vehicle channel");
+    return CBEV_ERR_ARG;
+  }
+  CU_TRY(cudaGetLastError());
   return CBEV_OK;
 }
 

@@ -89,6 +89,7 @@ struct cbev_engine {
   int32_t* desc = nullptr;         // [N][CBEV_DESC_WORDS]
   uint32_t* rects = nullptr;       // [N][max_rects]
   uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)
+  uint8_t* fov_mask = nullptr;     // [S][S] 0x00 / 0xff corner mask (fov_masked) or null
   void* ring = nullptr;
   int64_t ring_bytes = 0, frame_bytes = 0;
   int32_t channels = 0;
@@ -112,3 +113,4 @@ void cbev_launch_reset(cbev_engine* e, const uint8_t* mask, const int32_t* scene
 void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, int lo, int hi, cudaStream_t s);
 int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int hi, cudaStream_t s);
 void cbev_set_error(const char* fmt, ...);
+int cbev_launch_fuse(cbev_engine* e, int32_t mode, float* out, cudaStream_t s);

@@ -77,6 +77,7 @@ struct RenderParams {
   const uint32_t* rects;
   int32_t max_rects;
   uint8_t* fov_out;  // [N][S][S] palette-index frames (nullable)
+  const uint8_t* fov_mask;  // [S][S] 0x00 / 0xff or null (fov_masked)
   void* ring;
 };
 
@@ -270,6 +271,15 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       }
     }
     __syncthreads();
+    // apply_mask (fov.py:96-99): opaque black corner triangles over the composed frame, before the ego is drawn
+    if (P.fov_mask != nullptr) {
+      for (int u = tid; u < S * S / 4; u += RT) {
+        const uint32_t mk = ((const uint32_t*)P.fov_mask)[u];
+        uint32_t* px = (uint32_t*)s_fov + u;
+        *px = (*px & ~mk) | ((CBEV_PAL_BLACK * 0x01010101u) & mk);
+      }
+      __syncthreads();
+    }
     // Hero.draw: 4x4 black square centred on the anchor (hero.py:26-32), clipped to the surface
     if (tid < 16) {
       const int x = ex0 + (tid & 3), y = ey0 + (tid >> 2);
@@ -393,6 +403,39 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   }
 }
 
+// ---- temporal fusion of the stacked masks (wrappers/rgb_to_semantic.py:152-193) ---------------------
+// One thread per float4 of one output plane; planes are gathered from the ring window.
+__global__ void __launch_bounds__(256)
+k_fuse(const float* __restrict__ ring, float* __restrict__ out, int N, int L, int C, int head, int veh, int mode) {
+  constexpr int HW4 = 96 * 96 / 4;
+  const int Cout = mode == CBEV_FUSE_VEHICLE_TEMPORAL ? C - 1 + 3 : C;
+  const long long total = (long long)N * Cout * HW4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % HW4);
+    const int c = (int)((i / HW4) % Cout);
+    const int env = (int)(i / ((long long)HW4 * Cout));
+    const float4* frame = (const float4*)ring + ((size_t)env * L + head) * C * HW4;  // newest frame
+    float4 v;
+    if (c < C - 1) {
+      const int src = c < veh ? c : c + 1;  // np.delete(current, vehicle_idx, axis=0)
+      v = frame[(size_t)src * HW4 + q];
+    } else if (mode == CBEV_FUSE_VEHICLE_TEMPORAL) {
+      const int age = c - (C - 1);          // history[::-1]: t, t-1, t-2
+      v = (frame - (size_t)age * C * HW4)[(size_t)veh * HW4 + q];
+    } else {
+      const float4 a = frame[(size_t)veh * HW4 + q];
+      const float4 b = (frame - (size_t)C * HW4)[(size_t)veh * HW4 + q];
+      const float4 d = (frame - (size_t)2 * C * HW4)[(size_t)veh * HW4 + q];
+      // float32: ((0 + 1.0 a) + 0.5 b) + 0.25 d, then clip to [0, 1]
+      v.x = fminf(fmaxf(__fadd_rn(__fadd_rn(a.x, __fmul_rn(0.5f, b.x)), __fmul_rn(0.25f, d.x)), 0.f), 1.f);
+      v.y = fminf(fmaxf(__fadd_rn(__fadd_rn(a.y, __fmul_rn(0.5f, b.y)), __fmul_rn(0.25f, d.y)), 0.f), 1.f);
+      v.z = fminf(fmaxf(__fadd_rn(__fadd_rn(a.z, __fmul_rn(0.5f, b.z)), __fmul_rn(0.25f, d.z)), 0.f), 1.f);
+      v.w = fminf(fmaxf(__fadd_rn(__fadd_rn(a.w, __fmul_rn(0.5f, b.w)), __fmul_rn(0.25f, d.w)), 0.f), 1.f);
+    }
+    st_f4((float*)((float4*)out + i), v.x, v.y, v.z, v.w);
+  }
+}
+
 bool g_tables_ready = false;
 
 void upload_tables() {
@@ -460,6 +503,7 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.rects = e->rects;
   P.max_rects = e->max_rects;
   P.fov_out = e->keep_fov ? e->fov : nullptr;
+  P.fov_mask = e->fov_mask;
   P.ring = e->ring;
   const int S = P.fov;
   size_t tile = (size_t)P.crop * P.box_w;
@@ -485,4 +529,19 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   }
   if (rc == 0) e->launches += 1;
   return rc;
+}
+
+int cbev_launch_fuse(cbev_engine* e, int32_t mode, float* out, cudaStream_t s) {
+  // vehicle channel index per mask mode (wrappers/rgb_to_semantic.py:6-62); binary / 2-class have none
+  static const int veh_of[6] = {-1, -1, 1, 2, 3, 3};
+  const int veh = veh_of[e->cfg.mask_mode];
+  if (veh < 0) return 1;
+  const int C = e->channels;
+  const int Cout = mode == CBEV_FUSE_VEHICLE_TEMPORAL ? C - 1 + 3 : C;
+  long long total = (long long)e->N * Cout * (96 * 96 / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_fuse<<<blocks, 256, 0, s>>>((const float*)e->ring, out, e->N, e->cfg.ring_slots, C, e->head, veh, mode);
+  e->launches += 1;
+  return 0;
 }

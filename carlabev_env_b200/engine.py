@@ -37,7 +37,7 @@ SG_MAX = 12
 EXPORTS = ("cbev_version", "cbev_last_error", "cbev_create", "cbev_destroy", "cbev_upload_map",
            "cbev_upload_scene_pool", "cbev_frame_bytes", "cbev_bind_obs_ring", "cbev_reset", "cbev_step",
            "cbev_step_host", "cbev_obs_head", "cbev_get_state", "cbev_set_ego_state", "cbev_copy_fov",
-           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov")
+           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse")
 
 
 class CbevConfig(C.Structure):
@@ -115,6 +115,8 @@ def load_library(build_if_missing: bool = True):
     lib.cbev_set_ego_state.argtypes = [_P, _P]
     lib.cbev_copy_fov.argtypes = [_P, _P, _P]
     lib.cbev_keep_fov.argtypes = [_P, C.c_int32]
+    lib.cbev_upload_fov_mask.argtypes = [_P, _P]
+    lib.cbev_fuse.argtypes = [_P, C.c_int32, _P, _P]
     lib.cbev_read_stats.argtypes = [_P, _P, C.c_int32, _P]
     lib.cbev_profile_enable.argtypes = [_P, C.c_int32]
     lib.cbev_profile_read.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -327,6 +329,27 @@ class Engine:
             ring = self.ring.view(N, L, *self.obs_hw)
             return ring[:, head - F + 1: head + 1]
         return self.ring.view(N, self.size, self.size, 3)
+
+    def upload_fov_mask(self, mask):
+        """mask: uint8 [S, S], non-zero = painted black (fov_masked); None removes it."""
+        if mask is None:
+            _check(self.lib, self.lib.cbev_upload_fov_mask(self.handle, None))
+            return
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert m.shape == (self.size, self.size)
+        _check(self.lib, self.lib.cbev_upload_fov_mask(self.handle, m.ctypes.data))
+
+    def fuse(self, mode: str):
+        """Temporal fusion of the current window: 'vehicle_temporal' -> [N, C+2, h, w], 'vehicle_weighted' -> [N, C, h, w]."""
+        code = {"vehicle_temporal": 1, "vehicle_weighted": 2}[mode]
+        cout = self.channels + 2 if code == 1 else self.channels
+        key = ("fuse", code)
+        buf = getattr(self, "_fuse_buf", {}).get(key)
+        if buf is None:
+            buf = self.torch.empty(self.N, cout, *self.obs_hw, dtype=self.torch.float32, device=self.device)
+            self._fuse_buf = {**getattr(self, "_fuse_buf", {}), key: buf}
+        _check(self.lib, self.lib.cbev_fuse(self.handle, code, buf.data_ptr(), self._stream()))
+        return buf
 
     def keep_fov(self, on=True):
         _check(self.lib, self.lib.cbev_keep_fov(self.handle, int(on)))

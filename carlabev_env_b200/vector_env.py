@@ -56,10 +56,7 @@ class CarlaBEVVectorEnv:
         self.num_envs = int(cfg.num_envs)
         self.to_numpy = to_numpy
         self.autoreset = autoreset
-        if env.temporal_fusion_mode != "stack":
-            raise NotImplementedError("temporal_fusion_mode != 'stack' is a SURVEY.md §8(f1) 'next' row")
-        if env.fov_masked:
-            raise NotImplementedError("fov_masked is a SURVEY.md §8(f1) 'next' row")
+        self.fusion = env.temporal_fusion_mode if env.obs_mode == "bev_semantic" else "stack"
         aspec = get_action_profile_spec(env.action_profile_id)
         rspec = get_reward_profile_spec(env.reward_profile_id)
         if env.obs_mode == "bev_semantic":
@@ -86,6 +83,10 @@ class CarlaBEVVectorEnv:
         self.cls_map = load_town01_map()
         self.engine.upload_map(self.cls_map)
         self.pad = self._crop_size(env)
+        if env.fov_masked:  # FovRenderSpec(mask_fov=True), envs/world.py:39-46
+            from .fovmask import corner_mask
+
+            self.engine.upload_fov_mask(corner_mask(env.size, 0.5))
         if self._scenes:
             self.engine.upload_pool(pack_pool(self._scenes))
         # spaces (envs/spaces.py:27-61 + wrappers)
@@ -97,7 +98,9 @@ class CarlaBEVVectorEnv:
         F = env.frame_stack
         if obs_mode == E.OBS_SEMANTIC:
             C = E.MASK_CHANNELS[env.semantic_mask_ch]
-            self.single_observation_space = Box(0.0, 1.0, (F * C, *env.obs_size), np.float32)
+            # FlattenStackedFrames | VehicleTemporalFusionWrapper | WeightedVehicleHistoryWrapper (envs/__init__.py:73-81)
+            c_out = {"stack": F * C, "vehicle_temporal": C - 1 + 3, "vehicle_weighted": C}[self.fusion]
+            self.single_observation_space = Box(0.0, 1.0, (c_out, *env.obs_size), np.float32)
         elif obs_mode == E.OBS_GRAY:
             self.single_observation_space = Box(0, 255, (F, *env.obs_size), np.uint8)
         else:
@@ -195,6 +198,8 @@ class CarlaBEVVectorEnv:
             raise RuntimeError("the first reset must cover every env")
         m = None if (mask is None or mask.all()) else mask
         obs = self.engine.reset(ids, m)
+        if self.fusion != "stack":
+            obs = self.engine.fuse(self.fusion)
         sel = slice(None) if m is None else t.as_tensor(m, device=self.device)
         self._ep_return[sel] = 0.0
         self._ep_len[sel] = 0
@@ -219,7 +224,7 @@ class CarlaBEVVectorEnv:
             a = t.as_tensor(actions, device=self.device).to(t.float32).contiguous().view(self.num_envs, 3)
         eng = self.engine
         eng.step(a)
-        obs = eng.obs()
+        obs = eng.obs() if self.fusion == "stack" else eng.fuse(self.fusion)
         rew, term, trunc = eng.reward, eng.terminated.bool(), eng.truncated.bool()
         self._ep_return += rew
         self._ep_len += 1

@@ -232,6 +232,20 @@ int cbev_step(cbev_handle h, const void* actions_dev, const cbev_step_out* out, 
 int cbev_step_host(cbev_handle h, const void* actions_host, double* reward_host, uint8_t* terminated_host,
                    uint8_t* truncated_host, void* stream);
 
+/* fov_masked (envs/fov.py:46-68, 96-99): static corner mask blitted over the composed frame before the ego
+ * square is drawn.  mask_host: uint8[S*S], non-zero = pixel is painted black; NULL removes the mask.  Synchronous. */
+int cbev_upload_fov_mask(cbev_handle h, const uint8_t* mask_host);
+
+/* Temporal fusion of the stacked semantic observation (wrappers/rgb_to_semantic.py:152-193, 275-332):
+ *   CBEV_FUSE_VEHICLE_TEMPORAL: current channels without the vehicle channel + vehicle_t, vehicle_t-1, vehicle_t-2
+ *                               -> float32 [N][C-1+3][oh][ow]
+ *   CBEV_FUSE_VEHICLE_WEIGHTED: current channels without vehicle + clip(1.0 v_t + 0.5 v_t-1 + 0.25 v_t-2, 0, 1)
+ *                               -> float32 [N][C][oh][ow]
+ * Reads the current window of the ring, writes the caller-owned `out_dev`. */
+#define CBEV_FUSE_VEHICLE_TEMPORAL 1
+#define CBEV_FUSE_VEHICLE_WEIGHTED 2
+int cbev_fuse(cbev_handle h, int32_t mode, float* out_dev, void* stream);
+
 /* Ring head: observation of env e = slots [head - frame_stack + 1, head] of its ring row. */
 int cbev_obs_head(cbev_handle h, int32_t* head);
 

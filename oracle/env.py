@@ -50,10 +50,12 @@ def unpack_pool(npz):
 class OracleEnv:
     def __init__(self, cls_map, *, obs_mode="bev_semantic", semantic_mask_ch="6-class", frame_stack=4,
                  obs_size=(96, 96), action_mode="discrete", action_profile="discrete9_v1", reward_mode="carl",
-                 reward_params=None, anchor=(0.5, 0.5), size=128):
+                 reward_params=None, anchor=(0.5, 0.5), size=128, fov_masked=False, temporal_fusion_mode="stack"):
         self.cls_map = np.ascontiguousarray(cls_map, dtype=np.uint8)
         self.geom = raster.FovGeometry(size, anchor[0], anchor[1])
         self.obs_mode = obs_mode
+        self.fov_mask = raster.corner_mask(size, 0.5) if fov_masked else None
+        self.fusion = temporal_fusion_mode
         self.mask_mode = semantic_mask_ch
         self.frame_stack = int(frame_stack)
         self.obs_size = tuple(obs_size)
@@ -71,7 +73,7 @@ class OracleEnv:
         s = self.sim
         theta = 0.0 if reset_frame else s.ego.yaw  # world.py:92-100: reset draws with _theta = 0 and no actors
         rects = raster.draw_list(s, with_actors=not reset_frame)
-        return raster.render_fov(self.cls_map, self.geom, s.ego.x, s.ego.y, theta, rects)
+        return raster.render_fov(self.cls_map, self.geom, s.ego.x, s.ego.y, theta, rects, self.fov_mask)
 
     def _wrap_frame(self, idx_img):
         rgb = raster.fov_rgb(idx_img)
@@ -85,6 +87,10 @@ class OracleEnv:
 
     def _stacked(self):
         st = np.stack(list(self.frames))
+        if self.obs_mode == "bev_semantic" and self.fusion == "vehicle_temporal":
+            return raster.fuse_vehicle_temporal(st, self.mask_mode)
+        if self.obs_mode == "bev_semantic" and self.fusion == "vehicle_weighted":
+            return raster.fuse_vehicle_weighted(st, self.mask_mode)
         if self.obs_mode == "bev_semantic":
             return st.reshape(-1, *st.shape[2:]).astype(np.float32)  # FlattenStackedFrames
         return st

@@ -262,7 +262,10 @@ def run_case(name, env_kwargs, reset_options, actions, frame_every=1, obs_every=
         episode_infos=np.array(json.dumps({str(k): v for k, v in ep_infos.items()}, default=str)),
         env_kwargs=np.array(json.dumps(env_kwargs)),
     )
-    if out["obs_full"].dtype == np.float32:  # 0/1 masks: store bit-packed
+    if out["obs_full"].dtype == np.float32 and not np.isin(out["obs_full"], (0.0, 1.0)).all():
+        out["obs_full"] = out["obs_full"].astype(np.float16)   # weighted history: multiples of 0.25, exact in f16
+        out["reset_obs"] = out["reset_obs"].astype(np.float16)
+    elif out["obs_full"].dtype == np.float32:  # 0/1 masks: store bit-packed
         out["obs_full"] = np.packbits(out["obs_full"].astype(bool), axis=-1)
         out["reset_obs"] = np.packbits(out["reset_obs"].astype(bool), axis=-1)
         out["obs_packed"] = np.array(True)
@@ -358,6 +361,25 @@ def rdm_rgb_lookahead():
     run_case("rdm_rgb_lookahead",
              dict(obs_mode="bev_rgb", action_mode="continuous", ego_anchor_x_frac=0.5, ego_anchor_y_frac=0.75),
              opts, acts, frame_every=3)
+
+
+@case
+def fusion_temporal_masked():
+    # vehicle_temporal fusion + fov_masked corner mask, lead_brake level 3 (vehicles in view)
+    acts = cont_actions(11, 150, gas_bias=0.1)
+    opts = lambda ep: dict(scene="lead_brake", level=3, scene_seed=300 + ep)  # noqa: E731
+    run_case("fusion_temporal_masked",
+             dict(obs_mode="bev_semantic", action_mode="continuous", temporal_fusion_mode="vehicle_temporal",
+                  fov_masked=True), opts, acts, frame_every=3, obs_every=10)
+
+
+@case
+def fusion_weighted():
+    acts = cont_actions(12, 150, gas_bias=0.1)
+    opts = lambda ep: dict(scene="lead_brake", level=2 + ep % 2, scene_seed=400 + ep)  # noqa: E731
+    run_case("fusion_weighted",
+             dict(obs_mode="bev_semantic", action_mode="continuous", temporal_fusion_mode="vehicle_weighted",
+                  semantic_mask_ch="5-class"), opts, acts, frame_every=3, obs_every=10)
 
 
 if __name__ == "__main__":

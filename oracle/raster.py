@@ -119,7 +119,57 @@ def draw_list(sim, with_actors=True):
     return rects
 
 
-def render_fov(cls_map, geom: FovGeometry, x, y, theta, rects):
+def _fill_polygon(mask, points):
+    """pygame 2.6.1 draw.c:draw_fillpoly restated (scan-line fill incl. edge pixels; parity unpinned)."""
+    h, w = mask.shape
+    xs = [int(p[0]) for p in points]
+    ys = [int(p[1]) for p in points]
+    n = len(points)
+    miny, maxy = min(ys), max(ys)
+
+    def hline(yy, x1, x2):
+        if 0 <= yy < h:
+            lo, hi = max(min(x1, x2), 0), min(max(x1, x2), w - 1)
+            if hi >= lo:
+                mask[yy, lo:hi + 1] = True
+
+    for yy in range(miny, maxy + 1):
+        inter = []
+        for i in range(n):
+            ip = i - 1 if i else n - 1
+            y1, y2 = ys[ip], ys[i]
+            if y1 < y2:
+                x1, x2 = xs[ip], xs[i]
+            elif y1 > y2:
+                y2, y1 = ys[ip], ys[i]
+                x2, x1 = xs[ip], xs[i]
+            else:
+                continue
+            if (y1 <= yy < y2) or (yy == maxy and y2 == maxy):
+                v = np.float32((yy - y1) * (x2 - x1)) / np.float32(y2 - y1)
+                v = math.floor(v) if len(inter) % 2 == 0 else math.ceil(v)
+                inter.append(int(v) + x1)
+        inter.sort()
+        for i in range(0, len(inter) - 1, 2):
+            hline(yy, inter[i], inter[i + 1])
+    for i in range(n):
+        ip = i - 1 if i else n - 1
+        if miny < ys[i] < maxy and ys[ip] == ys[i]:
+            hline(ys[i], xs[i], xs[ip])
+
+
+def corner_mask(size=128, mask_frac=0.5):
+    """FovRenderer._build_mask_surface, fov.py:46-68: True where apply_mask paints the frame black."""
+    m = int(size * mask_frac)
+    s = size
+    mask = np.zeros((s, s), dtype=bool)
+    for pts in ([(0, 0), (m, 0), (0, m)], [(s, 0), (s - m, 0), (s, m)], [(0, s), (0, s - m), (m, s)],
+                [(s, s), (s - m, s), (s, s - m)]):
+        _fill_polygon(mask, pts)
+    return mask
+
+
+def render_fov(cls_map, geom: FovGeometry, x, y, theta, rects, fov_mask=None):
     """128x128 palette-index image of the ego-centred, ego-aligned field of view.
 
     world.py:137-157 (draw_fov) = crop (fov.py:70-82) -> rotate (fov.py:84-88) -> compose on
@@ -168,6 +218,8 @@ def render_fov(cls_map, geom: FovGeometry, x, y, theta, rects):
     val = tile[np.clip(sy, 0, crop - 1), np.clip(sx, 0, crop - 1)]
     val = np.where(oob, tile[0, 0], val)           # background = crop's first pixel (transform.c)
     out = np.where(in_rot, val, PAL_BLACK).astype(np.uint8)
+    if fov_mask is not None:                       # apply_mask before the ego is drawn (world.py:150-156)
+        out[fov_mask] = PAL_BLACK
     ax, ay = geom.anchor
     out[max(ay - 2, 0):ay + 2, max(ax - 2, 0):ax + 2] = PAL_BLACK   # ego square, rect centred on the anchor
     return out
@@ -233,3 +285,26 @@ def semantic_masks(rgb, mode="6-class"):
 def grayscale(rgb):
     """gymnasium GrayscaleObservation (envs/__init__.py:70)."""
     return np.sum(np.multiply(rgb, np.array([0.2125, 0.7154, 0.0721])), axis=-1).astype(np.uint8)
+
+
+VEHICLE_CHANNEL = {m: ch.index("vehicle") for m, ch in MASK_CHANNELS.items() if "vehicle" in ch}
+
+
+def fuse_vehicle_temporal(stacked, mode, history_frames=3):
+    """fuse_vehicle_temporal_channels, wrappers/rgb_to_semantic.py:152-168; stacked is (F, C, H, W)."""
+    v = VEHICLE_CHANNEL[mode]
+    history = stacked[-history_frames:]
+    current = history[-1]
+    return np.concatenate([np.delete(current, v, axis=0), history[::-1, v]], axis=0).astype(np.float32)
+
+
+def fuse_vehicle_weighted(stacked, mode, weights=(1.0, 0.5, 0.25)):
+    """fuse_weighted_vehicle_history, wrappers/rgb_to_semantic.py:171-193."""
+    v = VEHICLE_CHANNEL[mode]
+    history = stacked[-len(weights):][::-1]
+    current = history[0]
+    acc = np.zeros_like(current[v], dtype=np.float32)
+    for frame, w in zip(history, weights):
+        acc += w * frame[v]
+    acc = np.clip(acc, 0.0, 1.0)
+    return np.concatenate([np.delete(current, v, axis=0), acc[None]], axis=0).astype(np.float32)

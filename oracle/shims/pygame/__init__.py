@@ -359,13 +359,9 @@ class _DrawModule:
                 else:
                     continue
                 if (y >= y1 and y < y2) or (y == maxy and y2 == maxy):
-                    # C integer division truncates toward zero
-                    num = (y - y1) * (x2 - x1)
-                    den = y2 - y1
-                    q = abs(num) // abs(den)
-                    if (num < 0) != (den < 0):
-                        q = -q
-                    inter.append(q + x1)
+                    v = _np.float32((y - y1) * (x2 - x1)) / _np.float32(y2 - y1)
+                    v = _math.floor(v) if len(inter) % 2 == 0 else _math.ceil(v)
+                    inter.append(int(v) + x1)
             inter.sort()
             for i in range(0, len(inter) - 1, 2):
                 hline(y, inter[i], inter[i + 1])

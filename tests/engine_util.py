@@ -36,6 +36,12 @@ def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb
     eng.upload_map(load_map())
     eng.upload_pool(g.pool)
     eng.keep_fov(True)
+    if kw.get("fov_masked"):
+        from carlabev_env_b200.fovmask import corner_mask
+
+        eng.upload_fov_mask(corner_mask(128, 0.5))
+    fusion = kw.get("temporal_fusion_mode", "stack")
+    eng.current_obs = (lambda: eng.obs()) if fusion == "stack" else (lambda: eng.fuse(fusion))
     return eng
 
 
@@ -62,7 +68,8 @@ def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12):
     for t in range(g.T):
         if t in resets:
             ids = torch.tensor([resets[t]], dtype=torch.int32)
-            obs = eng.reset(ids, None if first else np.array([True]))
+            eng.reset(ids, None if first else np.array([True]))
+            obs = eng.current_obs()
             first = False
             fr = eng.fov()[0].cpu().numpy()
             if not np.array_equal(fr, g["reset_frames"][ri]):
@@ -111,7 +118,7 @@ def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12):
             if not np.array_equal(fr, g["frames"][fsteps[t]]):
                 d = np.argwhere(fr != g["frames"][fsteps[t]])
                 bad.append(f"t={t} frame differs in {len(d)} px, first {d[:3].tolist()}")
-        obs = eng.obs()[0].cpu().numpy()
+        obs = eng.current_obs()[0].cpu().numpy()
         if crc(obs) != int(g["obs_crc"][t]):
             msg = f"t={t} obs crc differs"
             if t in osteps:

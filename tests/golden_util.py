@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 ALL_CASES = ("lead_brake_continuous", "rdm_medium_discrete", "jaywalk_levels", "jaywalk_drive", "red_light_runner",
-             "rdm_shaping_discrete13", "rdm_rgb_lookahead")
+             "rdm_shaping_discrete13", "rdm_rgb_lookahead", "fusion_temporal_masked", "fusion_weighted")
 
 
 def load_map():
@@ -44,12 +44,16 @@ class Golden:
             action_profile=kw.get("action_profile_id") or ("continuous_gsb_v1" if action_mode == "continuous" else "discrete9_v1"),
             reward_mode=kw.get("reward_mode", "carl"),
             anchor=(kw.get("ego_anchor_x_frac", 0.5), kw.get("ego_anchor_y_frac", 0.5)),
+            fov_masked=kw.get("fov_masked", False),
+            temporal_fusion_mode=kw.get("temporal_fusion_mode", "stack"),
         )
 
     def full_obs(self, key="obs_full"):
         o = self.d[key]
         if "obs_packed" in self.d:
             o = np.unpackbits(o, axis=-1)[..., :96].astype(np.float32)
+        elif o.dtype == np.float16:
+            o = o.astype(np.float32)
         return o
 
 
