@@ -297,9 +297,10 @@ def run_ours(args):
     value = world * N * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers (H2D actions, D2H reward/flags every step) ----
-    rew_h = torch.zeros(N, dtype=torch.float64).pin_memory()
-    term_h = torch.zeros(N, dtype=torch.uint8).pin_memory()
-    trunc_h = torch.zeros(N, dtype=torch.uint8).pin_memory()
+    out_h = torch.zeros(N * 10, dtype=torch.uint8).pin_memory()   # reward f64[N] | terminated u8[N] | truncated u8[N]
+    rew_h = out_h[: N * 8].view(torch.float64)
+    term_h = out_h[N * 8: N * 9]
+    trunc_h = out_h[N * 9:]
     e2e_steps = args.steps
     for i in range(min(3, args.warmup)):
         eng.step_host(acts_host[i % bank], rew_h, term_h, trunc_h)

@@ -202,9 +202,9 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   rc |= dev_alloc(&e->desc, N * CBEV_DESC_WORDS);
   rc |= dev_alloc(&e->fov, N * (size_t)cfg->fov_size * cfg->fov_size);
   rc |= dev_alloc(&e->gstats, (size_t)CBEV_STATS_FIELDS);
-  rc |= dev_alloc(&e->h_reward_dev, N);
-  rc |= dev_alloc(&e->h_term_dev, N);
-  rc |= dev_alloc(&e->h_trunc_dev, N);
+  rc |= dev_alloc((uint8_t**)&e->h_reward_dev, N * 10);  // one block: reward f64[N] | terminated u8[N] | truncated u8[N]
+  e->h_term_dev = (uint8_t*)e->h_reward_dev + N * 8;
+  e->h_trunc_dev = e->h_term_dev + N;
   rc |= dev_alloc((uint8_t**)&e->h_actions_dev, N * 16);
   if (rc) { cbev_destroy(e); return rc; }
   cudaMemset(e->st.scene, 0xff, N * sizeof(int32_t));
@@ -218,7 +218,7 @@ int cbev_destroy(cbev_handle e) {
   free_state(e->st);
   dev_free(e->fov_mask);
   dev_free(e->map); dev_free(e->desc); dev_free(e->rects); dev_free(e->fov); dev_free(e->gstats);
-  dev_free(e->h_reward_dev); dev_free(e->h_term_dev); dev_free(e->h_trunc_dev);
+  dev_free(e->h_reward_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }
   dev_free(e->all_scene_ids);
   if (e->prof_ev) {
@@ -421,9 +421,14 @@ int cbev_step_host(cbev_handle e, const void* actions_host, double* reward_host,
   out.truncated = e->h_trunc_dev;
   rc = cbev_step(e, e->h_actions_dev, &out, stream);
   if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(reward_host, e->h_reward_dev, N * 8, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaMemcpyAsync(terminated_host, e->h_term_dev, N, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaMemcpyAsync(truncated_host, e->h_trunc_dev, N, cudaMemcpyDeviceToHost, s));
+  if (terminated_host == (uint8_t*)reward_host + N * 8 && truncated_host == terminated_host + N) {
+    // the caller laid the three outputs out back to back: one D2H copy instead of three
+    CU_TRY(cudaMemcpyAsync(reward_host, e->h_reward_dev, N * 10, cudaMemcpyDeviceToHost, s));
+  } else {
+    CU_TRY(cudaMemcpyAsync(reward_host, e->h_reward_dev, N * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(terminated_host, e->h_term_dev, N, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(truncated_host, e->h_trunc_dev, N, cudaMemcpyDeviceToHost, s));
+  }
   return CBEV_OK;
 }
 

@@ -80,19 +80,20 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
 
 // calc_target_index (stanley_controller.py:100-117): global argmin of the front-axle distance,
 // first minimum wins.  Warp-cooperative; returns the same idx in every lane.
+template <int G>
 __device__ int warp_nearest(double fx, double fy, const double* __restrict__ cx, const double* __restrict__ cy, int n,
-                            int lane) {
+                            int lane, unsigned GM) {
   double best = INFINITY;
   int bi = 0x7fffffff;
-  for (int i = lane; i < n; i += 32) {
+  for (int i = lane; i < n; i += G) {
     double dx = fx - cx[i], dy = fy - cy[i];
     double d = dx * dx + dy * dy;
     if (d < best) { best = d; bi = i; }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ob = __shfl_xor_sync(FULL, best, o);
-    int oi = __shfl_xor_sync(FULL, bi, o);
+  for (int o = G / 2; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(GM, best, o);
+    int oi = __shfl_xor_sync(GM, bi, o);
     if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
   return bi;
@@ -191,7 +192,8 @@ __device__ __forceinline__ bool pack_rect(int rx, int ry, int rw, int rh, int pa
 // ---- reset ------------------------------------------------------------------------------------
 // CarlaBEV.reset with a pool scene: Scene.load_scene / reset_all / reward_fn.reset / stats.reset
 // (scenes/scene.py:41-88, actors/actor.py:86-108, carl_reward_fn.py:121-134, stats.py:104-105)
-__device__ void reset_env(const SimParams& P, const PoolDev& pool, const EnvState& st, int env, int scene, int lane) {
+__device__ void reset_env(const SimParams& P, const PoolDev& pool, const EnvState& st, int env, int scene, int lane,
+                          int stride = 32) {
   const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
   const int r0 = pool.ego_off[scene], nt = pool.ego_off[scene + 1] - r0;
   if (lane == 0) {
@@ -222,7 +224,7 @@ __device__ void reset_env(const SimParams& P, const PoolDev& pool, const EnvStat
     double* sa = st.stats + (size_t)env * S_SLOTS;
     for (int k = 0; k < S_SLOTS; ++k) sa[k] = 0.0;
   }
-  for (int a = lane; a < A; a += 32) {
+  for (int a = lane; a < A; a += stride) {
     size_t o = (size_t)env * P.max_actors + a;
     const double* s0 = pool.act_state0 + (size_t)(A0 + a) * 4;
     st.ax[o] = s0[0];
@@ -342,13 +344,22 @@ __device__ void start_retreat(const PoolDev& pool, double* rbuf, int32_t* rn, in
 }
 
 // ---- the step kernel ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, CBEV_SIM_BLOCKS_PER_SM)
+// G lanes cooperate on one environment (32 / G environments per warp).  The ego / reward arithmetic is scalar and
+// runs uniformly on the G lanes of a group, so a smaller G wastes less of the fp64 pipe; G = 32 is used when scenes
+// carry many actors (lanes = actors), G = 8 for the scripted scenarios (<= 8 actors).
+template <int G>
+__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, G == 32 ? CBEV_SIM_BLOCKS_PER_SM : 3)
 k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, cbev_step_out out,
       int32_t* __restrict__ desc, uint32_t* __restrict__ rects, double* __restrict__ gstats) {
-  __shared__ double s_hero[CBEV_WARPS_PER_BLOCK][CBEV_HERO_FIELDS];
+  constexpr int EPW = 32 / G;  // environments per warp
+  __shared__ double s_hero[CBEV_WARPS_PER_BLOCK][EPW][CBEV_HERO_FIELDS];
   const int warp = threadIdx.x >> 5;
-  const int env = P.env_lo + blockIdx.x * CBEV_WARPS_PER_BLOCK + warp;
-  const int lane = threadIdx.x & 31;
+  const int wl = threadIdx.x & 31;
+  const int lane = wl & (G - 1);   // lane within the environment's group
+  const int gb = wl & ~(G - 1);    // first warp lane of the group
+  const int grp = wl / G;
+  const unsigned GM = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gb);
+  const int env = P.env_lo + (blockIdx.x * CBEV_WARPS_PER_BLOCK + warp) * EPW + grp;
   if (env >= P.env_hi) return;
   int32_t* d = desc + (size_t)env * CBEV_DESC_WORDS;
   uint32_t* rl = rects + (size_t)env * P.max_rects;
@@ -358,8 +369,8 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     int ep = st.episode[env];
     uint64_t h = splitmix64(P.seed + (uint64_t)env * 0x9E3779B97F4A7C15ull + (uint64_t)ep * 0xD1B54A32D192ED03ull);
     int scene = (int)(h % (uint64_t)pool.n_scenes);
-    __syncwarp();
-    reset_env(P, pool, st, env, scene, lane);
+    __syncwarp(GM);
+    reset_env(P, pool, st, env, scene, lane, G);
     if (lane == 0) {
       const double* s0 = pool.ego_state0 + (size_t)scene * 4;
       write_desc_header(P, d, s0[0], s0[1], 0.0, 0, 1);
@@ -411,7 +422,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
   {
     double sn, cs;
     sincos(e.yaw, &sn, &cs);
-    int idx = warp_nearest(e.x + WB * cs, e.y + WB * sn, ecx, ecy, nt, lane);
+    int idx = warp_nearest<G>(e.x + WB * cs, e.y + WB * sn, ecx, ecy, nt, lane, GM);
     if (tidx < idx) tidx = idx;  // stanley_controller.py:76-77
   }
   double acc_val = gas > 0.0f ? (double)__fmul_rn(gas, 8.0f) : 0.0;
@@ -474,7 +485,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     hvx = e.v * cs; hvy = e.v * sn;                 // compute_ttc (px units)
     hvx_m = (e.v * MPP) * cs; hvy_m = (e.v * MPP) * sn;  // compute_ttc_raw (metres)
   }
-  for (int base = 0; base < A; base += 32) {
+  for (int base = 0; base < A; base += G) {
     const int a = base + lane;
     const bool has = a < A;
     const int ga = A0 + (has ? a : 0);
@@ -582,15 +593,15 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
       fx = b.x + WB * cs; fy = b.y + WB * sn;
     }
     int my_idx = 0;
-    unsigned am = __ballot_sync(FULL, active);
+    unsigned am = __ballot_sync(GM, active) >> gb;
     while (am) {
       int src = __ffs(am) - 1;
       am &= am - 1;
-      double bfx = __shfl_sync(FULL, fx, src), bfy = __shfl_sync(FULL, fy, src);
-      unsigned long long pcx = __shfl_sync(FULL, (unsigned long long)cxp, src);
-      unsigned long long pcy = __shfl_sync(FULL, (unsigned long long)cyp, src);
-      int bn = __shfl_sync(FULL, np, src);
-      int idx = warp_nearest(bfx, bfy, (const double*)pcx, (const double*)pcy, bn, lane);
+      double bfx = __shfl_sync(GM, fx, gb + src), bfy = __shfl_sync(GM, fy, gb + src);
+      unsigned long long pcx = __shfl_sync(GM, (unsigned long long)cxp, gb + src);
+      unsigned long long pcy = __shfl_sync(GM, (unsigned long long)cyp, gb + src);
+      int bn = __shfl_sync(GM, np, gb + src);
+      int idx = warp_nearest<G>(bfx, bfy, (const double*)pcx, (const double*)pcy, bn, lane, GM);
       if (lane == src) my_idx = idx;
     }
     if (active) {
@@ -627,14 +638,14 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
       near = dcx * dcx + dcy * dcy < 35 * 35;  // math.hypot(ints) < min_dist
       coll = overlap(hx, hy, 4, rx, ry, size);
     }
-    unsigned cm = __ballot_sync(FULL, coll);
+    unsigned cm = __ballot_sync(GM, coll) >> gb;
     if (cm) {
       int src = 31 - __clz(cm);  // last colliding actor in iteration order wins
-      int k = __shfl_sync(FULL, kind, src);
+      int k = __shfl_sync(GM, kind, gb + src);
       hit = k == 0 ? HIT_VEHICLE : HIT_PEDESTRIAN;
       hit_id = k;
     }
-    n_nearby += __popc(__ballot_sync(FULL, near));
+    n_nearby += __popc(__ballot_sync(GM, near));
     if (near) {
       double sn, cs;
       sincos(b.yaw, &sn, &cs);
@@ -655,16 +666,16 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     uint32_t packed = 0;
     bool vis = has && pack_rect(rx, ry, size, size, kind == 0 ? CBEV_PAL_VEHICLE : CBEV_PAL_PEDESTRIAN, xmin, ymin,
                                 crop, packed);
-    unsigned vm = __ballot_sync(FULL, vis);
+    unsigned vm = __ballot_sync(GM, vis) >> gb;
     if (vis) rl[nrects + __popc(vm & ((1u << lane) - 1u))] = packed;
     nrects += __popc(vm);
   }
 #pragma unroll
-  for (int o2 = 16; o2 > 0; o2 >>= 1) min_ttc = fmin(min_ttc, __shfl_xor_sync(FULL, min_ttc, o2));
+  for (int o2 = G / 2; o2 > 0; o2 >>= 1) min_ttc = fmin(min_ttc, __shfl_xor_sync(GM, min_ttc, o2));
 
   // ---- targets: draw (visible at draw time), then consume on overlap (target.py:37-50) ----------------
   unsigned long long tvis = st.tgt_vis[env];
-  for (int base = 0; base < nt; base += 32) {
+  for (int base = 0; base < nt; base += G) {
     int i = base + lane;
     bool has = i < nt && ((tvis >> i) & 1ull);
     int size = (i == nt - 1) ? 4 : 2;  // scenes/utils.py:114-122
@@ -675,11 +686,11 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     }
     uint32_t packed = 0;
     bool vis = has && pack_rect(tx, ty, size, size, CBEV_PAL_ROUTE, xmin, ymin, crop, packed);
-    unsigned vm = __ballot_sync(FULL, vis);
+    unsigned vm = __ballot_sync(GM, vis) >> gb;
     if (vis) rl[nrects + __popc(vm & ((1u << lane) - 1u))] = packed;
     nrects += __popc(vm);
     bool coll = has && overlap(hx, hy, 4, tx, ty, size);
-    unsigned cm = __ballot_sync(FULL, coll);
+    unsigned cm = __ballot_sync(GM, coll) >> gb;
     if (cm) {
       tvis &= ~((unsigned long long)cm << base);
       hit = HIT_TARGET;
@@ -689,7 +700,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
   // ---- traffic lights: drawn without the padding offset (traffic_light.py:81-90, quirk C-4) ----------
   {
     const int t0 = pool.tl_off[scene], ntl = pool.tl_off[scene + 1] - t0;
-    for (int base = 0; base < ntl; base += 32) {
+    for (int base = 0; base < ntl; base += G) {
       int i = base + lane;
       uint32_t packed = 0;
       bool vis = false;
@@ -697,7 +708,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
         const int32_t* r = pool.tl_rect + (size_t)(t0 + i) * 4;
         vis = pack_rect(r[0], r[1], r[2], r[3], pool.tl_color[t0 + i], xmin, ymin, crop, packed);
       }
-      unsigned vm = __ballot_sync(FULL, vis);
+      unsigned vm = __ballot_sync(GM, vis) >> gb;
       if (vis) rl[nrects + __popc(vm & ((1u << lane) - 1u))] = packed;
       nrects += __popc(vm);
     }
@@ -763,7 +774,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
       const double* qc = pool.rew_cum + q0;
       double best = 1e9;
       int bi = 0x7fffffff;
-      for (int i = lane; i + 1 < nq; i += 32) {
+      for (int i = lane; i + 1 < nq; i += G) {
         double Ax = qx[i], Ay = qy[i];
         int abx = qx[i + 1] - qx[i], aby = qy[i + 1] - qy[i];
         double tt = ((e.x - Ax) * (double)abx + (e.y - Ay) * (double)aby) / ((double)(abx * abx + aby * aby) + 1e-9);
@@ -773,9 +784,9 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
         if (dist < best) { best = dist; bi = i; }
       }
 #pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) {
-        double ob = __shfl_xor_sync(FULL, best, o2);
-        int oi = __shfl_xor_sync(FULL, bi, o2);
+      for (int o2 = G / 2; o2 > 0; o2 >>= 1) {
+        double ob = __shfl_xor_sync(GM, best, o2);
+        int oi = __shfl_xor_sync(GM, bi, o2);
         if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
       double s_t = 0.0;
@@ -910,7 +921,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     }
     write_desc_header(P, d, e.x, e.y, e.yaw, nrects, 0);
     if (out.hero) {
-      double* hb = s_hero[warp];
+      double* hb = s_hero[warp][grp];
       hb[CBEV_H_X] = e.x; hb[CBEV_H_Y] = e.y; hb[CBEV_H_YAW] = e.yaw; hb[CBEV_H_V] = e.v;
       hb[CBEV_H_X1] = e.x1; hb[CBEV_H_Y1] = e.y1; hb[CBEV_H_YAW1] = e.yaw1; hb[CBEV_H_V1] = e.v1;
       hb[CBEV_H_DIST2WP] = dist2wp; hb[CBEV_H_SP_X] = ecx[tidx]; hb[CBEV_H_SP_Y] = ecy[tidx];
@@ -925,10 +936,9 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
       hb[CBEV_H_DIST2GOAL] = d2g; hb[CBEV_H_T] = t_sim; hb[CBEV_H_SCENE] = (double)scene;
     }
   }
-  __syncwarp();
+  __syncwarp(GM);
   if (out.hero) {
-    static_assert(CBEV_HERO_FIELDS == 32, "hero block is written one field per lane");
-    out.hero[(size_t)env * CBEV_HERO_FIELDS + lane] = s_hero[warp][lane];
+    for (int f = lane; f < CBEV_HERO_FIELDS; f += G) out.hero[(size_t)env * CBEV_HERO_FIELDS + f] = s_hero[warp][grp][f];
   }
 }
 
@@ -971,7 +981,14 @@ void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* o
   SimParams P = make_params(e);
   P.env_lo = lo;
   P.env_hi = hi;
-  int blocks = (hi - lo + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
-  k_sim<<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->gstats);
+  if (e->pool.max_actors <= 8) {
+    constexpr int G = 8;
+    int per_block = CBEV_WARPS_PER_BLOCK * (32 / G);
+    int blocks = (hi - lo + per_block - 1) / per_block;
+    k_sim<G><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->gstats);
+  } else {
+    int blocks = (hi - lo + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
+    k_sim<32><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->gstats);
+  }
   e->launches += 1;
 }

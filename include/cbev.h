@@ -228,7 +228,9 @@ int cbev_reset(cbev_handle h, const uint8_t* mask_dev, const int32_t* scene_ids_
 int cbev_step(cbev_handle h, const void* actions_dev, const cbev_step_out* out, void* stream);
 
 /* Same, with HOST (pinned) buffers: copies actions H2D, steps, copies reward / terminated /
- * truncated back D2H on `stream`; the observation stays device resident.  */
+ * truncated back D2H on `stream`; the observation stays device resident.  If the three outputs are laid
+ * out back to back (terminated_host == reward_host + 8N bytes, truncated_host == terminated_host + N) they
+ * come back in a single copy. */
 int cbev_step_host(cbev_handle h, const void* actions_host, double* reward_host, uint8_t* terminated_host,
                    uint8_t* truncated_host, void* stream);
 
