@@ -75,6 +75,8 @@ void dev_free(T*& p) {
   p = nullptr;
 }
 
+void free_state(EnvState& s);
+
 void free_pool(PoolDev& p) {
   dev_free(p.ego_state0); dev_free(p.ego_target_speed); dev_free(p.len_ego_route); dev_free(p.ego_tidx0);
   dev_free(p.num_vehicles); dev_free(p.ego_off); dev_free(p.rew_off); dev_free(p.actor_off); dev_free(p.tl_off);
@@ -83,6 +85,8 @@ void free_pool(PoolDev& p) {
   dev_free(p.act_cruise_mps); dev_free(p.act_beh_p); dev_free(p.act_tidx0); dev_free(p.act_route_off);
   dev_free(p.act_raw_off); dev_free(p.act_retreat_slot); dev_free(p.act_cx); dev_free(p.act_cy); dev_free(p.act_cyaw);
   dev_free(p.act_raw_x); dev_free(p.act_raw_y); dev_free(p.tl_rect); dev_free(p.tl_color); dev_free(p.sg_mat);
+  dev_free(p.traj); dev_free(p.traj_off);
+  free_state(p.roll);
   p = PoolDev();
 }
 
@@ -337,6 +341,32 @@ int cbev_upload_scene_pool(cbev_handle e, const cbev_pool_desc* p) {
   rc |= dev_alloc(&e->st.retreat, (size_t)e->N * (max_retreat ? max_retreat : 1) * 3 * CBEV_SG_MAX);
   rc |= dev_alloc(&e->st.retreat_n, (size_t)e->N * (max_retreat ? max_retreat : 1));
   if (rc) return rc;
+  // ---- open-loop actor trajectories: roll every scene out once on the device (k_rollout) ----
+  int T = e->cfg.trajectory_steps;
+  if (T > 0 && na > 0) {
+    const size_t budget = (size_t)4 << 30;  // cap the tables at 4 GiB
+    while (T > 16 && (size_t)T * na * sizeof(double4) > budget) T /= 2;
+    std::vector<long long> off((size_t)n);
+    long long acc = 0;
+    for (int s2 = 0; s2 < n; ++s2) {
+      off[s2] = acc;
+      acc += (long long)T * (p->actor_off[s2 + 1] - p->actor_off[s2]);
+    }
+    const size_t S = (size_t)n, A = (size_t)(e->cfg.max_actors > 0 ? e->cfg.max_actors : 1);
+    EnvState& r = d.roll;
+    rc |= dev_upload(&d.traj_off, off.data(), S);
+    rc |= dev_alloc(&d.traj, (size_t)acc);
+    rc |= dev_alloc(&r.ax, S * A); rc |= dev_alloc(&r.ay, S * A); rc |= dev_alloc(&r.ayaw, S * A);
+    rc |= dev_alloc(&r.av, S * A); rc |= dev_alloc(&r.atarget_mps, S * A); rc |= dev_alloc(&r.aelapsed, S * A);
+    rc |= dev_alloc(&r.astate_elapsed, S * A); rc |= dev_alloc(&r.atidx, S * A); rc |= dev_alloc(&r.arxlen, S * A);
+    rc |= dev_alloc(&r.aflags, S * A);
+    rc |= dev_alloc(&r.retreat, S * (max_retreat ? max_retreat : 1) * 3 * CBEV_SG_MAX);
+    rc |= dev_alloc(&r.retreat_n, S * (max_retreat ? max_retreat : 1));
+    if (rc) return rc;
+    d.traj_steps = T;
+    cbev_launch_rollout(e, 0);
+    CU_TRY(cudaDeviceSynchronize());
+  }
   e->has_pool = true;
   return CBEV_OK;
 }

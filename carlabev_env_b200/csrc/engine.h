@@ -28,24 +28,6 @@ enum {
   RD_PAD
 };
 
-struct PoolDev {
-  int32_t n_scenes = 0, n_actors_total = 0, max_actors = 0, max_targets = 0, max_tl = 0, max_retreat = 0;
-  double *ego_state0 = nullptr, *ego_target_speed = nullptr, *len_ego_route = nullptr;
-  int32_t *ego_tidx0 = nullptr, *num_vehicles = nullptr;
-  int32_t *ego_off = nullptr, *rew_off = nullptr, *actor_off = nullptr, *tl_off = nullptr;
-  double *ego_cx = nullptr, *ego_cy = nullptr, *ego_cyaw = nullptr;
-  int32_t *rew_rx = nullptr, *rew_ry = nullptr;
-  double* rew_cum = nullptr;
-  uint8_t *act_kind = nullptr, *act_beh = nullptr;
-  double *act_state0 = nullptr, *act_cruise_px = nullptr, *act_cruise_mps = nullptr, *act_beh_p = nullptr;
-  int32_t *act_tidx0 = nullptr, *act_route_off = nullptr, *act_raw_off = nullptr;
-  int32_t* act_retreat_slot = nullptr;  // per actor: slot in the per-env retreat-route buffer or -1
-  double *act_cx = nullptr, *act_cy = nullptr, *act_cyaw = nullptr, *act_raw_x = nullptr, *act_raw_y = nullptr;
-  int32_t* tl_rect = nullptr;
-  uint8_t* tl_color = nullptr;
-  double* sg_mat = nullptr;
-};
-
 struct EnvState {
   int32_t* scene = nullptr;        // [N] pool index, -1 before the first reset
   int32_t* episode = nullptr;      // [N] episodes finished by this env
@@ -63,6 +45,29 @@ struct EnvState {
   // retreat routes [N][max_retreat][CBEV_SG_MAX][3] + lengths [N][max_retreat]
   double* retreat = nullptr;
   int32_t* retreat_n = nullptr;
+};
+
+struct PoolDev {
+  int32_t n_scenes = 0, n_actors_total = 0, max_actors = 0, max_targets = 0, max_tl = 0, max_retreat = 0;
+  double *ego_state0 = nullptr, *ego_target_speed = nullptr, *len_ego_route = nullptr;
+  int32_t *ego_tidx0 = nullptr, *num_vehicles = nullptr;
+  int32_t *ego_off = nullptr, *rew_off = nullptr, *actor_off = nullptr, *tl_off = nullptr;
+  double *ego_cx = nullptr, *ego_cy = nullptr, *ego_cyaw = nullptr;
+  int32_t *rew_rx = nullptr, *rew_ry = nullptr;
+  double* rew_cum = nullptr;
+  uint8_t *act_kind = nullptr, *act_beh = nullptr;
+  double *act_state0 = nullptr, *act_cruise_px = nullptr, *act_cruise_mps = nullptr, *act_beh_p = nullptr;
+  int32_t *act_tidx0 = nullptr, *act_route_off = nullptr, *act_raw_off = nullptr;
+  int32_t* act_retreat_slot = nullptr;  // per actor: slot in the per-env retreat-route buffer or -1
+  double *act_cx = nullptr, *act_cy = nullptr, *act_cyaw = nullptr, *act_raw_x = nullptr, *act_raw_y = nullptr;
+  int32_t* tl_rect = nullptr;
+  uint8_t* tl_color = nullptr;
+  double* sg_mat = nullptr;
+  // open-loop actor trajectories: pose after step t of actor a of scene s at traj[traj_off[s] + t * A_s + a]
+  int32_t traj_steps = 0;
+  double4* traj = nullptr;
+  long long* traj_off = nullptr;
+  EnvState roll;  // actor state of every scene after traj_steps steps (rows = scenes), continuation for long episodes
 };
 
 struct SimParams {
@@ -114,3 +119,4 @@ void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* o
 int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int hi, cudaStream_t s);
 void cbev_set_error(const char* fmt, ...);
 int cbev_launch_fuse(cbev_engine* e, int32_t mode, float* out, cudaStream_t s);
+void cbev_launch_rollout(cbev_engine* e, cudaStream_t s);

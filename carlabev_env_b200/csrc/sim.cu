@@ -40,7 +40,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // ego double slots
 enum { E_X = 0, E_Y, E_YAW, E_V, E_X1, E_Y1, E_YAW1, E_V1, E_ACC, E_T, E_D2G, E_D2G1, E_SPREV, E_LAST_DYAW,
        E_PC_AL, E_PC_AT, E_PC_YR, E_TARGET, E_SLOTS = 24 };
-enum { I_TIDX = 0, I_FLAGS, I_K, I_OFFROAD, I_SLOTS = 8 };
+enum { I_TIDX = 0, I_FLAGS, I_K, I_OFFROAD, I_STEP, I_SLOTS = 8 };
 enum { S_RET = 0, S_LEN, S_SPEED, S_C0, S_VIOL = 9, S_HARSH, S_CAUSE, S_SLOTS = 12 };
 enum { FL_COMFORT = 1, FL_SPREV = 2 };
 // fsm states (behavior/jaywalk.py)
@@ -189,12 +189,33 @@ __device__ __forceinline__ bool pack_rect(int rx, int ry, int rw, int rh, int pa
   return true;
 }
 
+// Actor.reset (actors/actor.py:86-108) for every actor of `scene` into row `row` of the actor arrays of S
+__device__ void init_actors(const SimParams& P, const PoolDev& pool, const EnvState& S, size_t row, int scene, int lane,
+                            int stride) {
+  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
+  for (int a = lane; a < A; a += stride) {
+    size_t o = row * P.max_actors + a;
+    const double* s0 = pool.act_state0 + (size_t)(A0 + a) * 4;
+    S.ax[o] = s0[0];
+    S.ay[o] = s0[1];
+    S.ayaw[o] = s0[2];
+    S.av[o] = s0[3];
+    S.atidx[o] = pool.act_tidx0[A0 + a];
+    int beh = pool.act_beh[A0 + a];
+    bool jay = beh == CBEV_BEH_CROSS || beh == CBEV_BEH_STOP_MID || beh == CBEV_BEH_STOP_RETURN;
+    S.atarget_mps[o] = jay ? 0.0 : pool.act_cruise_mps[A0 + a];  // jaywalk.py:23-28 / actor.py:94-95
+    S.aelapsed[o] = 0.0;
+    S.astate_elapsed[o] = 0.0;
+    S.arxlen[o] = pool.act_raw_off[A0 + a + 1] - pool.act_raw_off[A0 + a];
+    S.aflags[o] = jay ? ST_WAITING : ST_IDLE;
+  }
+}
+
 // ---- reset ------------------------------------------------------------------------------------
 // CarlaBEV.reset with a pool scene: Scene.load_scene / reset_all / reward_fn.reset / stats.reset
 // (scenes/scene.py:41-88, actors/actor.py:86-108, carl_reward_fn.py:121-134, stats.py:104-105)
 __device__ void reset_env(const SimParams& P, const PoolDev& pool, const EnvState& st, int env, int scene, int lane,
                           int stride = 32) {
-  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
   const int r0 = pool.ego_off[scene], nt = pool.ego_off[scene + 1] - r0;
   if (lane == 0) {
     double* e = st.ego + (size_t)env * E_SLOTS;
@@ -218,28 +239,14 @@ __device__ void reset_env(const SimParams& P, const PoolDev& pool, const EnvStat
     ei[I_FLAGS] = 0;
     ei[I_K] = 0;
     ei[I_OFFROAD] = 0;
+    ei[I_STEP] = 0;
     st.scene[env] = scene;
     st.done[env] = 0;
     st.tgt_vis[env] = nt >= 64 ? ~0ull : ((1ull << nt) - 1ull);
     double* sa = st.stats + (size_t)env * S_SLOTS;
     for (int k = 0; k < S_SLOTS; ++k) sa[k] = 0.0;
   }
-  for (int a = lane; a < A; a += stride) {
-    size_t o = (size_t)env * P.max_actors + a;
-    const double* s0 = pool.act_state0 + (size_t)(A0 + a) * 4;
-    st.ax[o] = s0[0];
-    st.ay[o] = s0[1];
-    st.ayaw[o] = s0[2];
-    st.av[o] = s0[3];
-    st.atidx[o] = pool.act_tidx0[A0 + a];
-    int beh = pool.act_beh[A0 + a];
-    bool jay = beh == CBEV_BEH_CROSS || beh == CBEV_BEH_STOP_MID || beh == CBEV_BEH_STOP_RETURN;
-    st.atarget_mps[o] = jay ? 0.0 : pool.act_cruise_mps[A0 + a];  // jaywalk.py:23-28 / actor.py:94-95
-    st.aelapsed[o] = 0.0;
-    st.astate_elapsed[o] = 0.0;
-    st.arxlen[o] = pool.act_raw_off[A0 + a + 1] - pool.act_raw_off[A0 + a];
-    st.aflags[o] = jay ? ST_WAITING : ST_IDLE;
-  }
+  init_actors(P, pool, st, (size_t)env, scene, lane, stride);
 }
 
 __global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK)
@@ -341,6 +348,153 @@ __device__ void start_retreat(const PoolDev& pool, double* rbuf, int32_t* rn, in
   tidx = scalar_nearest(fx, fy, cx, cy, n);
   b.yaw = cyaw[tidx];
   rxlen = cur + 2;
+}
+
+// One chunk of G actors of one scene instance: behaviour FSM (Actor.step, actors/actor.py:110-116), Stanley / P
+// control with the cooperative nearest-waypoint argmin and the bicycle update (stanley_controller.py:51-123).
+// Actor state lives in row `row` of the actor arrays of S (an environment, or a scene during the roll-out).
+// Returns the post-step pose in `b` and the actor kind.
+template <int G>
+__device__ __forceinline__ void actor_chunk_step(const SimParams& P, const PoolDev& pool, const EnvState& S, size_t row,
+                                                 int ga, size_t o, bool has, double t_sim, int lane, int gb, unsigned GM,
+                                                 Body& b, int& kind) {
+    int atidx = 0, rxlen = 0, fsm = 0, np = 0, beh = 0;
+    kind = 0;
+    bool braking = false, on_retreat = false;
+    double target_mps = 0.0, elapsed = 0.0, state_elapsed = 0.0, cruise_mps = 0.0;
+    const double *cxp = nullptr, *cyp = nullptr, *cyawp = nullptr;
+    double* rbuf = nullptr;
+    int32_t* rnp = nullptr;
+    if (has) {
+      b.x = S.ax[o]; b.y = S.ay[o]; b.yaw = S.ayaw[o]; b.v = S.av[o];
+      b.x1 = b.x; b.y1 = b.y; b.yaw1 = b.yaw; b.v1 = b.v;
+      atidx = S.atidx[o];
+      rxlen = S.arxlen[o];
+      int fl = S.aflags[o];
+      fsm = fl & 15; braking = fl & 16; on_retreat = fl & 32;
+      target_mps = S.atarget_mps[o];
+      kind = pool.act_kind[ga];
+      beh = pool.act_beh[ga];
+      cruise_mps = pool.act_cruise_mps[ga];
+      int slot = pool.act_retreat_slot ? pool.act_retreat_slot[ga] : -1;
+      if (slot >= 0) {
+        rbuf = S.retreat + (row * P.max_retreat + slot) * (3 * CBEV_SG_MAX);
+        rnp = S.retreat_n + row * P.max_retreat + slot;
+      }
+      if (on_retreat) {
+        cxp = rbuf; cyp = rbuf + CBEV_SG_MAX; cyawp = rbuf + 2 * CBEV_SG_MAX; np = *rnp;
+      } else {
+        int ro = pool.act_route_off[ga];
+        np = pool.act_route_off[ga + 1] - ro;
+        cxp = pool.act_cx + ro; cyp = pool.act_cy + ro; cyawp = pool.act_cyaw + ro;
+      }
+      // ---- behaviour (Actor.step: behaviour first, actor.py:110-116) ----
+      if (beh == CBEV_BEH_LEAD_BRAKE) {  // lead_brake.py:10-15
+        const double* p = pool.act_beh_p + (size_t)ga * 4;
+        if (t_sim >= p[0]) braking = true;
+        if (braking) target_mps = fmax(0.0, target_mps - p[1] * DT);
+      } else if (beh != CBEV_BEH_NONE) {  // jaywalk.py:56-138
+        const double* p = pool.act_beh_p + (size_t)ga * 4;
+        elapsed = S.aelapsed[o] + DT;
+        state_elapsed = S.astate_elapsed[o] + DT;
+        const bool complete = atidx >= rxlen - 1;
+        if (beh == CBEV_BEH_CROSS) {
+          if (fsm == ST_WAITING) {
+            target_mps = 0.0;
+            if (elapsed >= p[0]) { fsm = ST_CROSSING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps); }
+          } else if (fsm == ST_CROSSING) {
+            target_mps = fmax(0.0, cruise_mps);
+            if (complete) { fsm = ST_CLEARED; state_elapsed = 0.0; target_mps = 0.0; }
+          } else if (fsm == ST_CLEARED) {
+            target_mps = 0.0;
+          }
+        } else {
+          const bool has_stop = p[2] >= 0.0;
+          const bool retreat = p[3] != 0.0;
+          if (fsm == ST_WAITING) {
+            target_mps = 0.0;
+            if (elapsed >= p[0]) { fsm = ST_ENTERING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps); }
+          } else if (fsm == ST_ENTERING) {
+            target_mps = fmax(0.0, cruise_mps);
+            int mid = max(1, min(rxlen - 1, (int)(p[1] * (double)(rxlen - 1))));
+            if (atidx >= mid) {
+              fsm = (retreat || has_stop) ? ST_YIELDING : ST_STALLED;
+              state_elapsed = 0.0; target_mps = 0.0;
+            } else if (complete) {
+              fsm = ST_CLEARED; state_elapsed = 0.0; target_mps = 0.0;
+            }
+          } else if (fsm == ST_YIELDING) {
+            target_mps = 0.0;
+            if (has_stop && state_elapsed >= p[2]) {
+              if (retreat && rbuf != nullptr && pool.sg_mat != nullptr) {
+                start_retreat(pool, rbuf, rnp, ga, b, atidx, rxlen);
+                on_retreat = true;
+                cxp = rbuf; cyp = rbuf + CBEV_SG_MAX; cyawp = rbuf + 2 * CBEV_SG_MAX; np = *rnp;
+                fsm = ST_RETREATING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps);
+              } else {
+                fsm = ST_CROSSING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps);
+              }
+            }
+          } else if (fsm == ST_CROSSING) {
+            target_mps = fmax(0.0, cruise_mps);
+            if (complete) { fsm = ST_CLEARED; state_elapsed = 0.0; target_mps = 0.0; }
+          } else if (fsm == ST_STALLED) {
+            target_mps = 0.0;
+          } else if (fsm == ST_RETREATING) {
+            target_mps = fmax(0.0, cruise_mps);
+            int w0 = pool.act_raw_off[ga];
+            double gx = b.x - pool.act_raw_x[w0], gy = b.y - pool.act_raw_y[w0];
+            bool reached = sqrt(gx * gx + gy * gy) <= 1.0;
+            if (reached || complete) { fsm = ST_RETREATED; state_elapsed = 0.0; target_mps = 0.0; }
+          } else if (fsm == ST_CLEARED || fsm == ST_RETREATED) {
+            target_mps = 0.0;
+          }
+        }
+      }
+    }
+    // ---- Controller.control_step (stanley_controller.py:51-62): frozen once at the last waypoint
+    const bool active = has && (atidx < np - 1);
+    double fx = 0.0, fy = 0.0;
+    if (active) {
+      double sn, cs;
+      sincos(b.yaw, &sn, &cs);
+      fx = b.x + WB * cs; fy = b.y + WB * sn;
+    }
+    int my_idx = 0;
+    unsigned am = __ballot_sync(GM, active) >> gb;
+    while (am) {
+      int src = __ffs(am) - 1;
+      am &= am - 1;
+      double bfx = __shfl_sync(GM, fx, gb + src), bfy = __shfl_sync(GM, fy, gb + src);
+      unsigned long long pcx = __shfl_sync(GM, (unsigned long long)cxp, gb + src);
+      unsigned long long pcy = __shfl_sync(GM, (unsigned long long)cyp, gb + src);
+      int bn = __shfl_sync(GM, np, gb + src);
+      int idx = warp_nearest<G>(bfx, bfy, (const double*)pcx, (const double*)pcy, bn, lane, GM);
+      if (lane == src) my_idx = idx;
+    }
+    if (active) {
+      const double target = target_mps / MPP;  // set_target_speed_mps, actor.py:121-124
+      double ai = KPS * (target - b.v);
+      double ddx = fx - cxp[my_idx], ddy = fy - cyp[my_idx];
+      double sn2, cs2;
+      sincos(b.yaw + HALF_PI, &sn2, &cs2);
+      double err = ddx * (-cs2) + ddy * (-sn2);  // stanley_controller.py:119-121
+      int cur = atidx >= my_idx ? atidx : my_idx;
+      double theta_e = angle_mod(cyawp[cur] - b.yaw);
+      double theta_d = atan2(KST * err, fmax(b.v, 1e-3));
+      double di = clipd(theta_e + theta_d, -MAX_STEER, MAX_STEER);
+      atidx = cur;
+      body_update(b, ai, di, target);
+    }
+    if (has) {
+      S.ax[o] = b.x; S.ay[o] = b.y; S.ayaw[o] = b.yaw; S.av[o] = b.v;
+      S.atidx[o] = atidx;
+      S.arxlen[o] = rxlen;
+      S.atarget_mps[o] = target_mps;
+      S.aelapsed[o] = elapsed;
+      S.astate_elapsed[o] = state_elapsed;
+      S.aflags[o] = (uint8_t)(fsm | (braking ? 16 : 0) | (on_retreat ? 32 : 0));
+    }
 }
 
 // ---- the step kernel ----------------------------------------------------------------------------
@@ -485,147 +639,41 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     hvx = e.v * cs; hvy = e.v * sn;                 // compute_ttc (px units)
     hvx_m = (e.v * MPP) * cs; hvy_m = (e.v * MPP) * sn;  // compute_ttc_raw (metres)
   }
+  // Scripted actors never read the ego: their trajectories are functions of (scene, step).
+  // The first traj_steps steps of every scene were rolled out at pool upload by the same device code
+  // (k_rollout); afterwards the env continues live from the roll-out's final state.
+  const int step_idx = ei[I_STEP];
+  const bool use_table = step_idx < pool.traj_steps;
+  if (!use_table && pool.traj_steps > 0 && step_idx == pool.traj_steps) {
+    for (int a = lane; a < A; a += G) {
+      const size_t o = (size_t)env * P.max_actors + a, r = (size_t)scene * P.max_actors + a;
+      st.ax[o] = pool.roll.ax[r]; st.ay[o] = pool.roll.ay[r]; st.ayaw[o] = pool.roll.ayaw[r]; st.av[o] = pool.roll.av[r];
+      st.atarget_mps[o] = pool.roll.atarget_mps[r]; st.aelapsed[o] = pool.roll.aelapsed[r];
+      st.astate_elapsed[o] = pool.roll.astate_elapsed[r]; st.atidx[o] = pool.roll.atidx[r];
+      st.arxlen[o] = pool.roll.arxlen[r]; st.aflags[o] = pool.roll.aflags[r];
+    }
+    for (int k = lane; k < P.max_retreat * 3 * CBEV_SG_MAX; k += G)
+      st.retreat[(size_t)env * P.max_retreat * 3 * CBEV_SG_MAX + k] = pool.roll.retreat[(size_t)scene * P.max_retreat * 3 * CBEV_SG_MAX + k];
+    for (int k = lane; k < P.max_retreat; k += G)
+      st.retreat_n[(size_t)env * P.max_retreat + k] = pool.roll.retreat_n[(size_t)scene * P.max_retreat + k];
+    __syncwarp(GM);
+  }
   for (int base = 0; base < A; base += G) {
     const int a = base + lane;
     const bool has = a < A;
     const int ga = A0 + (has ? a : 0);
     const size_t o = (size_t)env * P.max_actors + (has ? a : 0);
     Body b;
-    int atidx = 0, rxlen = 0, fsm = 0, kind = 0, np = 0, beh = 0;
-    bool braking = false, on_retreat = false;
-    double target_mps = 0.0, elapsed = 0.0, state_elapsed = 0.0, cruise_mps = 0.0;
-    const double *cxp = nullptr, *cyp = nullptr, *cyawp = nullptr;
-    double* rbuf = nullptr;
-    int32_t* rnp = nullptr;
-    if (has) {
-      b.x = st.ax[o]; b.y = st.ay[o]; b.yaw = st.ayaw[o]; b.v = st.av[o];
-      b.x1 = b.x; b.y1 = b.y; b.yaw1 = b.yaw; b.v1 = b.v;
-      atidx = st.atidx[o];
-      rxlen = st.arxlen[o];
-      int fl = st.aflags[o];
-      fsm = fl & 15; braking = fl & 16; on_retreat = fl & 32;
-      target_mps = st.atarget_mps[o];
-      kind = pool.act_kind[ga];
-      beh = pool.act_beh[ga];
-      cruise_mps = pool.act_cruise_mps[ga];
-      int slot = pool.act_retreat_slot ? pool.act_retreat_slot[ga] : -1;
-      if (slot >= 0) {
-        rbuf = st.retreat + ((size_t)env * P.max_retreat + slot) * (3 * CBEV_SG_MAX);
-        rnp = st.retreat_n + (size_t)env * P.max_retreat + slot;
+    int kind = 0;
+    if (use_table) {
+      if (has) {  // open-loop actors: pose after this step was rolled out once per scene at pool upload
+        const double4 q = pool.traj[pool.traj_off[scene] + (size_t)step_idx * A + a];
+        b.x = q.x; b.y = q.y; b.yaw = q.z; b.v = q.w;
+        kind = pool.act_kind[ga];
+        st.ax[o] = b.x; st.ay[o] = b.y; st.ayaw[o] = b.yaw; st.av[o] = b.v;  // kept for cbev_get_state
       }
-      if (on_retreat) {
-        cxp = rbuf; cyp = rbuf + CBEV_SG_MAX; cyawp = rbuf + 2 * CBEV_SG_MAX; np = *rnp;
-      } else {
-        int ro = pool.act_route_off[ga];
-        np = pool.act_route_off[ga + 1] - ro;
-        cxp = pool.act_cx + ro; cyp = pool.act_cy + ro; cyawp = pool.act_cyaw + ro;
-      }
-      // ---- behaviour (Actor.step: behaviour first, actor.py:110-116) ----
-      if (beh == CBEV_BEH_LEAD_BRAKE) {  // lead_brake.py:10-15
-        const double* p = pool.act_beh_p + (size_t)ga * 4;
-        if (t_sim >= p[0]) braking = true;
-        if (braking) target_mps = fmax(0.0, target_mps - p[1] * DT);
-      } else if (beh != CBEV_BEH_NONE) {  // jaywalk.py:56-138
-        const double* p = pool.act_beh_p + (size_t)ga * 4;
-        elapsed = st.aelapsed[o] + DT;
-        state_elapsed = st.astate_elapsed[o] + DT;
-        const bool complete = atidx >= rxlen - 1;
-        if (beh == CBEV_BEH_CROSS) {
-          if (fsm == ST_WAITING) {
-            target_mps = 0.0;
-            if (elapsed >= p[0]) { fsm = ST_CROSSING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps); }
-          } else if (fsm == ST_CROSSING) {
-            target_mps = fmax(0.0, cruise_mps);
-            if (complete) { fsm = ST_CLEARED; state_elapsed = 0.0; target_mps = 0.0; }
-          } else if (fsm == ST_CLEARED) {
-            target_mps = 0.0;
-          }
-        } else {
-          const bool has_stop = p[2] >= 0.0;
-          const bool retreat = p[3] != 0.0;
-          if (fsm == ST_WAITING) {
-            target_mps = 0.0;
-            if (elapsed >= p[0]) { fsm = ST_ENTERING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps); }
-          } else if (fsm == ST_ENTERING) {
-            target_mps = fmax(0.0, cruise_mps);
-            int mid = max(1, min(rxlen - 1, (int)(p[1] * (double)(rxlen - 1))));
-            if (atidx >= mid) {
-              fsm = (retreat || has_stop) ? ST_YIELDING : ST_STALLED;
-              state_elapsed = 0.0; target_mps = 0.0;
-            } else if (complete) {
-              fsm = ST_CLEARED; state_elapsed = 0.0; target_mps = 0.0;
-            }
-          } else if (fsm == ST_YIELDING) {
-            target_mps = 0.0;
-            if (has_stop && state_elapsed >= p[2]) {
-              if (retreat && rbuf != nullptr && pool.sg_mat != nullptr) {
-                start_retreat(pool, rbuf, rnp, ga, b, atidx, rxlen);
-                on_retreat = true;
-                cxp = rbuf; cyp = rbuf + CBEV_SG_MAX; cyawp = rbuf + 2 * CBEV_SG_MAX; np = *rnp;
-                fsm = ST_RETREATING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps);
-              } else {
-                fsm = ST_CROSSING; state_elapsed = 0.0; target_mps = fmax(0.0, cruise_mps);
-              }
-            }
-          } else if (fsm == ST_CROSSING) {
-            target_mps = fmax(0.0, cruise_mps);
-            if (complete) { fsm = ST_CLEARED; state_elapsed = 0.0; target_mps = 0.0; }
-          } else if (fsm == ST_STALLED) {
-            target_mps = 0.0;
-          } else if (fsm == ST_RETREATING) {
-            target_mps = fmax(0.0, cruise_mps);
-            int w0 = pool.act_raw_off[ga];
-            double gx = b.x - pool.act_raw_x[w0], gy = b.y - pool.act_raw_y[w0];
-            bool reached = sqrt(gx * gx + gy * gy) <= 1.0;
-            if (reached || complete) { fsm = ST_RETREATED; state_elapsed = 0.0; target_mps = 0.0; }
-          } else if (fsm == ST_CLEARED || fsm == ST_RETREATED) {
-            target_mps = 0.0;
-          }
-        }
-      }
-    }
-    // ---- Controller.control_step (stanley_controller.py:51-62): frozen once at the last waypoint
-    const bool active = has && (atidx < np - 1);
-    double fx = 0.0, fy = 0.0;
-    if (active) {
-      double sn, cs;
-      sincos(b.yaw, &sn, &cs);
-      fx = b.x + WB * cs; fy = b.y + WB * sn;
-    }
-    int my_idx = 0;
-    unsigned am = __ballot_sync(GM, active) >> gb;
-    while (am) {
-      int src = __ffs(am) - 1;
-      am &= am - 1;
-      double bfx = __shfl_sync(GM, fx, gb + src), bfy = __shfl_sync(GM, fy, gb + src);
-      unsigned long long pcx = __shfl_sync(GM, (unsigned long long)cxp, gb + src);
-      unsigned long long pcy = __shfl_sync(GM, (unsigned long long)cyp, gb + src);
-      int bn = __shfl_sync(GM, np, gb + src);
-      int idx = warp_nearest<G>(bfx, bfy, (const double*)pcx, (const double*)pcy, bn, lane, GM);
-      if (lane == src) my_idx = idx;
-    }
-    if (active) {
-      const double target = target_mps / MPP;  // set_target_speed_mps, actor.py:121-124
-      double ai = KPS * (target - b.v);
-      double ddx = fx - cxp[my_idx], ddy = fy - cyp[my_idx];
-      double sn2, cs2;
-      sincos(b.yaw + HALF_PI, &sn2, &cs2);
-      double err = ddx * (-cs2) + ddy * (-sn2);  // stanley_controller.py:119-121
-      int cur = atidx >= my_idx ? atidx : my_idx;
-      double theta_e = angle_mod(cyawp[cur] - b.yaw);
-      double theta_d = atan2(KST * err, fmax(b.v, 1e-3));
-      double di = clipd(theta_e + theta_d, -MAX_STEER, MAX_STEER);
-      atidx = cur;
-      body_update(b, ai, di, target);
-    }
-    if (has) {
-      st.ax[o] = b.x; st.ay[o] = b.y; st.ayaw[o] = b.yaw; st.av[o] = b.v;
-      st.atidx[o] = atidx;
-      st.arxlen[o] = rxlen;
-      st.atarget_mps[o] = target_mps;
-      st.aelapsed[o] = elapsed;
-      st.astate_elapsed[o] = state_elapsed;
-      st.aflags[o] = (uint8_t)(fsm | (braking ? 16 : 0) | (on_retreat ? 32 : 0));
+    } else {
+      actor_chunk_step<G>(P, pool, st, (size_t)env, ga, o, has, t_sim, lane, gb, GM, b, kind);
     }
     // ---- a9: collision / proximity (scene.py:110-140, actor.py:166-176) ----
     const int size = kind == 0 ? 4 : 2;  // vehicle.py:24, pedestrian.py:24
@@ -886,7 +934,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     eg[E_ACC] = acc; eg[E_T] = t_sim; eg[E_D2G] = d2g; eg[E_D2G1] = d2g_1;
     eg[E_SPREV] = s_prev; eg[E_LAST_DYAW] = last_dyaw;
     eg[E_PC_AL] = accel_long; eg[E_PC_AT] = accel_lat; eg[E_PC_YR] = yaw_rate_deg;
-    ei[I_TIDX] = tidx; ei[I_FLAGS] = flags; ei[I_K] = kcount; ei[I_OFFROAD] = offroad;
+    ei[I_TIDX] = tidx; ei[I_FLAGS] = flags; ei[I_K] = kcount; ei[I_OFFROAD] = offroad; ei[I_STEP] = step_idx + 1;
     st.tgt_vis[env] = tvis;
     out.reward[env] = reward;
     out.terminated[env] = terminated;
@@ -942,6 +990,32 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
   }
 }
 
+// Roll every scene's scripted actors out for traj_steps steps (one warp per scene) and record the poses.
+__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK)
+k_rollout(SimParams P, PoolDev pool) {
+  const int scene = blockIdx.x * CBEV_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (scene >= pool.n_scenes) return;
+  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
+  init_actors(P, pool, pool.roll, (size_t)scene, scene, lane, 32);
+  __syncwarp();
+  double t_sim = 0.0;
+  for (int step = 0; step < pool.traj_steps; ++step) {
+    t_sim += DT;  // scene.py:91
+    for (int base = 0; base < A; base += 32) {
+      const int a = base + lane;
+      const bool has = a < A;
+      const int ga = A0 + (has ? a : 0);
+      const size_t o = (size_t)scene * P.max_actors + (has ? a : 0);
+      Body b;
+      int kind = 0;
+      actor_chunk_step<32>(P, pool, pool.roll, (size_t)scene, ga, o, has, t_sim, lane, 0, FULL, b, kind);
+      if (has) pool.traj[pool.traj_off[scene] + (size_t)step * A + a] = make_double4(b.x, b.y, b.yaw, b.v);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 static SimParams make_params(cbev_engine* e) {
@@ -981,7 +1055,7 @@ void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* o
   SimParams P = make_params(e);
   P.env_lo = lo;
   P.env_hi = hi;
-  if (e->pool.max_actors <= 8) {
+  if (e->pool.max_actors <= 8 || e->pool.traj_steps > 0) {  // table look-ups need no wide actor loops
     constexpr int G = 8;
     int per_block = CBEV_WARPS_PER_BLOCK * (32 / G);
     int blocks = (hi - lo + per_block - 1) / per_block;
@@ -990,5 +1064,12 @@ void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* o
     int blocks = (hi - lo + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
     k_sim<32><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->gstats);
   }
+  e->launches += 1;
+}
+
+void cbev_launch_rollout(cbev_engine* e, cudaStream_t s) {
+  SimParams P = make_params(e);
+  int blocks = (e->pool.n_scenes + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
+  k_rollout<<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool);
   e->launches += 1;
 }

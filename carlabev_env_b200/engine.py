@@ -47,7 +47,7 @@ class CbevConfig(C.Structure):
         ("obs_h", C.c_int32), ("obs_w", C.c_int32), ("obs_mode", C.c_int32), ("mask_mode", C.c_int32),
         ("frame_stack", C.c_int32), ("ring_slots", C.c_int32), ("action_mode", C.c_int32), ("n_discrete", C.c_int32),
         ("discrete_table", C.c_float * 48),
-        ("reward_mode", C.c_int32), ("autoreset", C.c_int32), ("max_actors", C.c_int32), ("reserved0", C.c_int32),
+        ("reward_mode", C.c_int32), ("autoreset", C.c_int32), ("max_actors", C.c_int32), ("trajectory_steps", C.c_int32),
         ("lane_center_exponent", C.c_double), ("lane_center_floor", C.c_double), ("off_lane_penalty", C.c_double),
         ("speed_penalty_scale", C.c_double), ("speed_penalty_floor", C.c_double), ("ttc_threshold", C.c_double),
         ("ttc_penalty_floor", C.c_double),
@@ -162,7 +162,7 @@ class Engine:
     def __init__(self, num_envs, *, obs_mode=OBS_SEMANTIC, mask_mode="6-class", frame_stack=4, ring_slots=None,
                  action_mode=ACTION_DISCRETE, discrete_table=None, reward_mode=REWARD_CARL, reward_params=None,
                  autoreset=AUTORESET_DISABLED, anchor=(0.5, 0.5), max_actors=0, seed=0, device=None,
-                 ring_budget_bytes=None, size=128, obs_size=(96, 96)):
+                 ring_budget_bytes=None, size=128, obs_size=(96, 96), trajectory_steps=1024):
         import torch
 
         if not torch.cuda.is_available():
@@ -213,6 +213,7 @@ class Engine:
         cfg.reward_mode = reward_mode
         cfg.autoreset = autoreset
         cfg.max_actors = int(max_actors)
+        cfg.trajectory_steps = int(trajectory_steps)
         params = dict(CARL_DEFAULTS)
         params.update(SHAPING_DEFAULTS)
         params.update({k: v for k, v in (reward_params or {}).items() if k in params})

@@ -134,7 +134,7 @@ typedef struct {
   int32_t reward_mode;       /* CBEV_REWARD_*                                        */
   int32_t autoreset;         /* CBEV_AUTORESET_*                                     */
   int32_t max_actors;        /* capacity of the per-env actor arrays (>= pool max)   */
-  int32_t reserved0;
+  int32_t trajectory_steps;  /* steps of open-loop actor trajectory rolled out per scene at pool upload (0 = off) */
   /* CaRL parameters (carl_reward_fn.py:73-88; config/reward_profiles.py) */
   double lane_center_exponent, lane_center_floor, off_lane_penalty;
   double speed_penalty_scale, speed_penalty_floor, ttc_threshold, ttc_penalty_floor;

@@ -8,7 +8,7 @@ from golden_util import Golden, crc, load_map
 CAUSES = (None, "ckpt", "collision", "success", "out_of_bounds", "off_road", "max_actions", "unknown")
 
 
-def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb=False, seed=0):
+def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb=False, seed=0, trajectory_steps=1024):
     import torch  # noqa: F401
 
     from carlabev_env_b200 import engine as E
@@ -32,6 +32,7 @@ def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb
         anchor=(kw.get("ego_anchor_x_frac", 0.5), kw.get("ego_anchor_y_frac", 0.5)),
         max_actors=int(max(1, np.diff(g.pool["actor_off"]).max())),
         seed=seed,
+        trajectory_steps=trajectory_steps,
     )
     eng.upload_map(load_map())
     eng.upload_pool(g.pool)
@@ -45,15 +46,20 @@ def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb
     return eng
 
 
-def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12):
-    """Free-running replay of one golden case on the GPU; returns a list of mismatch strings."""
+def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12, trajectory_steps=1024):
+    """Free-running replay of one golden case on the GPU; returns a list of mismatch strings.
+
+    trajectory_steps = 0 steps the scripted actors live; > 0 reads their poses from the per-scene tables rolled
+    out at pool upload for that many steps and continues live afterwards (target indices / FSM states of the
+    actors are only observable through cbev_get_state while they are stepped live)."""
     import torch
 
     from carlabev_env_b200 import engine as E
 
     g = Golden(name)
-    eng = make_engine_for(g)
+    eng = make_engine_for(g, trajectory_steps=trajectory_steps)
     dev = eng.device
+    since_reset = 0
     resets = dict(zip(g["reset_steps"].tolist(), g["reset_scene"].tolist()))
     fsteps = {int(s): i for i, s in enumerate(g["frame_steps"])}
     osteps = {int(s): i for i, s in enumerate(g["obs_steps"])}
@@ -71,6 +77,7 @@ def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12):
             eng.reset(ids, None if first else np.array([True]))
             obs = eng.current_obs()
             first = False
+            since_reset = 0
             fr = eng.fov()[0].cpu().numpy()
             if not np.array_equal(fr, g["reset_frames"][ri]):
                 bad.append(f"t={t} reset frame differs in {(fr != g['reset_frames'][ri]).sum()} px")
@@ -81,6 +88,8 @@ def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12):
         at = torch.tensor([int(a)], dtype=torch.int64, device=dev) if discrete else \
             torch.tensor(np.asarray(a, dtype=np.float32)[None], device=dev)
         eng.step(at)
+        since_reset += 1
+        live = since_reset > trajectory_steps
         hero = eng.hero[0].cpu().numpy()
         st = hero[[H["x"], H["y"], H["yaw"], H["v"]]]
         ref = g["ego_state"][t]
@@ -108,10 +117,10 @@ def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12):
         n = int(np.sum(~np.isnan(ga[:, 0])))
         if n and not np.allclose(act[0, :n, :4], ga[:n], rtol=pose_rtol, atol=1e-9):
             bad.append(f"t={t} actor state max abs diff {np.abs(act[0, :n, :4] - ga[:n]).max()}")
-        if n and not np.array_equal(act[0, :n, 4].astype(int), g["actor_tidx"][t][:n]):
+        if live and n and not np.array_equal(act[0, :n, 4].astype(int), g["actor_tidx"][t][:n]):
             bad.append(f"t={t} actor tidx")
         fsm = g["actor_fsm"][t][:n]
-        if n and not np.array_equal(act[0, :n, 5].astype(int)[fsm > 0], fsm[fsm > 0]):
+        if live and n and not np.array_equal(act[0, :n, 5].astype(int)[fsm > 0], fsm[fsm > 0]):
             bad.append(f"t={t} actor fsm {act[0, :n, 5].astype(int)} vs {fsm}")
         if check_frames and t in fsteps:
             fr = eng.fov()[0].cpu().numpy()

@@ -12,9 +12,12 @@ from golden_util import ALL_CASES
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("trajectory_steps", [0, 1024, 9])
 @pytest.mark.parametrize("case", ALL_CASES)
-def test_engine_replays_reference_golden(case):
+def test_engine_replays_reference_golden(case, trajectory_steps):
+    """trajectory_steps: 0 = scripted actors stepped live every step; 1024 = poses read from the per-scene tables
+    rolled out at pool upload; 9 = table for 9 steps, then the live continuation (exercises the hand-over)."""
     from engine_util import replay_golden
 
-    bad = replay_golden(case)
+    bad = replay_golden(case, trajectory_steps=trajectory_steps)
     assert not bad, "\n".join(bad)
