@@ -225,6 +225,9 @@ int cbev_destroy(cbev_handle e) {
   dev_free(e->h_reward_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }
   dev_free(e->all_scene_ids);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
+  if (e->ev_sim) cudaEventDestroy(e->ev_sim);
+  if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   if (e->prof_ev) {
     for (int i = 0; i < 3 * CBEV_PROF_MAX; ++i) cudaEventDestroy(e->prof_ev[i]);
     delete[] e->prof_ev;
@@ -426,6 +429,20 @@ int cbev_step(cbev_handle e, const void* actions_dev, const cbev_step_out* out, 
   cbev_launch_sim(e, actions_dev, out, 0, e->N, s);
   if (prof) cudaEventRecord(e->prof_ev[3 * e->prof_n + 1], s);
   if ((rc = debug_sync("k_sim", s))) return rc;
+  if (e->host_out) {  // reward / flags are final after the sim kernel: copy them out while the raster kernel runs
+    const size_t N = (size_t)e->N;
+    CU_TRY(cudaEventRecord(e->ev_sim, s));
+    CU_TRY(cudaStreamWaitEvent(e->side_stream, e->ev_sim, 0));
+    if (e->host_term == (uint8_t*)e->host_out + N * 8 && e->host_trunc == e->host_term + N) {
+      // the caller laid the three outputs out back to back: one D2H copy instead of three
+      CU_TRY(cudaMemcpyAsync(e->host_out, e->h_reward_dev, N * 10, cudaMemcpyDeviceToHost, e->side_stream));
+    } else {
+      CU_TRY(cudaMemcpyAsync(e->host_out, e->h_reward_dev, N * 8, cudaMemcpyDeviceToHost, e->side_stream));
+      CU_TRY(cudaMemcpyAsync(e->host_term, e->h_term_dev, N, cudaMemcpyDeviceToHost, e->side_stream));
+      CU_TRY(cudaMemcpyAsync(e->host_trunc, e->h_trunc_dev, N, cudaMemcpyDeviceToHost, e->side_stream));
+    }
+    CU_TRY(cudaEventRecord(e->ev_copy, e->side_stream));
+  }
   if (cbev_launch_render(e, head, mirror, 0, e->N, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
   if (prof) { cudaEventRecord(e->prof_ev[3 * e->prof_n + 2], s); e->prof_n += 1; }
   if ((rc = debug_sync("k_render", s))) return rc;
@@ -449,16 +466,18 @@ int cbev_step_host(cbev_handle e, const void* actions_host, double* reward_host,
   out.reward = e->h_reward_dev;
   out.terminated = e->h_term_dev;
   out.truncated = e->h_trunc_dev;
-  rc = cbev_step(e, e->h_actions_dev, &out, stream);
-  if (rc) return rc;
-  if (terminated_host == (uint8_t*)reward_host + N * 8 && truncated_host == terminated_host + N) {
-    // the caller laid the three outputs out back to back: one D2H copy instead of three
-    CU_TRY(cudaMemcpyAsync(reward_host, e->h_reward_dev, N * 10, cudaMemcpyDeviceToHost, s));
-  } else {
-    CU_TRY(cudaMemcpyAsync(reward_host, e->h_reward_dev, N * 8, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(terminated_host, e->h_term_dev, N, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(truncated_host, e->h_trunc_dev, N, cudaMemcpyDeviceToHost, s));
+  if (!e->side_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&e->ev_sim, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming));
   }
+  e->host_out = reward_host;
+  e->host_term = terminated_host;
+  e->host_trunc = truncated_host;
+  rc = cbev_step(e, e->h_actions_dev, &out, stream);
+  e->host_out = nullptr;
+  if (rc) return rc;
+  CU_TRY(cudaStreamWaitEvent(s, e->ev_copy, 0));  // a synchronize on `stream` also covers the copy
   return CBEV_OK;
 }
 

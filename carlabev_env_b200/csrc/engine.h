@@ -105,6 +105,12 @@ struct cbev_engine {
   double* h_reward_dev = nullptr;
   uint8_t *h_term_dev = nullptr, *h_trunc_dev = nullptr;
   int32_t* all_scene_ids = nullptr;
+  // cbev_step_host: the D2H copy of reward / flags runs on a side stream right after the sim kernel,
+  // overlapped with the raster kernel
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_sim = nullptr, ev_copy = nullptr;
+  void* host_out = nullptr;       // pending host destination(s) for the current step, or null
+  uint8_t *host_term = nullptr, *host_trunc = nullptr;
   int64_t launches = 0;
   int64_t steps = 0;
   // per-kernel profiling (cbev_profile_enable)

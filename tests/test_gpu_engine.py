@@ -403,3 +403,44 @@ def test_pose_drift_over_1000_steps():
     assert steps_alive.max() == 1000 and (steps_alive >= 900).sum() >= 2, steps_alive
     print(f"max relative pose deviation over {steps_alive.tolist()} steps: {worst:.3e}")
     eng.close()
+
+
+def test_step_host_matches_device_step():
+    """cbev_step_host (pinned host actions in, reward / flags out on a side stream overlapped with the raster
+    kernel) returns exactly what cbev_step leaves on the device."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+
+    scenes = _scenes([("lead_brake", 1 + i % 3) for i in range(16)], seed0=700)
+    n = 64
+    a_dev = _engine(n, scenes, autoreset=E.AUTORESET_NEXT_STEP, seed=3)
+    a_host = _engine(n, scenes, autoreset=E.AUTORESET_NEXT_STEP, seed=3)
+    ids = torch.arange(n, dtype=torch.int32) % len(scenes)
+    a_dev.reset(ids)
+    a_host.reset(ids)
+    out = torch.zeros(n * 10, dtype=torch.uint8).pin_memory()
+    rew, term, trunc = out[: n * 8].view(torch.float64), out[n * 8: n * 9], out[n * 9:]
+    sep = [torch.zeros(n, dtype=torch.float64).pin_memory(), torch.zeros(n, dtype=torch.uint8).pin_memory(),
+           torch.zeros(n, dtype=torch.uint8).pin_memory()]
+    g = torch.Generator().manual_seed(1)
+    n_term = 0
+    for t in range(60):
+        a = torch.rand(n, 3, generator=g)
+        a[:, 1] = a[:, 1] * 2 - 1
+        ap = a.pin_memory()
+        a_dev.step(a.cuda())
+        if t % 2 == 0:
+            a_host.step_host(ap, rew, term, trunc)          # contiguous outputs: single copy
+            got = (rew, term, trunc)
+        else:
+            a_host.step_host(ap, *sep)                       # separate buffers: three copies
+            got = sep
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(got[0], a_dev.reward.cpu()) and torch.equal(got[1], a_dev.terminated.cpu())
+        assert torch.equal(got[2], a_dev.truncated.cpu())
+        assert torch.equal(a_host.obs(), a_dev.obs())
+        n_term += int(got[1].sum())
+    assert n_term > 0
+    a_dev.close()
+    a_host.close()
