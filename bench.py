@@ -173,7 +173,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps_per_env = max(20, min(400, args.steps * 4))
+    steps_per_env = max(1000, min(6000, args.steps * 3))  # bounded sample: roughly 5-25 s of stepping per core
     cb = cpu_baseline(steps_per_env=steps_per_env)
     n_env = cb["cores"]
     line = {
@@ -378,14 +378,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config; c2 is the bench line")
     ap.add_argument("--pool", type=int, default=POOL_SCENES)
     ap.add_argument("--ring-slots", type=int, default=None)
-    ap.add_argument("--cpu-steps", type=int, default=150)
+    ap.add_argument("--cpu-steps", type=int, default=3000,
+                    help="oracle steps per worker process for cpu_baseline (about 10-15 s of CPU work per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
