@@ -263,6 +263,14 @@ def run_ours(args):
         lo = torch.tensor([0.0, -1.0, 0.0])
         hi = torch.tensor([1.0, 1.0, 1.0])
         acts_host = [(lo + (hi - lo) * torch.rand(N, 3, generator=gen)).float().pin_memory() for _ in range(bank)]
+    if args.brake:  # diagnostic: full brake -> the ego stands still, no episode ends, no reset frames are written
+        for a in acts_host:
+            if not discrete:
+                a[:, 0] = 0.0
+                a[:, 1] = 0.0
+                a[:, 2] = 1.0
+            else:
+                a[:] = 2
     acts_dev = [a.to(dev) for a in acts_host]
     stream = torch.cuda.current_stream(dev)
 
@@ -388,6 +396,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3000,
                     help="oracle steps per worker process for cpu_baseline (about 10-15 s of CPU work per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--brake", action="store_true", help="diagnostic: constant full-brake actions (no resets)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -507,6 +507,16 @@ int cbev_fuse(cbev_handle e, int32_t mode, float* out_dev, void* stream) {
   return CBEV_OK;
 }
 
+int cbev_debug_rerender(cbev_handle e, int32_t times, void* stream) {
+  int rc = check_ready(e, true);
+  if (rc) return rc;
+  const int F = e->cfg.frame_stack, L = e->cfg.ring_slots;
+  for (int i = 0; i < times; ++i)
+    if (cbev_launch_render(e, e->head, F > 1 ? L - F + 1 : 0, 0, e->N, (cudaStream_t)stream)) return CBEV_ERR_CUDA;
+  CU_TRY(cudaGetLastError());
+  return CBEV_OK;
+}
+
 int cbev_obs_head(cbev_handle e, int32_t* head) {
   if (!e || !head) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
   *head = e->head;

@@ -273,6 +273,12 @@ class CarlaBEVVectorEnv:
     def _out_obs(self, obs):
         return obs.cpu().numpy() if self.to_numpy else obs
 
+    def vector_observation(self):
+        """The reference's `obs_mode="vector"` observation of every env (envs/carlabev.py:237-244):
+        float32 [N, 7] = hero.state (x, y, yaw, v) ++ set_point (x, y, yaw).  Valid after a step."""
+        h = self.engine.hero
+        return self.torch.cat([h[:, 0:4], h[:, 9:12]], dim=1).to(self.torch.float32)
+
     def episode_statistics(self, reset=False):
         """Device-accumulated episode statistics (CBEV_S_* of include/cbev.h) as a CUDA float64 tensor.
         This vector is the only thing ranks exchange (carlabev_env_b200.distributed.allreduce_stats)."""

@@ -275,6 +275,9 @@ int64_t cbev_launch_count(cbev_handle h);
 int cbev_profile_enable(cbev_handle h, int32_t on);
 int cbev_profile_read(cbev_handle h, double* sim_ms, double* render_ms, int64_t* steps);
 
+/* Diagnostic: re-run the raster kernel `times` times on the current descriptors (timing experiments). */
+int cbev_debug_rerender(cbev_handle h, int32_t times, void* stream);
+
 /* ABI self-check: sizeof(cbev_config), sizeof(cbev_pool_desc), sizeof(cbev_step_out). */
 int cbev_abi_sizes(int32_t* config_bytes, int32_t* pool_desc_bytes, int32_t* step_out_bytes);
 

@@ -187,6 +187,9 @@ def test_vector_env_surface_and_infos():
             assert abs(ei["return"][i] - infos["episode"]["r"][i]) < 1e-9
             break
     assert finished is not None
+    vec = envs.vector_observation()  # obs_mode="vector" of the base env: state ++ set_point, float32 (7,)
+    assert vec.shape == (6, 7) and vec.dtype == torch.float32
+    assert torch.equal(vec[:, :4], infos["hero"][:, :4].float())
     with pytest.raises(AssertionError):  # SyncVectorEnv(AutoresetMode.DISABLED) refuses to step finished envs
         envs.step(np.zeros((6, 3), np.float32))
     obs, _ = envs.reset(options={"scene_ids": np.arange(6), "reset_mask": finished})
@@ -444,3 +447,21 @@ def test_step_host_matches_device_step():
     assert n_term > 0
     a_dev.close()
     a_host.close()
+
+
+def test_vector_env_temporal_fusion_and_mask_shapes():
+    import torch
+
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+
+    scenes = _scenes([("lead_brake", 3)] * 2, seed0=77)
+    for mode, c_out in (("vehicle_temporal", 8), ("vehicle_weighted", 6)):
+        cfg = RunConfig(env=EnvConfig(action_mode="continuous", temporal_fusion_mode=mode, fov_masked=True), num_envs=2)
+        envs = make_env(cfg, scenes=scenes, ring_budget_bytes=32 << 20)
+        assert envs.single_observation_space.shape == (c_out, 96, 96)
+        obs, _ = envs.reset(options={"scene_ids": np.arange(2)})
+        assert obs.shape == (2, c_out, 96, 96)
+        obs, *_ = envs.step(np.tile(np.array([[0.5, 0.0, 0.0]], np.float32), (2, 1)))
+        assert obs.shape == (2, c_out, 96, 96) and float(obs.max()) <= 1.0
+        assert float(obs[:, :, 0, 0].abs().sum()) == 0.0   # masked corner pixel matches no class
+        envs.close()
