@@ -20,6 +20,7 @@
 //   5. masks are expanded to float32 planes and streamed to HBM with coalesced 16-byte stores,
 //      once per ring slot the frame belongs to.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "engine.h"
 
