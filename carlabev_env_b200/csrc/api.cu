@@ -507,12 +507,24 @@ int cbev_fuse(cbev_handle e, int32_t mode, float* out_dev, void* stream) {
   return CBEV_OK;
 }
 
+__global__ void k_debug_spin(int ns) {
+  if (ns > 0) __nanosleep((unsigned)ns);
+}
+
 int cbev_debug_rerender(cbev_handle e, int32_t times, void* stream) {
   int rc = check_ready(e, true);
   if (rc) return rc;
   const int F = e->cfg.frame_stack, L = e->cfg.ring_slots;
-  for (int i = 0; i < times; ++i)
-    if (cbev_launch_render(e, e->head, F > 1 ? L - F + 1 : 0, 0, e->N, (cudaStream_t)stream)) return CBEV_ERR_CUDA;
+  // diagnostic variants: times = count | (mode << 16); mode bit0: advance the ring head per launch,
+  // bit1: a small latency-only kernel (1024 blocks x 128 threads, ~20 us) between raster launches
+  const int mode = times >> 16;
+  times &= 0xffff;
+  int head = e->head;
+  for (int i = 0; i < times; ++i) {
+    if (mode & 2) k_debug_spin<<<1024, 128, 0, (cudaStream_t)stream>>>(20000);
+    if (mode & 1) { head += 1; if (head >= L) head = F - 1; }
+    if (cbev_launch_render(e, head, F > 1 ? L - F + 1 : 0, 0, e->N, (cudaStream_t)stream)) return CBEV_ERR_CUDA;
+  }
   CU_TRY(cudaGetLastError());
   return CBEV_OK;
 }

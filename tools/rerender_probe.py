@@ -17,6 +17,10 @@ if __name__ == "__main__":
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); E._check(eng.lib, eng.lib.cbev_debug_rerender(eng.handle, 50, s)); e1.record(); torch.cuda.synchronize()
     print("re-render only: %.1f us per launch" % (e0.elapsed_time(e1) / 50 * 1e3))
+    for mode, name in ((1, "advance head"), (2, "spin kernel between"), (3, "advance head + spin kernel")):
+        E._check(eng.lib, eng.lib.cbev_debug_rerender(eng.handle, 5 | (mode << 16), s)); torch.cuda.synchronize()
+        e0.record(); E._check(eng.lib, eng.lib.cbev_debug_rerender(eng.handle, 50 | (mode << 16), s)); e1.record(); torch.cuda.synchronize()
+        print("re-render, %s: %.1f us per iteration" % (name, e0.elapsed_time(e1) / 50 * 1e3))
     e0.record()
     for _ in range(50): eng.step(a)
     e1.record(); torch.cuda.synchronize()
