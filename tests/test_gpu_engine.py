@@ -465,3 +465,19 @@ def test_vector_env_temporal_fusion_and_mask_shapes():
         assert obs.shape == (2, c_out, 96, 96) and float(obs.max()) <= 1.0
         assert float(obs[:, :, 0, 0].abs().sum()) == 0.0   # masked corner pixel matches no class
         envs.close()
+
+
+def test_make_env_spaces_like_reference_smoke_tests():
+    """The reference's tests/test_public_config.py:212-256: discrete9 -> Discrete(9), continuous -> Box shape (3,)."""
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+
+    scenes = _scenes([("lead_brake", 1)])
+    envs = make_env(RunConfig(env=EnvConfig(), num_envs=1), scenes=scenes, ring_budget_bytes=16 << 20)
+    assert envs.single_action_space.n == 9 and envs.single_observation_space.shape == (24, 96, 96)
+    envs.close()
+    envs = make_env(EnvConfig(action_mode="continuous", obs_mode="bev_rgb"), scenes=scenes, ring_budget_bytes=16 << 20)
+    assert envs.single_action_space.shape == (3,) and envs.single_observation_space.shape == (4, 96, 96)
+    assert envs.single_observation_space.dtype == np.uint8
+    obs, _ = envs.reset(options={"scene_ids": 0})
+    assert tuple(obs.shape) == (1, 4, 96, 96)
+    envs.close()

@@ -73,6 +73,40 @@ def test_host_scene_generators_match_reference_snapshots(case, kind, seed0, nlev
                 assert np.array_equal(a, b), k
 
 
+def test_seeded_scene_consistency():
+    """Modelled on the reference's tests/test_seeded_scene_consistency.py: same seed -> identical spawn, route and
+    actors; the ego anchor does not change the world spawn; different seeds give different scenes."""
+    from carlabev_env_b200.scenes import build_scripted_scene
+
+    cls = load_map()
+    for kind in ("lead_brake", "jaywalk"):
+        a = build_scripted_scene(kind, 123, level=None, cls_map=cls)
+        b = build_scripted_scene(kind, 123, level=None, cls_map=cls)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (kind, k)
+        c = build_scripted_scene(kind, 123, level=None, cls_map=cls, pad=230)  # lookahead_75 crop: same world spawn
+        assert np.array_equal(a["ego_state0"], c["ego_state0"]) and np.array_equal(a["act_state0"], c["act_state0"])
+        d = build_scripted_scene(kind, 124, level=int(a["level"]), cls_map=cls)
+        assert not np.array_equal(a["ego_state0"], d["ego_state0"]) or not np.array_equal(a["ego_cy"], d["ego_cy"])
+        assert 1 <= int(a["level"]) <= 4
+    with pytest.raises(KeyError):
+        build_scripted_scene("unknown", 0)
+
+
+def test_shipped_pools_load_and_validate():
+    from carlabev_env_b200.pool import SHIPPED_POOLS, load_shipped_pool, shipped_pool_for
+
+    for name, opts in SHIPPED_POOLS.items():
+        scenes = load_shipped_pool(name)
+        assert len(scenes) >= 32 and shipped_pool_for(opts) == name
+        for i, s in enumerate(scenes[:8]):
+            assert int(s["seed"]) == i and 2 <= len(s["ego_cx"]) <= 64
+            kinds = s["act_kind"]
+            assert np.all(np.diff(kinds.astype(int)) >= 0)            # vehicles precede pedestrians
+            assert s["act_route_off"][-1] == len(s["act_cx"])
+    assert shipped_pool_for({"scene": "rdm", "num_vehicles": 3}) is None
+
+
 def test_pool_pack_roundtrip():
     from carlabev_env_b200.pool import pack_pool, unpack_pool
 
