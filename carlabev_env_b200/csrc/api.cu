@@ -91,7 +91,7 @@ void free_pool(PoolDev& p) {
 }
 
 void free_state(EnvState& s) {
-  dev_free(s.scene); dev_free(s.episode); dev_free(s.done); dev_free(s.ego); dev_free(s.ego2); dev_free(s.egoi);
+  dev_free(s.scene); dev_free(s.episode); dev_free(s.done); dev_free(s.ego); dev_free(s.egoi);
   dev_free(s.tgt_vis); dev_free(s.stats); dev_free(s.ax); dev_free(s.ay); dev_free(s.ayaw); dev_free(s.av);
   dev_free(s.atarget_mps); dev_free(s.aelapsed); dev_free(s.astate_elapsed); dev_free(s.atidx); dev_free(s.arxlen);
   dev_free(s.aflags); dev_free(s.retreat); dev_free(s.retreat_n);
@@ -224,7 +224,6 @@ int cbev_destroy(cbev_handle e) {
   dev_free(e->map); dev_free(e->desc); dev_free(e->rects); dev_free(e->fov); dev_free(e->gstats);
   dev_free(e->h_reward_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }
-  dev_free(e->all_scene_ids);
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->ev_sim) cudaEventDestroy(e->ev_sim);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);

@@ -32,9 +32,9 @@ struct EnvState {
   int32_t* scene = nullptr;        // [N] pool index, -1 before the first reset
   int32_t* episode = nullptr;      // [N] episodes finished by this env
   uint8_t* done = nullptr;         // [N] last step was terminal (needs reset)
-  double* ego = nullptr;           // [N][16]: x,y,yaw,v,x1,y1,yaw1,v1,acc,t,dist2goal,dist2goal_1,s_prev,last_dyaw,pc0..1 (see sim.cu)
-  double* ego2 = nullptr;          // [N][4]: prev comfort yaw_rate, spare
-  int32_t* egoi = nullptr;         // [N][8]: tidx, flags(bit0 comfort valid, bit1 s_prev valid), k, consecutive_offroad, spare
+  double* ego = nullptr;           // [N][24]: x,y,yaw,v,x1,y1,yaw1,v1,acc,t,dist2goal,dist2goal_1,s_prev,last_dyaw,
+                                   //          previous comfort (accel_long, accel_lat, yaw_rate), target speed (sim.cu E_*)
+  int32_t* egoi = nullptr;         // [N][8]: tidx, flags(bit0 comfort valid, bit1 s_prev valid), k, consecutive_offroad, step
   unsigned long long* tgt_vis = nullptr;  // [N]
   double* stats = nullptr;         // [N][12]: return, length, sum speed, sum |comfort| x6, viol, harsh, cause
   // actors [N][max_actors]
@@ -104,7 +104,6 @@ struct cbev_engine {
   void* h_actions_dev = nullptr;
   double* h_reward_dev = nullptr;
   uint8_t *h_term_dev = nullptr, *h_trunc_dev = nullptr;
-  int32_t* all_scene_ids = nullptr;
   // cbev_step_host: the D2H copy of reward / flags runs on a side stream right after the sim kernel,
   // overlapped with the raster kernel
   cudaStream_t side_stream = nullptr;
