@@ -143,7 +143,18 @@ SHIPPED_POOLS = {
     "rdm_rt_medium_v1": dict(scene="rdm", difficulty_id="rt_medium_v1", num_vehicles=16, route_dist_range=(40, 100)),
     "rdm_dense_50": dict(scene="rdm", num_vehicles=50, route_dist_range=(30, 130)),
     "red_light_runner": dict(scene="red_light_runner"),
+    # the reference's 7 authored scenes (assets/scenes/*.json) x 4 seeded variations; see authored_manifest()
+    "authored_scenes": dict(config_file="*.json", variation_enabled=True),
 }
+
+
+def authored_manifest() -> list[dict]:
+    """[{config_file, scenario_id, variation_seed}] for the entries of the `authored_scenes` pool."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "pools", "authored_scenes.json")) as f:
+        return json.load(f)
 
 
 def load_shipped_pool(name: str) -> list[dict]:
@@ -157,6 +168,8 @@ def load_shipped_pool(name: str) -> list[dict]:
 def shipped_pool_for(options: dict) -> str | None:
     """Name of the shipped pool generated with these reset options, if any."""
     scene = options.get("scene", "rdm")
+    if options.get("config_file") or str(scene).endswith(".json"):
+        return "authored_scenes"
     if scene == "red_light_runner":
         return "red_light_runner"
     if scene == "rdm":

@@ -158,6 +158,26 @@ class CarlaBEVVectorEnv:
                 self._scripted_cache = cache
                 self.engine.upload_pool(pack_pool(self._scenes))
             return np.full(n, cache[key], dtype=np.int64)
+        if options.get("config_file") or str(scene).endswith(".json"):
+            # authored scenes (scenarios/__init__.py:210-338): snapshots of the reference's 7 scene files x variations
+            import os as _os
+
+            from .pool import authored_manifest
+
+            name = _os.path.basename(str(options.get("config_file") or scene))
+            vseed = int(options.get("variation_seed", 0))
+            cache = getattr(self, "_shipped_cache", {})
+            if "authored_scenes" not in cache:
+                sc = load_shipped_pool("authored_scenes")
+                cache["authored_scenes"] = (len(self._scenes), len(sc))
+                self._scenes.extend(sc)
+                self._shipped_cache = cache
+                self.engine.upload_pool(pack_pool(self._scenes))
+            base, _ = cache["authored_scenes"]
+            for i, m in enumerate(authored_manifest()):
+                if m["config_file"] == name and m["variation_seed"] == vseed:
+                    return np.full(n, base + i, dtype=np.int64)
+            raise KeyError(f"authored scene {name!r} with variation_seed={vseed} is not in the shipped pool")
         if scene in ("rdm", "red_light_runner"):
             # generated by the reference from its lane graphs; a pool exported with exactly these options ships
             # with the package (entry i == the reference's scene for scene_seed = i)

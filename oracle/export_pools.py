@@ -43,6 +43,36 @@ def export(name, n, options_of, env_kwargs=None):
     envs.close()
 
 
+def export_authored(variations=4):
+    """The reference's 7 authored scenes (assets/scenes/*.json) x seeded variations
+    (scenarios/__init__.py:210-338).  Scripted actors of authored scenes carry no np_rng, so their +-1 px start
+    jitter is unseeded in the reference: the pool holds snapshots of one realisation each."""
+    import glob
+    import json
+
+    from oracle.ref_loader import REFERENCE_ROOT
+
+    files = sorted(glob.glob(os.path.join(REFERENCE_ROOT, "CarlaBEV", "assets", "scenes", "*.json")))
+    cfg = RunConfig(env=EnvConfig(render_mode="rgb_array"), num_envs=1)
+    envs = make_env(cfg)
+    base = envs.envs[0].unwrapped
+    scenes, manifest = [], []
+    for f in files:
+        scenario_id = json.load(open(f))["scenario_id"]
+        for v in range(variations):
+            opts = dict(scene=scenario_id, config_file=f, variation_enabled=True, variation_seed=v, scene_seed=v)
+            envs.reset(options={**opts, "reset_mask": np.array([True])})
+            scenes.append(extract_scene(base, opts))
+            manifest.append({"config_file": os.path.basename(f), "scenario_id": scenario_id, "variation_seed": v})
+    os.makedirs(OUT, exist_ok=True)
+    save_pool(os.path.join(OUT, "authored_scenes.npz"), scenes)
+    json.dump(manifest, open(os.path.join(OUT, "authored_scenes.json"), "w"), indent=1)
+    print(f"authored_scenes: {len(scenes)} scenes from {len(files)} files, actors "
+          f"{min(len(s['act_kind']) for s in scenes)}..{max(len(s['act_kind']) for s in scenes)}, "
+          f"traffic lights <= {max(len(s['tl_color']) for s in scenes)}")
+    envs.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else ""
     if which in ("", "rdm_hard"):
@@ -57,6 +87,8 @@ if __name__ == "__main__":
         # BASELINE configs[4]: max actor density (num_vehicles = max_vehicles = 50), lookahead_75 camera
         export("rdm_dense_50", 48, lambda i: dict(scene="rdm", num_vehicles=50, route_dist_range=(30, 130), scene_seed=i),
                env_kwargs=dict(ego_anchor_x_frac=0.5, ego_anchor_y_frac=0.75))
+    if which in ("", "authored"):
+        export_authored()
     if which in ("", "red_light"):
         # BASELINE configs[3]: red_light_runner (first valid 4-way intersection); the adversary's start jitter is
         # unseeded in the reference (quirk C-10), so these are snapshots, not re-derivable from the seed

@@ -96,8 +96,14 @@ def test_seeded_scene_consistency():
 def test_shipped_pools_load_and_validate():
     from carlabev_env_b200.pool import SHIPPED_POOLS, load_shipped_pool, shipped_pool_for
 
+    from carlabev_env_b200.pool import authored_manifest
+
+    assert len(authored_manifest()) == len(load_shipped_pool("authored_scenes")) == 28
+    assert shipped_pool_for({"config_file": "/x/leadbrake-01.02.json"}) == "authored_scenes"
     for name, opts in SHIPPED_POOLS.items():
         scenes = load_shipped_pool(name)
+        if name == "authored_scenes":
+            continue
         assert len(scenes) >= 32 and shipped_pool_for(opts) == name
         for i, s in enumerate(scenes[:8]):
             assert int(s["seed"]) == i and 2 <= len(s["ego_cx"]) <= 64
