@@ -15,6 +15,8 @@ Differences that follow from the design:
     `to_numpy=True` returns NumPy copies with the reference's dtypes.
   * scenes come from a host-generated, device-resident pool; `reset(options=...)` selects or
     extends it.  `autoreset="next_step"` turns on device auto-reset from that pool.
+  * `host_infos=False` (with device auto-reset) makes `step` fully asynchronous: no host synchronisation,
+    terminal summaries stay in `infos["episode_block"]` (CBEV_E_* columns) on the device.
   * `infos` carries the reference's terminal keys (`episode_info`, `episode`) as dict-of-arrays
     with `_key` masks, plus the per-step `hero` comfort signals the reference documents
     (docs/control_and_actions.md:102) as a batched tensor.
@@ -46,7 +48,8 @@ class CarlaBEVVectorEnv:
     metadata = {"render_modes": ["rgb_array"], "render_fps": 60, "autoreset_mode": "Disabled"}
 
     def __init__(self, cfg: RunConfig, *, scenes=None, autoreset: str = "disabled", device=None, ring_slots=None,
-                 ring_budget_bytes=None, to_numpy: bool = False, raw_rgb: bool = False, seed=None):
+                 ring_budget_bytes=None, to_numpy: bool = False, raw_rgb: bool = False, seed=None,
+                 host_infos: bool = True):
         import torch
 
         self.torch = torch
@@ -55,6 +58,7 @@ class CarlaBEVVectorEnv:
         self.env_cfg = env
         self.num_envs = int(cfg.num_envs)
         self.to_numpy = to_numpy
+        self.host_infos = host_infos or autoreset == "disabled"  # masked-reset bookkeeping needs the done flags
         self.autoreset = autoreset
         self.fusion = env.temporal_fusion_mode if env.obs_mode == "bev_semantic" else "stack"
         aspec = get_action_profile_spec(env.action_profile_id)
@@ -106,8 +110,7 @@ class CarlaBEVVectorEnv:
         else:
             self.single_observation_space = Box(0, 255, (env.size, env.size, 3), np.uint8)
         self.single_action_space.seed(cfg.seed)
-        self._ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
-        self._ep_len = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+        self._done_host = torch.zeros(self.num_envs, dtype=torch.uint8).pin_memory()
         self._needs_reset = np.ones(self.num_envs, dtype=bool)
         self._scene_of_env = np.zeros(self.num_envs, dtype=np.int64)
         self.current_hero = None
@@ -220,9 +223,6 @@ class CarlaBEVVectorEnv:
         obs = self.engine.reset(ids, m)
         if self.fusion != "stack":
             obs = self.engine.fuse(self.fusion)
-        sel = slice(None) if m is None else t.as_tensor(m, device=self.device)
-        self._ep_return[sel] = 0.0
-        self._ep_len[sel] = 0
         if m is None:
             self._needs_reset[:] = False
             self._scene_of_env[:] = ids
@@ -246,47 +246,46 @@ class CarlaBEVVectorEnv:
         eng.step(a)
         obs = eng.obs() if self.fusion == "stack" else eng.fuse(self.fusion)
         rew, term, trunc = eng.reward, eng.terminated.bool(), eng.truncated.bool()
-        self._ep_return += rew
-        self._ep_len += 1
         self.current_hero = eng.hero
         infos = {"hero": eng.hero, "cause": eng.cause}
-        done = term | trunc
-        done_host = done.cpu().numpy()  # one small D2H per step: the reference's terminal info is host data
+        if not self.host_infos:
+            # fully asynchronous step: terminal summaries stay on the device (rows of finished envs are valid)
+            infos["episode_block"] = eng.episode
+            return obs, rew, term, trunc, infos
+        # one small D2H per step: the reference's terminal info (episode_info / episode) is host data
+        self._done_host.copy_(eng.terminated | eng.truncated, non_blocking=True)
+        t.cuda.current_stream(self.device).synchronize()
+        done_host = self._done_host.numpy().astype(bool)
         if done_host.any():
             infos.update(self._terminal_infos(done_host))
             if self.autoreset == "disabled":
                 self._needs_reset |= done_host
-            d = t.as_tensor(done_host, device=self.device)
-            self._ep_return[d] = 0.0
-            self._ep_len[d] = 0
         if self.to_numpy:
             return (self._out_obs(obs), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy(), infos)
         return obs, rew, term, trunc, infos
 
     def _terminal_infos(self, done_host):
-        """episode_info (stats.py:127-148 + carlabev.py:177-185) and RecordEpisodeStatistics' `episode`."""
+        """episode_info (stats.py:127-148 + carlabev.py:177-185) and RecordEpisodeStatistics' `episode`
+        (r = sum of rewards, l = steps: the same numbers as the summary's return / length)."""
         idx = np.flatnonzero(done_host)
         ep = self.engine.episode[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
         n = self.num_envs
-        info = {k: np.zeros(n, dtype=np.float64) for k in E.EPISODE_FIELDS if k not in ("cause",)}
-        term = np.full(n, None, dtype=object)
-        for j, i in enumerate(idx):
-            for k, name in enumerate(E.EPISODE_FIELDS):
-                if name == "cause":
-                    term[i] = E.CAUSE_NAMES[int(ep[j, k])]
-                else:
-                    info[name][i] = ep[j, k]
-        info["termination"] = term
-        info["length"] = info["length"].astype(np.int64)
         mask = done_host.copy()
         episode_info = {}
-        for k, v in info.items():
-            episode_info[k] = v
-            episode_info[f"_{k}"] = mask
+        for k, name in enumerate(E.EPISODE_FIELDS):
+            if name == "cause":
+                col = np.full(n, None, dtype=object)
+                col[idx] = np.array(E.CAUSE_NAMES, dtype=object)[ep[:, k].astype(np.int64)]
+                name = "termination"
+            else:
+                col = np.zeros(n, dtype=np.int64 if name == "length" else np.float64)
+                col[idx] = ep[:, k]
+            episode_info[name] = col
+            episode_info[f"_{name}"] = mask
         r = np.zeros(n)
         ln = np.zeros(n, dtype=np.int64)
-        r[idx] = self._ep_return[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
-        ln[idx] = self._ep_len[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
+        r[idx] = ep[:, E.EPISODE_FIELDS.index("return")]
+        ln[idx] = ep[:, E.EPISODE_FIELDS.index("length")]
         return {"episode_info": episode_info, "_episode_info": mask,
                 "episode": {"r": r, "_r": mask, "l": ln, "_l": mask}, "_episode": mask}
 
