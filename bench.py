@@ -245,6 +245,11 @@ def run_ours(args):
     a_mean = float(np.mean([len(s["act_kind"]) for s in scenes]))
     a_max = int(max(len(s["act_kind"]) for s in scenes))
     discrete = W["actions"] == "discrete"
+    if args.ring_slots is None and W["obs"] == "semantic":
+        # spend HBM on the observation ring: a longer ring wraps (and mirrors F-1 frames) less often;
+        # up to 96 slots within half of the free memory (87 GB at 4096 envs)
+        free, _ = torch.cuda.mem_get_info(local)
+        args.ring_slots = int(max(7, min(96, (free // 2) // (N * 6 * 96 * 96 * 4))))
     eng = E.Engine(N, obs_mode=E.OBS_SEMANTIC if W["obs"] == "semantic" else E.OBS_RGB, mask_mode="6-class",
                    frame_stack=4, action_mode=E.ACTION_DISCRETE if discrete else E.ACTION_CONTINUOUS,
                    discrete_table=ACTION_PROFILES["discrete9_v1"]["discrete_actions"],
