@@ -595,6 +595,12 @@ int cbev_set_ego_state(cbev_handle e, const double* ego_host) {
   return CBEV_OK;
 }
 
+int cbev_set_debug_flags(cbev_handle e, int32_t flags) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  e->debug_flags = flags;
+  return CBEV_OK;
+}
+
 int cbev_keep_fov(cbev_handle e, int32_t on) {
   if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
   e->keep_fov = on != 0;

@@ -91,6 +91,7 @@ struct cbev_engine {
   PoolDev pool;
   EnvState st;
   int32_t max_rects = 0;
+  int32_t debug_flags = 0;         // cbev_set_debug_flags
   int32_t* desc = nullptr;         // [N][CBEV_DESC_WORDS]
   uint32_t* rects = nullptr;       // [N][max_rects]
   uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)

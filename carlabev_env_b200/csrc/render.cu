@@ -202,7 +202,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     // The crop is sized so that the 128x128 window normally lies inside the rotated surface and inside the
     // source range of the fixed-point walk.  Both facts are linear in (x, y): checking the four window corners
     // proves them for every pixel, which removes all per-pixel range tests (the generic loop remains for the rest).
-    bool fast = left <= 0 && top <= 0 && left + nx >= S && top + ny >= S;
+    bool fast = left <= 0 && top <= 0 && left + nx >= S && top + ny >= S && !(P.pad0 & 1);
     if (mode == 1 && fast) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -512,7 +512,7 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   if (tile < 96 * 96 + 2 * 1024 + 64) tile = 96 * 96 + 2 * 1024 + 64;  // output bytes + mixed-block worklist
   tile = ((tile + 127) / 128) * 128;
   P.tile_bytes = (int32_t)tile;
-  P.pad0 = 0;
+  P.pad0 = e->debug_flags;  // bit0: force the generic (range-tested) rotate path
   size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16;
   int rc = 1;
   if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, s);

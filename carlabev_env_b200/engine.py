@@ -37,7 +37,7 @@ SG_MAX = 12
 EXPORTS = ("cbev_version", "cbev_last_error", "cbev_create", "cbev_destroy", "cbev_upload_map",
            "cbev_upload_scene_pool", "cbev_frame_bytes", "cbev_bind_obs_ring", "cbev_reset", "cbev_step",
            "cbev_step_host", "cbev_obs_head", "cbev_get_state", "cbev_set_ego_state", "cbev_copy_fov",
-           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse", "cbev_debug_rerender")
+           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse", "cbev_debug_rerender", "cbev_set_debug_flags")
 
 
 class CbevConfig(C.Structure):
@@ -118,6 +118,7 @@ def load_library(build_if_missing: bool = True):
     lib.cbev_upload_fov_mask.argtypes = [_P, _P]
     lib.cbev_fuse.argtypes = [_P, C.c_int32, _P, _P]
     lib.cbev_debug_rerender.argtypes = [_P, C.c_int32, _P]
+    lib.cbev_set_debug_flags.argtypes = [_P, C.c_int32]
     lib.cbev_read_stats.argtypes = [_P, _P, C.c_int32, _P]
     lib.cbev_profile_enable.argtypes = [_P, C.c_int32]
     lib.cbev_profile_read.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -352,6 +353,9 @@ class Engine:
             self._fuse_buf = {**getattr(self, "_fuse_buf", {}), key: buf}
         _check(self.lib, self.lib.cbev_fuse(self.handle, code, buf.data_ptr(), self._stream()))
         return buf
+
+    def set_debug_flags(self, flags: int):
+        _check(self.lib, self.lib.cbev_set_debug_flags(self.handle, int(flags)))
 
     def keep_fov(self, on=True):
         _check(self.lib, self.lib.cbev_keep_fov(self.handle, int(on)))

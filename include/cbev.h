@@ -275,6 +275,11 @@ int64_t cbev_launch_count(cbev_handle h);
 int cbev_profile_enable(cbev_handle h, int32_t on);
 int cbev_profile_read(cbev_handle h, double* sim_ms, double* render_ms, int64_t* steps);
 
+/* Test hook.  bit0: force the generic rotate path (pygame's per-pixel range tests and background colour) even
+ * when the window corners prove it unnecessary -- the reference's crop sizes never need it, so this is the only
+ * way to exercise that code. */
+int cbev_set_debug_flags(cbev_handle h, int32_t flags);
+
 /* Diagnostic: re-run the raster kernel `times` times on the current descriptors (timing experiments). */
 int cbev_debug_rerender(cbev_handle h, int32_t times, void* stream);
 

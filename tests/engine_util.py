@@ -46,7 +46,7 @@ def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb
     return eng
 
 
-def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12, trajectory_steps=1024):
+def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12, trajectory_steps=1024, debug_flags=0):
     """Free-running replay of one golden case on the GPU; returns a list of mismatch strings.
 
     trajectory_steps = 0 steps the scripted actors live; > 0 reads their poses from the per-scene tables rolled
@@ -58,6 +58,7 @@ def replay_golden(name, pose_rtol=1e-9, check_frames=True, max_report=12, trajec
 
     g = Golden(name)
     eng = make_engine_for(g, trajectory_steps=trajectory_steps)
+    eng.set_debug_flags(debug_flags)
     dev = eng.device
     since_reset = 0
     resets = dict(zip(g["reset_steps"].tolist(), g["reset_scene"].tolist()))

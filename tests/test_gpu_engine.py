@@ -518,3 +518,63 @@ def test_authored_scenes_pool_parity():
                 _check_env(t, i, hero[i], rew[i], term[i], obs[i], oracles[i], oracles[i].step(a[i]))
                 alive[i] = not term[i]
     eng.close()
+
+
+@pytest.mark.parametrize("anchor", [(0.5, 0.5), (0.5, 0.75), (0.5, 0.2)])
+def test_raster_parity_over_all_headings(anchor):
+    """Frames against the oracle for 384 ego headings per camera anchor (exact multiples of 45 degrees, their
+    float neighbours, and a dense sweep): exercises the exact rotate90 path, the branch-free fast path and the
+    generic path with pygame's range tests / background colour of the 16.16 fixed-point walk."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import load_shipped_pool, pack_pool
+    from oracle import raster
+    from oracle.env import OracleEnv
+
+    scene = load_shipped_pool("rdm_rt_medium_v1")[3]
+    special = [k * np.pi / 4 for k in range(-4, 4)]
+    yaws = special + [np.nextafter(y, 10.0) for y in special] + [np.nextafter(y, -10.0) for y in special]
+    yaws += list(np.linspace(-np.pi, np.pi, 384 - len(yaws), endpoint=False))
+    n = len(yaws)
+    eng = E.Engine(n, obs_mode=E.OBS_SEMANTIC, mask_mode="6-class", frame_stack=2, action_mode=E.ACTION_CONTINUOUS,
+                   max_actors=16, anchor=anchor, ring_budget_bytes=256 << 20)
+    eng.upload_map(load_map())
+    eng.upload_pool(pack_pool([scene]))
+    eng.keep_fov(True)
+    eng.reset(torch.zeros(n, dtype=torch.int32))
+    ego, _ = eng.get_state(16)
+    ego[:, 2] = yaws            # yaw
+    ego[:, 6] = yaws            # previous yaw
+    ego[:, 3] = 0.0             # standing still: the heading is kept by the step
+    eng.set_ego_state(ego)
+    a = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (n, 1))
+    eng.step(torch.from_numpy(a).cuda())
+    fov = eng.fov().cpu().numpy()
+    obs = eng.obs().cpu().numpy()
+    geom = raster.FovGeometry(128, *anchor)
+    n_generic = 0
+    for i, yaw in enumerate(yaws):
+        o = OracleEnv(load_map(), action_mode="continuous", frame_stack=2, anchor=anchor)
+        o.reset(scene)
+        o.sim.ego.yaw = o.sim.ego.yaw_1 = float(yaw)
+        o.sim.ego.v = 0.0
+        ref_obs, *_ = o.step(a[i])
+        assert float(o.sim.ego.yaw) == float(eng.hero[i, 2]), (i, yaw)
+        ref = o.render_index()
+        assert np.array_equal(fov[i], ref), (i, yaw, int((fov[i] != ref).sum()))
+        assert np.array_equal(obs[i, 6:], ref_obs[6:]), (i, yaw)
+        # does this heading leave the fast path? (window corners outside the rotated surface / source range)
+        rp = raster.rotate_params(float(o.sim.ego.yaw), geom.crop)
+        if rp["mode"] == 1:
+            left, top = geom.anchor[0] - (rp["nx"] >> 1), geom.anchor[1] - (rp["ny"] >> 1)
+            inside = left <= 0 and top <= 0 and left + rp["nx"] >= 128 and top + rp["ny"] >= 128
+            for cx in (0, 127):
+                for cy in (0, 127):
+                    rxp, ryp = cx - left, cy - top
+                    dx = rp["ax"] + rp["isin"] * (rp["cy"] - ryp) + rp["xd"] + rxp * rp["icos"]
+                    dy = rp["ay"] - rp["icos"] * (rp["cy"] - ryp) + rp["yd"] + rxp * rp["isin"]
+                    inside = inside and 0 <= dx <= (geom.crop << 16) - 1 and 0 <= dy <= (geom.crop << 16) - 1
+            n_generic += not inside
+    print(f"anchor {anchor}: {n} headings, {n_generic} on the generic (range-tested) path")
+    eng.close()

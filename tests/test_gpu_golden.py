@@ -21,3 +21,14 @@ def test_engine_replays_reference_golden(case, trajectory_steps):
 
     bad = replay_golden(case, trajectory_steps=trajectory_steps)
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("case", ["rdm_medium_discrete", "rdm_rgb_lookahead", "fusion_temporal_masked"])
+def test_generic_rotate_path(case):
+    """The reference's crop sizes always keep the 128x128 window inside the rotated surface, so the engine normally
+    takes the corner-proved fast path; the generic path (per-pixel range tests, background colour) is forced here
+    and must give the same frames."""
+    from engine_util import replay_golden
+
+    bad = replay_golden(case, debug_flags=1)
+    assert not bad, "\n".join(bad)
