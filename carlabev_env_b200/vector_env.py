@@ -29,8 +29,8 @@ import numpy as np
 
 from . import engine as E
 from . import scenes as S
-from .config import (ACTION_PROFILES, CARL_DEFAULTS, SHAPING_DEFAULTS, EnvConfig, RunConfig, get_action_profile_spec,
-                     get_difficulty_spec, get_reward_profile_spec, validate_run_config)
+from .config import (SHAPING_DEFAULTS, RunConfig, get_action_profile_spec, get_reward_profile_spec,
+                     validate_run_config)
 from .pool import load_shipped_pool, pack_pool, shipped_pool_for
 from .spaces import Box, Discrete
 

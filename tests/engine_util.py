@@ -12,7 +12,7 @@ def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb
     import torch  # noqa: F401
 
     from carlabev_env_b200 import engine as E
-    from carlabev_env_b200.config import ACTION_PROFILES, REWARD_PROFILES
+    from carlabev_env_b200.config import ACTION_PROFILES
 
     kw = g.env_kwargs
     obs_mode = kw.get("obs_mode", "bev_semantic")

@@ -4,7 +4,7 @@ size-independent properties at the benchmark size (4096 envs)."""
 import numpy as np
 import pytest
 
-from golden_util import Golden, load_map
+from golden_util import load_map
 
 pytestmark = pytest.mark.gpu
 
