@@ -144,23 +144,33 @@ class CarlaBEVVectorEnv:
             if not self._scenes:
                 raise RuntimeError("no scene pool: pass scenes=... / call set_scene_pool(), or reset with "
                                    "options={'scene': 'lead_brake' | 'jaywalk', ...}")
-            base = int(options.get("scene_seed", self.env_cfg.seed))
+            base = int(options.get("scene_seed", options.get("_vector_seed", self.env_cfg.seed)))
             return (base + np.arange(n)) % len(self._scenes)
         if scene in ("lead_brake", "jaywalk"):
-            # SyncVectorEnv passes the same options to every env, so every masked env gets the
-            # same (scene, level, scene_seed) -- identical scene per env, like the reference.
-            seed = int(options.get("scene_seed", self.env_cfg.seed))
+            # SyncVectorEnv passes the same options to every env: with options["scene_seed"] every env gets the
+            # same scene (like the reference); with reset(seed=s) env i is seeded s + i (gymnasium vector reset).
             level = options.get("level")
-            key = (scene, level, seed)
+            if "scene_seed" in options:
+                seeds = np.full(n, int(options["scene_seed"]), dtype=np.int64)
+            elif "_vector_seed" in options:
+                seeds = int(options["_vector_seed"]) + np.arange(n, dtype=np.int64)
+            else:
+                seeds = np.full(n, int(self.env_cfg.seed), dtype=np.int64)
             cache = getattr(self, "_scripted_cache", {})
-            if key not in cache:
-                sc = S.build_scripted_scene(scene, seed, level=level, cls_map=self.cls_map, pad=self.pad,
+            wanted = np.unique(seeds if mask is None else seeds[mask])
+            new = [int(sd) for sd in wanted if (scene, level, int(sd)) not in cache]
+            for sd in new:
+                sc = S.build_scripted_scene(scene, sd, level=level, cls_map=self.cls_map, pad=self.pad,
                                             max_reset_attempts=options.get("max_reset_attempts", 10))
                 self._scenes.append(sc)
-                cache[key] = len(self._scenes) - 1
+                cache[(scene, level, sd)] = len(self._scenes) - 1
+            if new:
                 self._scripted_cache = cache
                 self.engine.upload_pool(pack_pool(self._scenes))
-            return np.full(n, cache[key], dtype=np.int64)
+            sel = np.ones(n, bool) if mask is None else mask
+            ids = np.zeros(n, dtype=np.int64)
+            ids[sel] = [cache[(scene, level, int(sd))] for sd in seeds[sel]]
+            return ids
         if options.get("config_file") or str(scene).endswith(".json"):
             # authored scenes (scenarios/__init__.py:210-338): snapshots of the reference's 7 scene files x variations
             import os as _os
@@ -194,10 +204,15 @@ class CarlaBEVVectorEnv:
                     self._shipped_cache = cache
                     self.engine.upload_pool(pack_pool(self._scenes))
                 base, count = cache[name]
-                seed = int(options.get("scene_seed", self.env_cfg.seed))
-                if not 0 <= seed < count:
-                    raise ValueError(f"shipped pool {name!r} covers scene_seed 0..{count - 1}, got {seed}")
-                return np.full(n, base + seed, dtype=np.int64)
+                if "scene_seed" in options or "_vector_seed" not in options:
+                    seeds = np.full(n, int(options.get("scene_seed", self.env_cfg.seed)), dtype=np.int64)
+                else:
+                    seeds = int(options["_vector_seed"]) + np.arange(n, dtype=np.int64)
+                used = seeds if mask is None else seeds[mask]
+                if used.min() < 0 or used.max() >= count:
+                    raise ValueError(f"shipped pool {name!r} covers scene seeds 0..{count - 1}, got {int(used.min())}.."
+                                     f"{int(used.max())}")
+                return base + np.clip(seeds, 0, count - 1)
         if scene in ("rdm", "red_light_runner") or str(scene).endswith(".json"):
             raise NotImplementedError(
                 f"scene={scene!r} needs the reference's lane graphs / authored files on the host; export a pool with "
@@ -214,7 +229,9 @@ class CarlaBEVVectorEnv:
             assert mask.dtype == np.bool_ and mask.shape == (self.num_envs,) and mask.any(), \
                 "reset_mask must be a bool array of shape (num_envs,) with at least one True"
         if seed is not None and "scene_seed" not in options:
-            options["scene_seed"] = int(seed)  # CarlaBEV._resolve_rng_bundle, carlabev.py:83-94
+            # gymnasium SyncVectorEnv.reset(seed=s) seeds env i with s + i; CarlaBEV._resolve_rng_bundle then uses it
+            # as the scene seed (carlabev.py:83-94)
+            options["_vector_seed"] = int(seed)
         ids = self._scenes_from_options(options, mask)
         first = bool(self._needs_reset.all()) and self.engine.head < 0
         if first and mask is not None and not mask.all():

@@ -197,6 +197,11 @@ def test_vector_env_surface_and_infos():
     # scripted scene built on the host at reset time, like the reference's reset(options={"scene": ...})
     obs, _ = envs.reset(options={"scene": "jaywalk", "level": 3, "scene_seed": 11})
     assert obs.shape == (6, 24, 96, 96)
+    assert len(set(envs._scene_of_env.tolist())) == 1            # options["scene_seed"]: the same scene for every env
+    obs, _ = envs.reset(seed=40, options={"scene": "lead_brake", "level": 1})
+    assert len(set(envs._scene_of_env.tolist())) == 6            # reset(seed=s): env i is seeded s + i
+    obs, _ = envs.reset(seed=3, options={"scene": "rdm", "difficulty_id": "rt_medium_v1"})
+    assert len(set(envs._scene_of_env.tolist())) == 6
     with pytest.raises(NotImplementedError):
         envs.reset(options={"scene": "rdm", "num_vehicles": 3})
     envs.close()
