@@ -194,33 +194,55 @@ WORKLOADS = {
     "c2": dict(desc="configs[1]: {N} envs/GPU lead_brake (levels 1-3, pool of {K} seeded scenes), continuous actions, "
                     "6-class semantic masks 96x96 float32, frame_stack 4, CaRL reward, device auto-reset (next-step) "
                     "from the pool", envs=4096, obs="semantic", actions="continuous", anchor=(0.5, 0.5)),
-    "c3": dict(desc="configs[2]: {N} envs/GPU rdm rt_hard_v1 (25 vehicles, shipped pool of {K} reference scenes), "
+    "c3": dict(desc="configs[2]: {N} envs/GPU rdm rt_hard_v1 (25 vehicles, pool of {K} host-generated scenes, scene_seed = i), "
                     "discrete9 actions, 6-class semantic F=4, auto-reset", envs=8192, obs="semantic",
                actions="discrete", anchor=(0.5, 0.5), pool="rdm_rt_hard_v1"),
     "c4": dict(desc="configs[3]: {N} envs/GPU 50/50 jaywalk (levels 1-4) / red_light_runner, continuous actions, "
                     "6-class semantic F=4, auto-reset from a pool of {K} scenes", envs=8192, obs="semantic",
                actions="continuous", anchor=(0.5, 0.5), pool="mixed_edge"),
     "c5": dict(desc="configs[4]: {N} envs/GPU raw RGB (128,128,3) uint8 obs, lookahead_75 camera, rdm with 50 vehicles "
-                    "(shipped pool of {K} reference scenes), continuous actions, auto-reset", envs=8192, obs="rgb",
+                    "(pool of {K} host-generated scenes), continuous actions, auto-reset", envs=8192, obs="rgb",
                actions="continuous", anchor=(0.5, 0.75), pool="rdm_dense_50"),
 }
 
 
-def workload_pool(name, args):
-    from carlabev_env_b200.pool import load_shipped_pool
+def _cached_pool(tag, requests, pad=182):
+    """Pool generated on the host cores by carlabev_env_b200.scenes.build_pool (bit-identical to the reference's
+    post-reset state for the same options and scene_seed), cached next to the bench outputs."""
+    from carlabev_env_b200.pool import load_pool, save_pool
+    from carlabev_env_b200.scenes import build_pool as build
 
+    path = os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else ".",
+                        f".pool_{tag}_{len(requests)}.npz")
+    if os.path.exists(path):
+        try:
+            return load_pool(path)
+        except Exception:  # noqa: BLE001
+            pass
+    scenes = build(requests, pad=pad)
+    try:
+        save_pool(path, scenes)
+    except Exception:  # noqa: BLE001
+        pass
+    return scenes
+
+
+def workload_pool(name, args):
+    """Scene pools at the sizes SURVEY.md section 8(d) names: scene_seed = i, generated on the host."""
     w = WORKLOADS[name]
     if name == "c2":
         return build_pool(args.pool)
-    if w["pool"] == "mixed_edge":
-        from carlabev_env_b200.scenes import build_scripted_scene
-        from carlabev_env_b200.vector_env import load_town01_map
-
-        cls = load_town01_map()
-        jay = [build_scripted_scene("jaywalk", i, level=1 + i % 4, cls_map=cls) for i in range(256)]
-        rl = load_shipped_pool("red_light_runner")
-        return [jay[i // 2] if i % 2 == 0 else rl[(i // 2) % len(rl)] for i in range(512)]
-    return load_shipped_pool(w["pool"])
+    if w["pool"] == "rdm_rt_hard_v1":     # configs[2]: K = 4096 scenes, seeds 0..K-1
+        return _cached_pool("rdm_rt_hard_v1", [dict(scene="rdm", difficulty_id="rt_hard_v1", scene_seed=i)
+                                               for i in range(args.pool)])
+    if w["pool"] == "mixed_edge":         # configs[3]: K = 2048, jaywalk levels 1-4 round-robin / red_light_runner
+        k = min(args.pool, 2048)
+        return _cached_pool("mixed_edge", [dict(scene="jaywalk", level=1 + (i // 2) % 4, scene_seed=i) if i % 2 == 0
+                                           else dict(scene="red_light_runner", scene_seed=i) for i in range(k)])
+    # configs[4]: rdm with num_vehicles = max_vehicles = 50, lookahead_75 camera (crop 230 px)
+    k = min(args.pool, 1024)
+    return _cached_pool("rdm_dense_50", [dict(scene="rdm", num_vehicles=50, route_dist_range=(30, 130), scene_seed=i)
+                                         for i in range(k)], pad=230)
 
 
 def run_ours(args):

@@ -1,8 +1,8 @@
-"""Host-side scene generation for the scripted scenarios -> scene-pool entries.
+"""Host-side scene generation -> scene-pool entries.
 
 The device never generates scenes: resets draw from a device-resident pool.
 This module rebuilds, on the host, exactly the state the reference reaches at the end of
-`CarlaBEV.reset` for the closed-form scenarios:
+`CarlaBEV.reset` for every generated scene kind:
 
   * seeding        -- src/randomness.py:13-65 (sha256-derived sub-seeds, RNGBundle)
   * lead_brake     -- src/scenes/scenarios/lead_brake.py:18-129
@@ -12,11 +12,14 @@ This module rebuilds, on the host, exactly the state the reference reaches at th
                       control/stanley_controller.py:34-49 + control/utils.py:200-269 (smoothing, jitter),
                       actors/actor.py:86-108 (actor controllers start at cruise speed)
 
-`rdm` and `red_light_runner` scenes need the reference's lane graphs (networkx pickles); they are
-exported from the reference by oracle/gen_golden.py / tools and shipped as packed pool files.
+  * rdm            -- managers/scene_generator.py:196-344, scenes/utils.py:75-214 (random routes on the lane
+                      graphs; lanegraph.py holds the graphs and the shortest-path search)
+  * red_light_runner -- src/scenes/scenarios/red_light_running.py:13-245
+  * actor start jitter draws from a deep copy of the bundle's generator (managers/actor_manager.py:88-95)
 """
 from __future__ import annotations
 
+import copy
 import hashlib
 import random
 
@@ -38,14 +41,17 @@ def derive_seed(base_seed: int, *parts) -> int:
 
 
 class RNGBundle:
-    """randomness.py:35-65 (the streams the scripted scenarios consume)."""
+    """randomness.py:35-65 (the streams scene generation consumes)."""
 
     def __init__(self, scene_seed, route_seed=None, traffic_seed=None, scenario_seed=None):
         self.scene_seed = int(scene_seed)
         self.route_seed = derive_seed(scene_seed, "route") if route_seed is None else int(route_seed)
         self.traffic_seed = derive_seed(scene_seed, "traffic") if traffic_seed is None else int(traffic_seed)
         self.scenario_seed = derive_seed(scene_seed, "scenario") if scenario_seed is None else int(scenario_seed)
+        self.route_rng = random.Random(self.route_seed)
+        self.traffic_rng = random.Random(self.traffic_seed)
         self.scenario_rng = random.Random(self.scenario_seed)
+        self.traffic_np_rng = np.random.default_rng(self.traffic_seed)
         self.route_np_rng = np.random.default_rng(self.route_seed)
         self.scenario_np_rng = np.random.default_rng(self.scenario_seed)
 
@@ -198,6 +204,64 @@ def _route_length_m(rx, ry) -> float:
     return float(total) * MPP
 
 
+def _assemble(agent, specs, len_route, hero_np_rng, actor_np_rngs, kind, level, scene_seed, lights=()) -> dict:
+    """Scene.load_scene (scenes/scene.py:61-88) on a sampled actor dict -> pool entry: int32 ego route, hero spawn
+    with its start jitter, then ActorManager.reset_all (vehicles, then pedestrians; each Controller.set_route draws
+    two jitter integers from that actor's generator)."""
+    ego_rx, ego_ry, init_mps, target_mps = agent
+    rx_i = np.array(ego_rx, dtype=np.int32)                  # scene.py:192-193: truncation to int32
+    ry_i = np.array(ego_ry, dtype=np.int32)
+    s = empty_scene()
+    v0 = float(init_mps) / MPP
+    st0, _, cx, cy, cyaw = controller_init(rx_i, ry_i, v0, hero_np_rng)
+    # BaseAgent.__init__: second stanley_control() with the route yaw (hero.py:84-86)
+    t0 = _nearest(st0[0], st0[1], 0.0, cx, cy)
+    t1 = _nearest(st0[0], st0[1], st0[2], cx, cy)
+    tidx = t0 if t0 >= t1 else t1
+    s.update(ego_state0=st0, ego_target_speed=np.float64(float(target_mps) / MPP), ego_tidx0=np.int32(tidx),
+             ego_cx=cx, ego_cy=cy, ego_cyaw=cyaw, rew_rx=rx_i, rew_ry=ry_i,
+             route_length_m=np.float64(_route_length_m(rx_i, ry_i)), len_ego_route=np.float64(len_route),
+             num_vehicles=np.int32(sum(1 for a in specs if a.kind == 0)), kind=np.int32(KIND_IDS[kind]),
+             level=np.int32(level), seed=np.int64(scene_seed))
+    st, ti, rcx, rcy, rcyaw, roff, wx, wy, woff = [], [], [], [], [], [0], [], [], [0]
+    # ActorManager.load deep-copies the actor dict (actor_manager.py:88-95): every actor of one load shares ONE copy
+    # of its generator, so start jitter never advances the bundle's own stream (a retry re-draws the same jitter).
+    copies = {id(g): copy.deepcopy(g) for g in actor_np_rngs}
+    for a, np_rng in zip(specs, (copies[id(g)] for g in actor_np_rngs)):
+        cruise_px = a.speed_mps / MPP
+        a_st, a_t, acx, acy, acyaw = controller_init(a.rx, a.ry, cruise_px, np_rng)
+        st.append(a_st)
+        ti.append(a_t)
+        rcx.append(acx), rcy.append(acy), rcyaw.append(acyaw)
+        roff.append(roff[-1] + len(acx))
+        wx.append(np.asarray(a.rx, dtype=np.float64)), wy.append(np.asarray(a.ry, dtype=np.float64))
+        woff.append(woff[-1] + len(a.rx))
+    n = len(specs)
+    cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0)  # noqa: E731
+    s.update(act_kind=np.array([a.kind for a in specs], dtype=np.uint8),
+             act_state0=np.array(st, dtype=np.float64).reshape(n, 4), act_tidx0=np.array(ti, dtype=np.int32),
+             act_cruise_px=np.array([a.speed_mps / MPP for a in specs], dtype=np.float64),
+             act_cruise_mps=np.array([a.speed_mps for a in specs], dtype=np.float64),
+             act_beh=np.array([a.beh for a in specs], dtype=np.uint8),
+             act_beh_p=np.array([a.beh_p for a in specs], dtype=np.float64).reshape(n, 4),
+             act_cx=cat(rcx), act_cy=cat(rcy), act_cyaw=cat(rcyaw),
+             act_route_off=np.array(roff, dtype=np.int32), act_raw_x=cat(wx),
+             act_raw_y=cat(wy), act_raw_off=np.array(woff, dtype=np.int32))
+    if lights:
+        s["tl_rect"] = np.array([r for r, _ in lights], dtype=np.int32).reshape(-1, 4)
+        s["tl_color"] = np.array([c for _, c in lights], dtype=np.uint8)
+    return s
+
+
+def _reset_loop(sample, bundle, cls_map, pad, max_reset_attempts, what):
+    """CarlaBEV.reset's retry loop (carlabev.py:108-131): resample on an invalid spawn, generators keep running."""
+    for _ in range(max_reset_attempts):
+        s = sample()
+        if cls_map is None or _spawn_valid(s, cls_map, pad):
+            return s
+    raise RuntimeError(f"Failed to reset into a valid initial state after {max_reset_attempts} attempts ({what})")
+
+
 def build_scripted_scene(kind: str, scene_seed: int, level: int | None = None, cls_map=None, pad: int = 182,
                          max_reset_attempts: int = 10) -> dict:
     """CarlaBEV.reset for scene in {"lead_brake", "jaywalk"} -> pool entry.
@@ -207,54 +271,279 @@ def build_scripted_scene(kind: str, scene_seed: int, level: int | None = None, c
     if kind not in _SAMPLERS:
         raise KeyError(f"Unknown scenario '{kind}'")
     bundle = RNGBundle(scene_seed)
-    last = None
-    for _ in range(max_reset_attempts):
+
+    def sample():
         lvl = level
         if lvl is None:
             lvl = bundle.scenario_rng.choice([1, 2, 3, 4])  # scene_generator.py:171-176
         agent, specs = _SAMPLERS[kind](int(lvl), bundle.scenario_np_rng)
-        ego_rx, ego_ry, init_mps, target_mps = agent
-        len_route = _route_length_m(ego_rx, ego_ry)              # compute_total_dist_m
-        rx_i = np.array(ego_rx, dtype=np.int32)                  # scene.py:192-193: truncation to int32
-        ry_i = np.array(ego_ry, dtype=np.int32)
-        s = empty_scene()
-        v0 = float(init_mps) / MPP
-        st0, _, cx, cy, cyaw = controller_init(rx_i, ry_i, v0, bundle.route_np_rng)
-        # BaseAgent.__init__: second stanley_control() with the route yaw (hero.py:84-86)
-        t0 = _nearest(st0[0], st0[1], 0.0, cx, cy)
-        t1 = _nearest(st0[0], st0[1], st0[2], cx, cy)
-        tidx = t0 if t0 >= t1 else t1
-        s.update(ego_state0=st0, ego_target_speed=np.float64(float(target_mps) / MPP), ego_tidx0=np.int32(tidx),
-                 ego_cx=cx, ego_cy=cy, ego_cyaw=cyaw, rew_rx=rx_i, rew_ry=ry_i,
-                 route_length_m=np.float64(_route_length_m(rx_i, ry_i)), len_ego_route=np.float64(len_route),
-                 num_vehicles=np.int32(sum(1 for a in specs if a.kind == 0)), kind=np.int32(KIND_IDS[kind]),
-                 level=np.int32(lvl), seed=np.int64(scene_seed))
-        # ActorManager.reset_all: vehicles then pedestrians, each Controller.set_route(v0=cruise) draws 2 jitter ints
-        st, ti, rcx, rcy, rcyaw, roff, wx, wy, woff = [], [], [], [], [], [0], [], [], [0]
-        for a in specs:
-            cruise_px = a.speed_mps / MPP
-            a_st, a_t, acx, acy, acyaw = controller_init(a.rx, a.ry, cruise_px, bundle.scenario_np_rng)
-            st.append(a_st)
-            ti.append(a_t)
-            rcx.append(acx), rcy.append(acy), rcyaw.append(acyaw)
-            roff.append(roff[-1] + len(acx))
-            wx.append(np.asarray(a.rx, dtype=np.float64)), wy.append(np.asarray(a.ry, dtype=np.float64))
-            woff.append(woff[-1] + len(a.rx))
-        n = len(specs)
-        s.update(act_kind=np.array([a.kind for a in specs], dtype=np.uint8),
-                 act_state0=np.array(st, dtype=np.float64).reshape(n, 4), act_tidx0=np.array(ti, dtype=np.int32),
-                 act_cruise_px=np.array([a.speed_mps / MPP for a in specs], dtype=np.float64),
-                 act_cruise_mps=np.array([a.speed_mps for a in specs], dtype=np.float64),
-                 act_beh=np.array([a.beh for a in specs], dtype=np.uint8),
-                 act_beh_p=np.array([a.beh_p for a in specs], dtype=np.float64).reshape(n, 4),
-                 act_cx=np.concatenate(rcx), act_cy=np.concatenate(rcy), act_cyaw=np.concatenate(rcyaw),
-                 act_route_off=np.array(roff, dtype=np.int32), act_raw_x=np.concatenate(wx),
-                 act_raw_y=np.concatenate(wy), act_raw_off=np.array(woff, dtype=np.int32))
-        last = s
-        if cls_map is None or _spawn_valid(s, cls_map, pad):
-            return s
-    raise RuntimeError(f"Failed to reset into a valid initial state after {max_reset_attempts} attempts "
-                       f"(kind={kind}, seed={scene_seed}, last level={int(last['level'])})")
+        len_route = _route_length_m(agent[0], agent[1])             # compute_total_dist_m
+        return _assemble(agent, specs, len_route, bundle.route_np_rng, [bundle.scenario_np_rng] * len(specs),
+                         kind, lvl, scene_seed)
+
+    return _reset_loop(sample, bundle, cls_map, pad, max_reset_attempts, f"kind={kind}, seed={scene_seed}")
+
+
+# ---- scenes that need the lane graphs ----------------------------------------------------------------------------------
+DIFFICULTY_PRESETS = {  # config/difficulty.py:22-47: (traffic_enabled, num_vehicles, route_dist_range)
+    "rt_no_traffic_v1": (False, 0, (30, 80)),
+    "rt_easy_v1": (True, 8, (30, 80)),
+    "rt_medium_v1": (True, 16, (40, 100)),
+    "rt_hard_v1": (True, 25, (50, 130)),
+}
+_EGO_GRAPHS = {"full_vehicle": ("vehicle-full", "vehicle"), "right_lane": ("vehicle-R", "R"),
+               "left_lane": ("vehicle-L", "L")}  # scene_generator.py:252-268
+
+
+def _ego_route_in_range(graph, node_cls, lo_m, hi_m, rng, max_attempts=100):
+    """find_route_in_range (scenes/utils.py:121-214) without route-profile filters: two random nodes, shortest
+    path thinned at 10 raw px, waypoints of path[1:] in surface pixels, accepted when lo <= length [m] <= hi."""
+    for _ in range(max_attempts):
+        a = graph.random_node(node_cls, rng)
+        b = graph.random_node(node_cls, rng)
+        if a == b:
+            continue
+        path = graph.find_path(a, b)
+        if len(path) < 2:
+            continue
+        pts = [graph.pos_surface(n) for n in path[1:]]
+        rx, ry = [p[0] for p in pts], [p[1] for p in pts]
+        total = _route_length_m(rx, ry)
+        if lo_m <= total <= hi_m:
+            return rx, ry, total
+    return None
+
+
+def sample_rdm(bundle, num_vehicles, dist_range, ego_target_speed=12.0, ego_route_graph="full_vehicle",
+               traffic_enabled=True, max_route_attempts=20):
+    """SceneGenerator.generate_random (managers/scene_generator.py:196-330) + get_actor (:333-344)."""
+    from .lanegraph import load_graph
+
+    if ego_route_graph not in _EGO_GRAPHS:
+        raise ValueError(f"Unsupported ego_route_graph={ego_route_graph!r}. "
+                         "Expected one of: full_vehicle, right_lane, left_lane.")
+    key, node_cls = _EGO_GRAPHS[ego_route_graph]
+    graph = load_graph(key)
+    ego = None
+    for _ in range(max_route_attempts):
+        ego = _ego_route_in_range(graph, node_cls, dist_range[0], dist_range[1], bundle.route_rng)
+        if ego is not None and len(ego[0]) > 1:
+            break
+        ego = None
+    if ego is None:
+        raise RuntimeError(f"Failed to generate a valid ego route in range {list(dist_range)} after "
+                           f"{max_route_attempts} attempts.")
+    rx, ry, len_route = ego
+    specs = []
+    for _ in range(int(num_vehicles) if traffic_enabled else 0):
+        lane = bundle.traffic_rng.choice(["L", "R"])
+        g = load_graph(f"vehicle-{lane}")
+        n1 = g.random_node(lane, bundle.traffic_rng)
+        n2 = g.random_node(lane, bundle.traffic_rng)
+        path = g.find_path(n1, n2)
+        pts = [g.pos_surface(n) for n in path[1:-1]]      # find_route, scenes/utils.py:94-108
+        if len(pts) > 5:
+            specs.append(_ActorSpec(0, [p[0] for p in pts], [p[1] for p in pts], 12.0))  # Vehicle(target_speed=12.0)
+    return (rx, ry, 0.0, float(ego_target_speed)), specs, len_route
+
+
+def build_rdm_scene(scene_seed: int, difficulty_id: str | None = None, num_vehicles: int | None = None,
+                    route_dist_range=None, ego_target_speed: float | None = None, ego_route_graph="full_vehicle",
+                    traffic_enabled: bool | None = None, max_route_attempts: int | None = None, cls_map=None,
+                    pad: int = 182, max_reset_attempts: int = 10, max_vehicles: int = 50, **unsupported) -> dict:
+    """CarlaBEV.reset(options={"scene": "rdm", ...}) -> pool entry (random navigation with background traffic).
+
+    Option meaning and defaults follow build_scene (scene_generator.py:95-168): `num_vehicles` defaults to
+    EnvConfig.max_vehicles, `route_dist_range` to [30, 100], `ego_target_speed` to 12 m/s; `difficulty_id`
+    expands like build_random_navigation_options (config/reset.py:104-116).  Vehicles draw lanes / nodes from
+    traffic_rng and start jitter from traffic_np_rng, the ego route from route_rng, the hero jitter from
+    route_np_rng (src/randomness.py)."""
+    bad = [k for k in ("route_profile", "route_profile_mix", "min_turns", "max_turns", "intersection_required")
+           if unsupported.get(k) is not None]
+    if bad:
+        raise NotImplementedError(f"route-profile filters are not built (SURVEY.md section 2, out of scope): {bad}")
+    if difficulty_id is not None:
+        if difficulty_id not in DIFFICULTY_PRESETS:
+            raise KeyError(f"Unknown difficulty_id={difficulty_id!r}. Available difficulty presets: "
+                           + ", ".join(sorted(DIFFICULTY_PRESETS)))
+        traffic_enabled, num_vehicles, route_dist_range = DIFFICULTY_PRESETS[difficulty_id]
+    num_vehicles = max_vehicles if num_vehicles is None else num_vehicles
+    route_dist_range = [30, 100] if route_dist_range is None else route_dist_range
+    bundle = RNGBundle(scene_seed, unsupported.get("route_seed"), unsupported.get("traffic_seed"),
+                       unsupported.get("scenario_seed"))
+
+    def sample():
+        agent, specs, len_route = sample_rdm(bundle, num_vehicles, route_dist_range,
+                                             12.0 if ego_target_speed is None else ego_target_speed,
+                                             ego_route_graph, True if traffic_enabled is None else traffic_enabled,
+                                             20 if max_route_attempts is None else int(max_route_attempts))
+        return _assemble(agent, specs, len_route, bundle.route_np_rng, [bundle.traffic_np_rng] * len(specs),
+                         "rdm", 0, scene_seed)
+
+    return _reset_loop(sample, bundle, cls_map, pad, max_reset_attempts, f"kind=rdm, seed={scene_seed}")
+
+
+# red_light_running.py:24-41: intersection centres as (raw_y, raw_x)
+_INTERSECTIONS = ((8642, 1564), (8654, 6755), (7250, 1552), (7241, 2446), (7242, 3652), (7242, 4704), (7257, 6773),
+                  (6199, 1552), (6197, 2439), (3349, 1545), (3350, 2456), (3350, 3639), (3335, 4714), (3315, 6773),
+                  (2456, 1563), (2446, 6757))
+PAL_ROUTE, PAL_TL_RED = 5, 6  # palette indices (include/cbev.h CBEV_PAL_*): a green strip is drawn in the route colour
+
+
+def _direction_key(dx, dy):
+    if abs(dx) > abs(dy):
+        return "east" if dx > 0 else "west"
+    return "south" if dy > 0 else "north"
+
+
+def _select_intersection(graph, intersection_index=None, anchor_x=None, anchor_y=None):
+    """RedLightRunningScenario._select_intersection (red_light_running.py:73-107): candidates by distance to the
+    requested centre / anchor (else list order); the first with lane nodes in all four directions within 1200 raw px."""
+    centres = [np.array([float(x), float(y)]) for y, x in _INTERSECTIONS]
+    if intersection_index is not None:
+        idx = int(intersection_index)
+        if not 0 <= idx < len(centres):
+            raise IndexError(f"intersection_index {idx} out of range for red_light_runner.")
+        order = [i for _, i in sorted((float(np.linalg.norm(c - centres[idx])), i) for i, c in enumerate(centres))]
+    elif anchor_x is not None and anchor_y is not None:
+        anchor = np.array([anchor_x * 8.0, anchor_y * 8.0], dtype=float)
+        order = [i for _, i in sorted((float(np.linalg.norm(c - anchor)), i) for i, c in enumerate(centres))]
+    else:
+        order = list(range(len(centres)))
+    for i in order:
+        delta = graph.pos - centres[i]
+        near = np.linalg.norm(delta, axis=1) < 1200.0
+        seen = {_direction_key(dx, dy) for dx, dy in delta[near]}
+        if len(seen) == 4:
+            return i, centres[i]
+    raise RuntimeError("No valid 4-way intersection candidate found for red_light_runner.")
+
+
+def _candidate_nodes(graph, centre, direction, min_dist=150.0, max_dist=1500.0):
+    """_candidate_nodes (red_light_running.py:109-128): nodes of one approach ordered by |dist - 950| + 0.2 lateral."""
+    cands = []
+    for n in range(len(graph.names)):
+        delta = graph.pos[n] - centre
+        dist = np.linalg.norm(delta)
+        if not (min_dist <= dist <= max_dist) or _direction_key(delta[0], delta[1]) != direction:
+            continue
+        lateral = abs(delta[0]) if direction in ("north", "south") else abs(delta[1])
+        cands.append((abs(dist - 950.0) + 0.2 * lateral, n))
+    cands.sort(key=lambda item: item[0])
+    return [n for _, n in cands]
+
+
+def _straight_route(graph, centre, start_dir, end_dir):
+    """_sample_straight_route (red_light_running.py:139-165): first of the 25 x 25 best node pairs whose shortest
+    path passes within 180 raw px of the centre with at least 6 nodes; waypoints = float raw positions / 8."""
+    from .lanegraph import NoPath
+
+    starts = _candidate_nodes(graph, centre, start_dir)[:25]
+    ends = _candidate_nodes(graph, centre, end_dir)[:25]
+    for a in starts:
+        for b in ends:
+            try:
+                path = graph.shortest_path(a, b)
+            except NoPath:
+                continue
+            coords = graph.pos[path]
+            if min(float(np.linalg.norm(p - centre)) for p in coords) > 180.0 or len(coords) < 6:
+                continue
+            return [float(p[0]) / 8.0 for p in coords], [float(p[1]) / 8.0 for p in coords]
+    raise RuntimeError(f"Unable to build a valid {start_dir}->{end_dir} route through the selected 4-way intersection.")
+
+
+def _stop_line(centre_surface, direction, color):
+    """_build_stop_line + TrafficLight._update_rect (red_light_running.py:167-199, traffic_light.py:60-72):
+    8 m x (0.45 m + 1 px) strip, 4 m before the centre; pygame.Rect truncates its float arguments."""
+    off, length, width = m2s(4.0), m2s(8.0), m2s(0.45) + 1.0
+    x, y = float(centre_surface[0]), float(centre_surface[1])
+    if direction == "south":
+        y, horizontal = y + off, True
+    elif direction == "north":
+        y, horizontal = y - off, True
+    elif direction == "west":
+        x, horizontal = x - off, False
+    else:
+        x, horizontal = x + off, False
+    w, h = (length, width) if horizontal else (width, length)
+    return [int(x - w / 2), int(y - h / 2), int(w), int(h)], color
+
+
+def build_red_light_scene(scene_seed: int, intersection_index=None, anchor_x=None, anchor_y=None, ego_speed=10.0,
+                          adv_speed=16.0, level=None, cls_map=None, pad: int = 182, max_reset_attempts: int = 10,
+                          **seeds) -> dict:
+    """CarlaBEV.reset(options={"scene": "red_light_runner", ...}) -> pool entry (red_light_running.py:201-245).
+
+    The geometry is fixed by the intersection; only the +-1 px start jitters vary.  The hero's comes from
+    route_np_rng as in the reference.  The adversary's generator is `None` in the reference, so its jitter is drawn
+    from an unseeded `np.random.default_rng()` there (quirk C-10): here it is drawn from a stream derived from the
+    scene seed, which is one of the nine realisations the reference can produce for that seed."""
+    from .lanegraph import load_graph
+
+    graph = load_graph("vehicle")
+    bundle = RNGBundle(scene_seed, seeds.get("route_seed"), seeds.get("traffic_seed"), seeds.get("scenario_seed"))
+    adv_np_rng = np.random.default_rng(derive_seed(scene_seed, "adversary_jitter"))
+
+    def sample():
+        if level is None:
+            bundle.scenario_rng.choice([1, 2, 3, 4])            # scene_generator.py:171-176 (the level is unused)
+        _, centre = _select_intersection(graph, intersection_index, anchor_x, anchor_y)
+        ego_rx, ego_ry = _straight_route(graph, centre, "south", "north")
+        adv_rx, adv_ry = _straight_route(graph, centre, "west", "east")
+        centre_s = centre / 8.0
+        lights = [_stop_line(centre_s, "south", PAL_ROUTE), _stop_line(centre_s, "west", PAL_TL_RED)]
+        return _assemble((ego_rx, ego_ry, ego_speed, ego_speed), [_ActorSpec(0, adv_rx, adv_ry, adv_speed)],
+                         _route_length_m(ego_rx, ego_ry), bundle.route_np_rng, [adv_np_rng], "red_light_runner",
+                         level or 0, scene_seed, lights)
+
+    return _reset_loop(sample, bundle, cls_map, pad, max_reset_attempts, f"kind=red_light_runner, seed={scene_seed}")
+
+
+def build_scene(options: dict, cls_map=None, pad: int = 182, max_vehicles: int = 50) -> dict:
+    """Host mirror of CarlaBEV.reset(options=...) -> SceneGenerator.build_scene (scene_generator.py:95-194) for
+    the generated scene kinds: one reset-options dict -> one pool entry."""
+    o = dict(options)
+    o.pop("reset_mask", None)
+    scene = o.pop("scene", "rdm")
+    seed = int(o.pop("scene_seed", 0))
+    common = dict(cls_map=cls_map, pad=pad, max_reset_attempts=o.pop("max_reset_attempts", 10))
+    if scene == "rdm":
+        return build_rdm_scene(seed, max_vehicles=max_vehicles, **common, **o)
+    if scene in _SAMPLERS:
+        return build_scripted_scene(scene, seed, level=o.get("level"), **common)
+    if scene == "red_light_runner":
+        return build_red_light_scene(seed, **common, **o)
+    raise KeyError(f"Unknown scenario '{scene}' (authored JSON scenes ship as a pool: pool.load_shipped_pool)")
+
+
+def _build_chunk(args):
+    requests, pad, max_vehicles = args
+    from .vector_env import load_town01_map
+
+    cls = load_town01_map()
+    return [build_scene(r, cls_map=cls, pad=pad, max_vehicles=max_vehicles) for r in requests]
+
+
+def build_pool(requests: list[dict], pad: int = 182, max_vehicles: int = 50, workers: int | None = None) -> list[dict]:
+    """Reset-option dicts -> pool entries, on `workers` host processes (default: one per core, serial for small
+    pools).  Scene generation is host work by design (the device steps scenes, it does not build them)."""
+    import os
+
+    n = len(requests)
+    workers = min(os.cpu_count() or 1, 32) if workers is None else workers
+    if workers <= 1 or n < 64:
+        return _build_chunk((requests, pad, max_vehicles))
+    import multiprocessing as mp
+
+    chunks = [list(range(w, n, workers)) for w in range(workers)]
+    with mp.get_context("spawn").Pool(workers) as pool:
+        parts = pool.map(_build_chunk, [([requests[i] for i in c], pad, max_vehicles) for c in chunks])
+    out = [None] * n
+    for c, part in zip(chunks, parts):
+        for i, sc in zip(c, part):
+            out[i] = sc
+    return out
 
 
 def _spawn_valid(s, cls_map, pad) -> bool:

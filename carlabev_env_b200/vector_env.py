@@ -114,6 +114,7 @@ class CarlaBEVVectorEnv:
         self._needs_reset = np.ones(self.num_envs, dtype=bool)
         self._scene_of_env = np.zeros(self.num_envs, dtype=np.int64)
         self.current_hero = None
+        self._generated, self._shipped_lists = {}, {}
 
     @staticmethod
     def _crop_size(env) -> int:
@@ -125,6 +126,17 @@ class CarlaBEVVectorEnv:
         return max(env.size, int(math.ceil(2.0 * math.hypot(max(ax, m - ax), max(ay, m - ay)))))
 
     # ---------------------------------------------------------------- pool
+    def _shipped_scenes(self, name):
+        if name not in self._shipped_lists:
+            self._shipped_lists[name] = load_shipped_pool(name)
+        return self._shipped_lists[name]
+
+    def _check_actor_capacity(self):
+        need = max(len(s["act_kind"]) for s in self._scenes)
+        if need > self.engine.cfg.max_actors:
+            raise ValueError(f"scene with {need} actors exceeds the engine's max_actors={self.engine.cfg.max_actors} "
+                             "(EnvConfig.max_vehicles + 2); raise max_vehicles")
+
     def set_scene_pool(self, scenes):
         """Replace the device-resident pool (list of scene dicts, see pool.py)."""
         self._scenes = list(scenes)
@@ -146,31 +158,6 @@ class CarlaBEVVectorEnv:
                                    "options={'scene': 'lead_brake' | 'jaywalk', ...}")
             base = int(options.get("scene_seed", options.get("_vector_seed", self.env_cfg.seed)))
             return (base + np.arange(n)) % len(self._scenes)
-        if scene in ("lead_brake", "jaywalk"):
-            # SyncVectorEnv passes the same options to every env: with options["scene_seed"] every env gets the
-            # same scene (like the reference); with reset(seed=s) env i is seeded s + i (gymnasium vector reset).
-            level = options.get("level")
-            if "scene_seed" in options:
-                seeds = np.full(n, int(options["scene_seed"]), dtype=np.int64)
-            elif "_vector_seed" in options:
-                seeds = int(options["_vector_seed"]) + np.arange(n, dtype=np.int64)
-            else:
-                seeds = np.full(n, int(self.env_cfg.seed), dtype=np.int64)
-            cache = getattr(self, "_scripted_cache", {})
-            wanted = np.unique(seeds if mask is None else seeds[mask])
-            new = [int(sd) for sd in wanted if (scene, level, int(sd)) not in cache]
-            for sd in new:
-                sc = S.build_scripted_scene(scene, sd, level=level, cls_map=self.cls_map, pad=self.pad,
-                                            max_reset_attempts=options.get("max_reset_attempts", 10))
-                self._scenes.append(sc)
-                cache[(scene, level, sd)] = len(self._scenes) - 1
-            if new:
-                self._scripted_cache = cache
-                self.engine.upload_pool(pack_pool(self._scenes))
-            sel = np.ones(n, bool) if mask is None else mask
-            ids = np.zeros(n, dtype=np.int64)
-            ids[sel] = [cache[(scene, level, int(sd))] for sd in seeds[sel]]
-            return ids
         if options.get("config_file") or str(scene).endswith(".json"):
             # authored scenes (scenarios/__init__.py:210-338): snapshots of the reference's 7 scene files x variations
             import os as _os
@@ -191,32 +178,40 @@ class CarlaBEVVectorEnv:
                 if m["config_file"] == name and m["variation_seed"] == vseed:
                     return np.full(n, base + i, dtype=np.int64)
             raise KeyError(f"authored scene {name!r} with variation_seed={vseed} is not in the shipped pool")
-        if scene in ("rdm", "red_light_runner"):
-            # generated by the reference from its lane graphs; a pool exported with exactly these options ships
-            # with the package (entry i == the reference's scene for scene_seed = i)
-            name = shipped_pool_for(options)
-            if name is not None:
-                cache = getattr(self, "_shipped_cache", {})
-                if name not in cache:
-                    sc = load_shipped_pool(name)
-                    cache[name] = (len(self._scenes), len(sc))
-                    self._scenes.extend(sc)
-                    self._shipped_cache = cache
-                    self.engine.upload_pool(pack_pool(self._scenes))
-                base, count = cache[name]
-                if "scene_seed" in options or "_vector_seed" not in options:
-                    seeds = np.full(n, int(options.get("scene_seed", self.env_cfg.seed)), dtype=np.int64)
-                else:
-                    seeds = int(options["_vector_seed"]) + np.arange(n, dtype=np.int64)
-                used = seeds if mask is None else seeds[mask]
-                if used.min() < 0 or used.max() >= count:
-                    raise ValueError(f"shipped pool {name!r} covers scene seeds 0..{count - 1}, got {int(used.min())}.."
-                                     f"{int(used.max())}")
-                return base + np.clip(seeds, 0, count - 1)
-        if scene in ("rdm", "red_light_runner") or str(scene).endswith(".json"):
-            raise NotImplementedError(
-                f"scene={scene!r} needs the reference's lane graphs / authored files on the host; export a pool with "
-                "oracle/gen_golden.py:extract_scene and pass it via scenes=... (DESIGN.md, out of scope rows)")
+        if scene in ("rdm", "lead_brake", "jaywalk", "red_light_runner"):
+            # The reference builds the scene inside reset (carlabev.py:96-148); here the host generator
+            # (scenes.py, bit-identical to the reference's post-reset state) fills the device pool on demand.
+            # SyncVectorEnv passes the same options to every env: with options["scene_seed"] every env gets the
+            # same scene; with reset(seed=s) env i is seeded s + i (gymnasium vector reset).
+            if "scene_seed" in options:
+                seeds = np.full(n, int(options["scene_seed"]), dtype=np.int64)
+            elif "_vector_seed" in options:
+                seeds = int(options["_vector_seed"]) + np.arange(n, dtype=np.int64)
+            else:
+                seeds = np.full(n, int(self.env_cfg.seed), dtype=np.int64)
+            base_opts = {k: v for k, v in options.items() if k not in ("scene_seed", "_vector_seed", "reset_mask")}
+            key = repr(sorted((k, repr(v)) for k, v in base_opts.items()))
+            cache = self._generated.setdefault(key, {})
+            sel = np.ones(n, bool) if mask is None else np.asarray(mask, bool)
+            new = [int(sd) for sd in np.unique(seeds[sel]) if int(sd) not in cache]
+            if new:
+                shipped = shipped_pool_for(options)   # snapshots exported from the reference with these options
+                ready = {}
+                if shipped is not None:
+                    pool = self._shipped_scenes(shipped)
+                    ready = {sd: pool[sd] for sd in new if 0 <= sd < len(pool)}
+                todo = [sd for sd in new if sd not in ready]
+                built = S.build_pool([{**base_opts, "scene_seed": sd} for sd in todo], pad=self.pad,
+                                     max_vehicles=self.env_cfg.max_vehicles)
+                ready.update(zip(todo, built))
+                for sd in new:
+                    self._scenes.append(ready[sd])
+                    cache[sd] = len(self._scenes) - 1
+                self._check_actor_capacity()
+                self.engine.upload_pool(pack_pool(self._scenes))
+            ids = np.zeros(n, dtype=np.int64)
+            ids[sel] = [cache[int(sd)] for sd in seeds[sel]]
+            return ids
         raise KeyError(f"Unknown scenario '{scene}'")
 
     # ---------------------------------------------------------------- gym surface

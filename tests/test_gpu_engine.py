@@ -202,8 +202,14 @@ def test_vector_env_surface_and_infos():
     assert len(set(envs._scene_of_env.tolist())) == 6            # reset(seed=s): env i is seeded s + i
     obs, _ = envs.reset(seed=3, options={"scene": "rdm", "difficulty_id": "rt_medium_v1"})
     assert len(set(envs._scene_of_env.tolist())) == 6
+    # seeds outside the shipped snapshots are generated on the host (lane graphs + shortest paths, scenes.py)
+    obs, _ = envs.reset(seed=1000, options={"scene": "rdm", "num_vehicles": 3, "route_dist_range": [30, 60]})
+    assert len(set(envs._scene_of_env.tolist())) == 6
+    assert max(len(envs._scenes[i]["act_kind"]) for i in envs._scene_of_env) <= 3
+    obs, _ = envs.reset(options={"scene": "red_light_runner", "scene_seed": 77})
+    envs.step(np.zeros((6, 3), np.float32))
     with pytest.raises(NotImplementedError):
-        envs.reset(options={"scene": "rdm", "num_vehicles": 3})
+        envs.reset(options={"scene": "rdm", "route_profile": "left_turn"})
     envs.close()
 
 

@@ -196,3 +196,111 @@ def test_stats_allreduce_gloo_world2():
     for _, _, _, out in res:
         assert out["episodes"] == 64 and out["env_steps"] == 640
         assert abs(out["mean_return"] - 3.0 / 64) < 1e-12 and abs(out["rate_collision"] - 6.0 / 64) < 1e-12
+
+
+# ---- lane graphs and graph-backed scene generation (rdm, red_light_runner) ------------------------------------------------
+def _same_scene(a, b, skip=()):
+    return [k for k in a if k not in skip
+            and (np.asarray(a[k]).shape != np.asarray(b[k]).shape or not np.array_equal(a[k], b[k]))]
+
+
+@pytest.mark.parametrize("key", ["vehicle-full", "vehicle", "vehicle-L", "vehicle-R"])
+def test_lanegraph_shortest_path_matches_networkx(key):
+    """LaneGraph.shortest_path restates networkx.bidirectional_dijkstra (what the reference calls through
+    nx.shortest_path(..., weight="cost")): same node sequence, including equal-cost ties, and the same NoPath."""
+    nx = pytest.importorskip("networkx")
+    import random
+
+    from carlabev_env_b200.lanegraph import NoPath, load_graph
+
+    g = load_graph(key)
+    G = nx.DiGraph() if g.directed else nx.Graph()
+    G.add_nodes_from(range(len(g.names)))
+    # adjacency written in the exported iteration order (it decides the tie-breaks)
+    tables = (G._succ, G._pred) if g.directed else (G._adj, G._adj)
+    for d in (0, 1):
+        for u, row in enumerate(g._adj[d]):
+            for v, cost in row:
+                tables[d][u][v] = {"cost": cost}
+    rng = random.Random(7)
+    n = len(g.names)
+    hits = 0
+    for _ in range(400):
+        a, b = rng.randrange(n), rng.randrange(n)
+        try:
+            want = nx.shortest_path(G, a, b, weight="cost")
+        except nx.NetworkXNoPath:
+            want = None
+        try:
+            got = g.shortest_path(a, b)
+        except NoPath:
+            got = None
+        assert got == want, (key, a, b)
+        hits += want is not None
+    assert hits > 50
+
+
+@pytest.mark.parametrize("name,seeds", [("rdm_rt_hard_v1", range(16, 40)), ("rdm_rt_medium_v1", range(0, 8)),
+                                        ("rdm_dense_50", range(34, 42))])
+def test_rdm_generation_matches_reference_snapshots(name, seeds):
+    """build_scene(scene="rdm") == the post-reset state of the UNMODIFIED reference for the same options and seed
+    (the shipped pools are snapshots exported by oracle/export_pools.py).  Seeds 23, 37 and 39 go through the
+    reset retry loop (first spawn overlaps a vehicle)."""
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.pool import SHIPPED_POOLS, load_shipped_pool
+
+    ref = load_shipped_pool(name)
+    cls = load_map()
+    for i in seeds:
+        got = S.build_scene({**SHIPPED_POOLS[name], "scene_seed": i}, cls_map=cls)
+        assert _same_scene(ref[i], got) == [], (name, i)
+
+
+def test_red_light_generation_matches_reference_snapshots():
+    """Everything but the adversary's start jitter (unseeded in the reference, quirk C-10) is reproduced."""
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.pool import load_shipped_pool
+
+    ref = load_shipped_pool("red_light_runner")
+    cls = load_map()
+    for i in (0, 1, 5, 17, 31):
+        got = S.build_scene({"scene": "red_light_runner", "scene_seed": i}, cls_map=cls)
+        assert _same_scene(ref[i], got, skip=("act_state0",)) == []
+        d = np.abs(ref[i]["act_state0"] - got["act_state0"])
+        assert d[:, 2:].max() == 0 and d[:, :2].max() <= 2.0
+    with pytest.raises(IndexError):
+        S.build_red_light_scene(0, intersection_index=99)
+    pinned = S.build_red_light_scene(0, intersection_index=11, cls_map=cls)   # the debug preset's intersection
+    assert len(pinned["tl_color"]) == 2 and pinned["num_vehicles"] == 1
+
+
+def test_build_pool_workers_and_option_errors():
+    from carlabev_env_b200 import scenes as S
+
+    reqs = [{"scene": "rdm", "difficulty_id": "rt_easy_v1", "scene_seed": i} for i in range(3)]
+    reqs += [{"scene": "lead_brake", "level": 2, "scene_seed": 5}, {"scene": "jaywalk", "scene_seed": 6}]
+    serial = S.build_pool(reqs, workers=1)
+    assert [int(s["kind"]) for s in serial] == [0, 0, 0, 1, 2]
+    assert all(int(s["num_vehicles"]) <= 8 for s in serial[:3])
+    again = S.build_pool(reqs, workers=1)
+    assert all(_same_scene(a, b) == [] for a, b in zip(serial, again))
+    with pytest.raises(KeyError):
+        S.build_scene({"scene": "rdm", "difficulty_id": "nope"})
+    with pytest.raises(NotImplementedError):
+        S.build_scene({"scene": "rdm", "route_profile": "left_turn"})
+    with pytest.raises(ValueError):
+        S.build_scene({"scene": "rdm", "ego_route_graph": "sidewalk"})
+    with pytest.raises(KeyError):
+        S.build_scene({"scene": "no_such_scene"})
+    no_traffic = S.build_scene({"scene": "rdm", "difficulty_id": "rt_no_traffic_v1", "scene_seed": 3})
+    assert len(no_traffic["act_kind"]) == 0 and 30.0 <= float(no_traffic["len_ego_route"]) <= 80.0
+
+
+def test_build_pool_parallel_equals_serial():
+    from carlabev_env_b200 import scenes as S
+
+    reqs = [{"scene": "lead_brake", "level": 1 + i % 3, "scene_seed": i} for i in range(60)]
+    reqs += [{"scene": "rdm", "difficulty_id": "rt_easy_v1", "scene_seed": i} for i in range(4)]
+    serial = S.build_pool(reqs, workers=1)
+    parallel = S.build_pool(reqs, workers=2)
+    assert all(_same_scene(a, b) == [] for a, b in zip(serial, parallel))
