@@ -123,15 +123,21 @@ class _ActorSpec:
         self.beh, self.beh_p = beh, tuple(float(v) for v in beh_p)
 
 
-def sample_lead_brake(level, np_rng):
-    """LeadBrakeScenario.sample, lead_brake.py:18-129 (draw order preserved)."""
-    ego_start_y = int(np_rng.integers(900, 1000))
-    lead_gap_m = float(np_rng.uniform(4.5, 12.5))
-    ego_speed = float(np_rng.uniform(8.0, 16.0))
-    lead_speed = ego_speed + float(np_rng.uniform(-2.0, 2.0))
-    brake_delay = float(np_rng.uniform(1.5, 4.0))
-    brake_strength = float(np_rng.uniform(2.0, 6.0))
-    x_center = 850
+def sample_lead_brake(level, np_rng, **kw):
+    """LeadBrakeScenario.sample, lead_brake.py:18-129 (draw order preserved).  Explicit parameters (`ego_speed`,
+    `lead_gap`, `anchor_y`, ... -- the scenario-preset / scenario-config fields, scenarios/specs.py:60-75) replace
+    the drawn value AFTER the draw: the reference evaluates `kwargs.get(key, <draw>)`, so the stream advances
+    either way."""
+    def pick(key, drawn):
+        return kw[key] if key in kw else drawn
+
+    ego_start_y = pick("anchor_y", int(np_rng.integers(900, 1000)))
+    lead_gap_m = pick("lead_gap", float(np_rng.uniform(4.5, 12.5)))
+    ego_speed = pick("ego_speed", float(np_rng.uniform(8.0, 16.0)))
+    lead_speed = pick("lead_speed", ego_speed + float(np_rng.uniform(-2.0, 2.0)))
+    brake_delay = pick("brake_delay", float(np_rng.uniform(1.5, 4.0)))
+    brake_strength = pick("brake_strength", float(np_rng.uniform(2.0, 6.0)))
+    x_center = pick("anchor_x", 850)
     lane_width = m2s(2.2)
     ego_step, lead_step, rear_step = m2s(6.25), m2s(1.56), m2s(3.12)
     ego_rx = [x_center] * 6
@@ -144,30 +150,33 @@ def sample_lead_brake(level, np_rng):
         left_ry = [ego_start_y - i * 20 for i in range(7)]
         left_rx.reverse()
         left_ry.reverse()
-        left_speed = float(np_rng.uniform(10.0, 18.0))
+        left_speed = pick("left_speed", float(np_rng.uniform(10.0, 18.0)))
         actors.append(_ActorSpec(0, left_rx, left_ry, left_speed))
     if level >= 3:
-        rear_gap_m = float(np_rng.uniform(3.0, 6.0))
+        rear_gap_m = pick("rear_gap", float(np_rng.uniform(3.0, 6.0)))
         rear_ry_start = ego_ry[0] + m2s(rear_gap_m)
         rear_ry = [rear_ry_start - i * rear_step for i in range(6)]
-        rear_speed = max(ego_speed - float(np_rng.uniform(1.0, 3.0)), 4.0)
-        rear_delay = float(np_rng.uniform(2.0, 5.0))
+        rear_speed = pick("rear_speed", max(ego_speed - float(np_rng.uniform(1.0, 3.0)), 4.0))
+        rear_delay = pick("rear_brake_delay", float(np_rng.uniform(2.0, 5.0)))
         actors.append(_ActorSpec(0, [x_center] * 6, rear_ry, rear_speed, BEH_LEAD_BRAKE,
                                  (rear_delay, brake_strength, 0, 0)))
     return (ego_rx, ego_ry, ego_speed, ego_speed), actors
 
 
-def sample_jaywalk(level, np_rng):
-    """JaywalkScenario.sample, jaywalk.py:29-117 (draw order preserved)."""
-    ego_start_y = int(np_rng.integers(900, 1000))
-    ego_speed = float(np_rng.uniform(8.0, 14.0))
-    ped_x_base = 850
+def sample_jaywalk(level, np_rng, **kw):
+    """JaywalkScenario.sample, jaywalk.py:29-117 (draw order preserved; overrides as in sample_lead_brake)."""
+    def pick(key, drawn):
+        return kw[key] if key in kw else drawn
+
+    ego_start_y = pick("anchor_y", int(np_rng.integers(900, 1000)))
+    ego_speed = pick("ego_speed", float(np_rng.uniform(8.0, 14.0)))
+    ped_x_base = pick("anchor_x", 850)
     lane_width = m2s(1.6)
-    cross_offset_m = float(np_rng.uniform(-3.0, 3.0))
-    cross_delay = float(np_rng.uniform(1.0, 2.5))
-    pedestrian_speed = float(np_rng.uniform(1.2, 2.2))
+    cross_offset_m = pick("cross_offset", float(np_rng.uniform(-3.0, 3.0)))
+    cross_delay = pick("cross_delay", float(np_rng.uniform(1.0, 2.5)))
+    pedestrian_speed = pick("pedestrian_speed", float(np_rng.uniform(1.2, 2.2)))
     ego_step, rear_step = m2s(6.25), m2s(3.12)
-    yield_duration = float(np_rng.uniform(0.8, 1.6))
+    yield_duration = pick("yield_duration", float(np_rng.uniform(0.8, 1.6)))
     ego_rx = [ped_x_base] * 6
     ego_ry = [ego_start_y - i * ego_step for i in range(6)]
     cross_offset = m2s(cross_offset_m)
@@ -185,10 +194,10 @@ def sample_jaywalk(level, np_rng):
     peds = [_ActorSpec(1, ped_rx, ped_ry, pedestrian_speed, beh, p)]
     vehicles = []
     if level >= 4:
-        rear_gap_m = float(np_rng.uniform(3.0, 6.0))
+        rear_gap_m = pick("rear_gap", float(np_rng.uniform(3.0, 6.0)))
         rear_ry_start = ego_ry[0] + m2s(rear_gap_m)
         rear_ry = [rear_ry_start - i * rear_step for i in range(6)]
-        rear_speed = max(ego_speed - float(np_rng.uniform(1.0, 3.0)), 4.0)
+        rear_speed = pick("rear_speed", max(ego_speed - float(np_rng.uniform(1.0, 3.0)), 4.0))
         vehicles.append(_ActorSpec(0, [ped_x_base] * 6, rear_ry, rear_speed))
     return (ego_rx, ego_ry, ego_speed, ego_speed), vehicles + peds
 
@@ -262,21 +271,30 @@ def _reset_loop(sample, bundle, cls_map, pad, max_reset_attempts, what):
     raise RuntimeError(f"Failed to reset into a valid initial state after {max_reset_attempts} attempts ({what})")
 
 
+_SCENARIO_FIELDS = {  # scenarios/specs.py:47-90 (+ the anchor the samplers read)
+    "lead_brake": ("ego_speed", "lead_gap", "lead_speed", "brake_delay", "brake_strength", "left_speed", "rear_gap",
+                   "rear_speed", "rear_brake_delay", "anchor_x", "anchor_y"),
+    "jaywalk": ("ego_speed", "cross_delay", "pedestrian_speed", "cross_offset", "yield_duration", "rear_gap",
+                "rear_speed", "anchor_x", "anchor_y"),
+}
+
+
 def build_scripted_scene(kind: str, scene_seed: int, level: int | None = None, cls_map=None, pad: int = 182,
-                         max_reset_attempts: int = 10) -> dict:
+                         max_reset_attempts: int = 10, **params) -> dict:
     """CarlaBEV.reset for scene in {"lead_brake", "jaywalk"} -> pool entry.
 
     `cls_map` (H, W) uint8 classes enables the reference's spawn validation / retry loop
     (carlabev.py:108-131, scene.py:142-170); without it the first sample is accepted."""
     if kind not in _SAMPLERS:
         raise KeyError(f"Unknown scenario '{kind}'")
-    bundle = RNGBundle(scene_seed)
+    bundle = RNGBundle(scene_seed, params.get("route_seed"), params.get("traffic_seed"), params.get("scenario_seed"))
+    fields = {k: params[k] for k in _SCENARIO_FIELDS[kind] if params.get(k) is not None}
 
     def sample():
         lvl = level
         if lvl is None:
             lvl = bundle.scenario_rng.choice([1, 2, 3, 4])  # scene_generator.py:171-176
-        agent, specs = _SAMPLERS[kind](int(lvl), bundle.scenario_np_rng)
+        agent, specs = _SAMPLERS[kind](int(lvl), bundle.scenario_np_rng, **fields)
         len_route = _route_length_m(agent[0], agent[1])             # compute_total_dist_m
         return _assemble(agent, specs, len_route, bundle.route_np_rng, [bundle.scenario_np_rng] * len(specs),
                          kind, lvl, scene_seed)
@@ -285,12 +303,6 @@ def build_scripted_scene(kind: str, scene_seed: int, level: int | None = None, c
 
 
 # ---- scenes that need the lane graphs ----------------------------------------------------------------------------------
-DIFFICULTY_PRESETS = {  # config/difficulty.py:22-47: (traffic_enabled, num_vehicles, route_dist_range)
-    "rt_no_traffic_v1": (False, 0, (30, 80)),
-    "rt_easy_v1": (True, 8, (30, 80)),
-    "rt_medium_v1": (True, 16, (40, 100)),
-    "rt_hard_v1": (True, 25, (50, 130)),
-}
 _EGO_GRAPHS = {"full_vehicle": ("vehicle-full", "vehicle"), "right_lane": ("vehicle-R", "R"),
                "left_lane": ("vehicle-L", "L")}  # scene_generator.py:252-268
 
@@ -363,10 +375,11 @@ def build_rdm_scene(scene_seed: int, difficulty_id: str | None = None, num_vehic
     if bad:
         raise NotImplementedError(f"route-profile filters are not built (SURVEY.md section 2, out of scope): {bad}")
     if difficulty_id is not None:
-        if difficulty_id not in DIFFICULTY_PRESETS:
-            raise KeyError(f"Unknown difficulty_id={difficulty_id!r}. Available difficulty presets: "
-                           + ", ".join(sorted(DIFFICULTY_PRESETS)))
-        traffic_enabled, num_vehicles, route_dist_range = DIFFICULTY_PRESETS[difficulty_id]
+        from .config import get_difficulty_spec
+
+        spec = get_difficulty_spec(difficulty_id)   # KeyError lists the presets (config/difficulty.py:50-58)
+        traffic_enabled, num_vehicles, route_dist_range = (spec["traffic_enabled"], spec["num_vehicles"],
+                                                           spec["route_dist_range"])
     num_vehicles = max_vehicles if num_vehicles is None else num_vehicles
     route_dist_range = [30, 100] if route_dist_range is None else route_dist_range
     bundle = RNGBundle(scene_seed, unsupported.get("route_seed"), unsupported.get("traffic_seed"),
@@ -500,6 +513,273 @@ def build_red_light_scene(scene_seed: int, intersection_index=None, anchor_x=Non
     return _reset_loop(sample, bundle, cls_map, pad, max_reset_attempts, f"kind=red_light_runner, seed={scene_seed}")
 
 
+# ---- authored scenes and scenario-config files (JSON) ----------------------------------------------------------------
+SCENARIO_PRESETS = {  # scenarios/specs.py:95-146
+    "jaywalk_debug": dict(scene="jaywalk", level=3, ego_speed=10.0, cross_delay=1.2, pedestrian_speed=1.6,
+                          yield_duration=1.2),
+    "lead_brake_debug": dict(scene="lead_brake", level=2, ego_speed=12.0, lead_gap=8.0, lead_speed=11.0,
+                             brake_delay=2.0, brake_strength=4.0),
+    "red_light_debug": dict(scene="red_light_runner", intersection_index=11, ego_speed=10.0, adv_speed=16.0),
+    "rdm_navigation": dict(scene="rdm", num_vehicles=25, route_dist_range=[30, 130]),
+}
+_SPEC_DEFAULTS = {  # ScenarioSpec field defaults (scenarios/specs.py:47-92): a scenario-config file fixes ALL of them
+    "jaywalk": dict(ego_speed=12.0, cross_delay=1.5, pedestrian_speed=1.6, cross_offset=0.0, yield_duration=1.2,
+                    rear_gap=5.0, rear_speed=10.0),
+    "lead_brake": dict(ego_speed=12.0, lead_gap=7.5, lead_speed=12.0, brake_delay=2.5, brake_strength=4.0,
+                       left_speed=14.0, rear_gap=5.0, rear_speed=10.0, rear_brake_delay=3.0),
+    "red_light_runner": dict(ego_speed=10.0, adv_speed=16.0, intersection_index=11),
+}
+_LEGACY_BEHAVIORS = {"Normal": "constant_speed", "CrossBehavior": "cross", "StopMidBehavior": "stop_mid",
+                     "StopReturnBehavior": "yield_return", "LeadBrakeBehavior": "timed_brake"}
+_BEHAVIOR_FIELDS = {  # actors/behavior/registry.py:33-68
+    "vehicle": {"constant_speed": {}, "timed_brake": {"start_brake_t": 3.5, "decel_mps2": 1.0}},
+    "pedestrian": {"cross": {"start_delay": 0.0}, "stop_mid": {"start_delay": 0.0},
+                   "yield_return": {"start_delay": 0.0, "yield_duration": 1.0}},
+}
+
+
+def scenario_preset_options(preset_id: str, overrides: dict | None = None) -> dict:
+    """build_runtime_scenario_options (scenarios/specs.py:167-183)."""
+    if preset_id not in SCENARIO_PRESETS:
+        raise KeyError(f"Unknown scenario preset '{preset_id}'")
+    options = copy.deepcopy(SCENARIO_PRESETS[preset_id])
+    options.update({k: v for k, v in (overrides or {}).items() if v is not None})
+    return options
+
+
+def scenario_config_options(data: dict, overrides: dict | None = None) -> dict:
+    """normalize_scenario_config + build_scenario_options_from_config (scenarios/specs.py:218-272): a scenario
+    config ({"scenario_id", "level", "anchor", "parameters"} or the legacy {"scenario", "kwargs"}) -> reset options
+    with every ScenarioSpec field filled in (missing ones take the spec default, so nothing is left to the draw)."""
+    if data.get("type") == "scenario_config" or "scenario_id" in data:
+        scenario_id, level = data.get("scenario_id"), int(data.get("level", 1))
+        anchor, raw = data.get("anchor", {}) or {}, data.get("parameters", {}) or {}
+    elif "scenario" in data and "kwargs" in data:
+        raw = dict(data.get("kwargs", {}))
+        scenario_id, level = data.get("scenario"), int(raw.pop("level", 1))
+        anchor = {"x": raw.pop("anchor_x", None), "y": raw.pop("anchor_y", None)}
+        raw.pop("scene", None)
+    else:
+        raise ValueError("Unsupported scenario config format.")
+    if scenario_id not in _SPEC_DEFAULTS:
+        raise KeyError(f"Unknown scenario '{scenario_id}'")
+    options = {k: type(d)(d if raw.get(k) in (None, "") else raw[k]) for k, d in _SPEC_DEFAULTS[scenario_id].items()}
+    if anchor.get("x") is not None:
+        options["anchor_x"] = int(anchor["x"])
+    if anchor.get("y") is not None:
+        options["anchor_y"] = int(anchor["y"])
+    options["level"], options["scene"] = level, scenario_id
+    for k, v in (overrides or {}).items():
+        if k not in ("config_file", "scene", "reset_mask") and v is not None:
+            options[k] = v
+    return options
+
+
+def _behavior_of(actor_type, behavior):
+    """normalize_behavior_spec + build_behavior (actors/behavior/registry.py:101-145) -> (BEH_*, 4 parameters)."""
+    specs = _BEHAVIOR_FIELDS[actor_type]
+    if behavior in (None, "", "Normal"):
+        bid, raw = next(iter(specs)), {}
+    elif isinstance(behavior, str):
+        bid, raw = _LEGACY_BEHAVIORS.get(behavior, behavior), {}
+    else:
+        bid = _LEGACY_BEHAVIORS.get(behavior.get("type", ""), behavior.get("type", ""))
+        raw = behavior.get("params", {}) or behavior.get("behavior_kwargs", {}) or {}
+    if bid not in specs:
+        bid = next(iter(specs))
+    p = {k: float(d if raw.get(k) in (None, "") else raw[k]) for k, d in specs[bid].items()}
+    if isinstance(behavior, str) or behavior in (None, ""):
+        p = dict(specs[bid])  # a bare name carries no parameters: build_behavior falls back to its own defaults
+    if bid == "cross":
+        return BEH_CROSS, (p["start_delay"], 2.0, 0.0, 0.0)
+    if bid == "stop_mid":
+        return BEH_STOP_MID, (p["start_delay"], 0.5, -1.0, 0.0)
+    if bid == "yield_return":
+        return BEH_STOP_RETURN, (p["start_delay"], 1.0 / 3.0, p["yield_duration"], 1.0)
+    if bid == "timed_brake":
+        return BEH_LEAD_BRAKE, (p["start_brake_t"], p["decel_mps2"], 0.0, 0.0)
+    return BEH_NONE, (0.0, 0.0, 0.0, 0.0)
+
+
+def _linear_route(start, end, step_px=8):
+    """_build_linear_route (scenarios/__init__.py:12-20)."""
+    dx, dy = end[0] - start[0], end[1] - start[1]
+    n = max(2, int(max(abs(dx), abs(dy)) / max(1, step_px)) + 1)
+    return (np.linspace(start[0], end[0], n).round().astype(int).tolist(),
+            np.linspace(start[1], end[1], n).round().astype(int).tolist())
+
+
+def _route_from_waypoints(waypoints):
+    rx, ry = [], []
+    for i in range(len(waypoints) - 1):
+        sx, sy = _linear_route(waypoints[i], waypoints[i + 1])
+        rx.extend(sx[1:] if i else sx)
+        ry.extend(sy[1:] if i else sy)
+    return rx, ry
+
+
+def _variation_value(spec, rng, fallback=None):
+    """_sample_variation_value (scenarios/__init__.py:43-66)."""
+    if spec is None:
+        return fallback
+    if not isinstance(spec, dict):
+        return spec
+    mode = spec.get("mode", "fixed")
+    if mode == "fixed":
+        return spec.get("value", fallback)
+    if mode == "uniform":
+        return rng.uniform(float(spec["low"]), float(spec["high"]))
+    if mode == "normal":
+        value = rng.normalvariate(float(spec["mean"]), float(spec["std"]))
+        clip = spec.get("clip")
+        if clip is not None and len(clip) == 2:
+            value = max(float(clip[0]), min(float(clip[1]), value))
+        return value
+    if mode == "choice":
+        values = spec.get("values", [])
+        return rng.choice(list(values)) if values else fallback
+    return fallback
+
+
+def _vary_actor(actor_data, enabled, seed, global_spec, index):
+    """_apply_actor_variation (scenarios/__init__.py:113-199): one random.Random per actor, seeded
+    variation_seed + seed_offset; waypoint jitter, then speed, then behaviour parameters, then signal state."""
+    actor = copy.deepcopy(actor_data)
+    var = actor.get("variation") or {}
+    if not enabled or not var.get("enabled", False):
+        return actor
+    rng = random.Random(seed + int(var.get("seed_offset", index)))
+    if actor.get("waypoints"):
+        wps = [[int(round(p[0])), int(round(p[1]))] for p in actor["waypoints"]]
+    else:
+        rx, ry = actor.get("rx", []), actor.get("ry", [])
+        start = actor.get("start") or ({"x": rx[0], "y": ry[0]} if rx and ry else None)
+        goal = actor.get("goal") or ({"x": rx[-1], "y": ry[-1]} if rx and ry else None)
+        wps = [] if start is None or goal is None else [[int(round(start["x"])), int(round(start["y"]))],
+                                                        [int(round(goal["x"])), int(round(goal["y"]))]]
+    lock = (var.get("constraints", {}) or {}).get("lock_endpoints", True)
+    jitter = var.get("waypoint_jitter_px", global_spec.get("waypoint_jitter_px"))
+    if jitter and wps:
+        r = float(jitter)
+        varied = []
+        for i, p in enumerate(wps):
+            if lock and i in (0, len(wps) - 1):
+                varied.append(list(p))
+            else:
+                varied.append([int(round(p[0] + rng.uniform(-r, r))), int(round(p[1] + rng.uniform(-r, r)))])
+        actor["waypoints"] = varied
+        actor["start"] = {"x": varied[0][0], "y": varied[0][1]}
+        actor["goal"] = {"x": varied[-1][0], "y": varied[-1][1]}
+    speed = float(actor.get("cruise_speed", actor.get("initial_speed", actor.get("speed", 0.0))))
+    scale = _variation_value(global_spec.get("speed_scale"), rng, fallback=1.0)
+    if var.get("speed") is not None:
+        speed = float(_variation_value(var.get("speed"), rng, fallback=speed))
+    else:
+        speed = speed * float(scale)
+    speed = max(0.0, speed)
+    actor["speed"] = actor["initial_speed"] = actor["cruise_speed"] = speed
+    behavior = copy.deepcopy(actor.get("behavior") or {})
+    if isinstance(behavior, dict):
+        params = copy.deepcopy(behavior.get("params") or {})
+        changed = False
+        for key, spec in (var.get("behavior_params", {}) or {}).items():
+            if key in params:
+                params[key] = _variation_value(spec, rng, fallback=params[key])
+                changed = True
+        if changed:
+            behavior["params"] = params
+            actor["behavior"] = behavior
+    if actor.get("type") == "traffic_light" and var.get("signal_state"):
+        actor["signal_state"] = _variation_value(var.get("signal_state"), rng, fallback=actor.get("signal_state", "red"))
+    return actor
+
+
+def bundled_authored_files() -> dict:
+    """The reference's authored scene files (assets/scenes/*.json), parsed: {file name: scene dict}."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "authored_scene_files.json")
+    with open(path, "r", encoding="utf-8") as f:
+        return json.load(f)
+
+
+def build_authored_scene(config, scene_seed: int = 0, variation_enabled=None, variation_seed=None, cls_map=None,
+                         pad: int = 182, max_reset_attempts: int = 10, **overrides) -> dict:
+    """CarlaBEV.reset(options={"config_file": path, ...}) -> pool entry.  `config` is a path or the parsed JSON.
+
+    Authored scenes ({"actors": [...]}, scenarios/__init__.py:210-338): routes from `rx`/`ry` or piecewise-linear
+    waypoints, optional seeded variation of waypoints / speeds / behaviour parameters / signal states.  Their
+    scripted actors are built without a generator, so the reference draws their +-1 px start jitter from an
+    unseeded stream; here it comes from a stream derived from (scene_seed, actor index).  Files without "actors"
+    are scenario configs and resolve to the scenario sampler with every parameter pinned."""
+    if isinstance(config, (str, bytes)) or hasattr(config, "__fspath__"):
+        import json
+
+        with open(config, "r", encoding="utf-8") as f:
+            data = json.load(f)
+    else:
+        data = config
+    if "actors" not in data:
+        opts = scenario_config_options(data, overrides)
+        opts.setdefault("scene_seed", scene_seed)
+        return build_scene(opts, cls_map=cls_map, pad=pad)
+    scenario_id = data.get("scenario_id") or data.get("scenario")
+    if scenario_id not in _SPEC_DEFAULTS:
+        raise KeyError(f"Unknown scenario '{scenario_id}' in authored config")
+    variation = data.get("variation") or {}
+    enabled = bool(variation.get("enabled", False)) if variation_enabled is None else bool(variation_enabled)
+    vseed = variation_seed if variation_seed is not None else variation.get("default_seed")
+    vseed = int(vseed) if vseed is not None else 0
+    global_spec = variation.get("global", {}) or {}
+    bundle = RNGBundle(scene_seed, overrides.get("route_seed"), overrides.get("traffic_seed"),
+                       overrides.get("scenario_seed"))
+
+    def sample():
+        agent, vehicles, peds, lights = None, [], [], []
+        for idx, actor_data in enumerate(data["actors"]):
+            a = _vary_actor(actor_data, enabled, vseed, global_spec, idx)
+            atype = actor_data["type"]
+            rx, ry = a.get("rx"), a.get("ry")
+            if (not rx or not ry) and a.get("waypoints"):
+                rx, ry = _route_from_waypoints(a["waypoints"])
+            rx, ry = rx or [], ry or []
+            speed = a.get("cruise_speed", a.get("initial_speed", a.get("speed", 2.0)))
+            if atype == "agent":
+                agent = (rx, ry, speed, speed)
+            elif atype in ("vehicle", "pedestrian"):
+                beh, p = _behavior_of(atype, a.get("behavior", "constant_speed" if atype == "vehicle" else "cross"))
+                if len(rx) > 0 and len(rx) == len(ry):  # ActorManager._has_valid_route
+                    (vehicles if atype == "vehicle" else peds).append(_ActorSpec(0 if atype == "vehicle" else 1,
+                                                                                 rx, ry, speed, beh, p))
+            elif atype == "traffic_light":
+                start = a.get("start") or ({"x": rx[0], "y": ry[0]} if rx and ry else None)
+                goal = a.get("goal") or ({"x": rx[-1], "y": ry[-1]} if rx and ry else None)
+                if start is None or goal is None:
+                    continue
+                dx, dy = float(goal["x"]) - float(start["x"]), float(goal["y"]) - float(start["y"])
+                cx, cy = 0.5 * (float(start["x"]) + float(goal["x"])), 0.5 * (float(start["y"]) + float(goal["y"]))
+                horizontal = a.get("orientation", "horizontal" if abs(dx) >= abs(dy) else "vertical") == "horizontal"
+                # TrafficLight.__init__ defaults (traffic_light.py:33-42)
+                width = float(a["width"]) if a.get("width") is not None else max(1.0, m2s(0.45)) + 1.0
+                length = float(a["length"]) if a.get("length") is not None else max(4.0, m2s(8.5))
+                w, h = (length, width) if horizontal else (width, length)
+                color = {"red": PAL_TL_RED, "yellow": 7, "green": PAL_ROUTE}.get(a.get("signal_state", "red"), PAL_TL_RED)
+                lights.append(([int(cx - w / 2), int(cy - h / 2), int(w), int(h)], color))
+        if agent is None:
+            raise ValueError("authored scene has no agent")
+        # compute_total_dist_px([rx, ry]) (scenes/utils.py:217-224) pairs the two coordinate LISTS as if they were
+        # two points: the reference's `len_ego_route` of an authored scene is hypot(ry[0]-rx[0], ry[1]-rx[1])
+        rx, ry = agent[0], agent[1]
+        len_route = float(np.hypot(ry[0] - rx[0], ry[1] - rx[1]))
+        specs = vehicles + peds
+        rngs = [np.random.default_rng(derive_seed(scene_seed, "authored_jitter", i)) for i in range(len(specs))]
+        return _assemble(agent, specs, len_route, bundle.route_np_rng, rngs, scenario_id,
+                         int(data.get("level", 0) or 0), scene_seed, lights)
+
+    return _reset_loop(sample, bundle, cls_map, pad, max_reset_attempts, f"authored scene, seed={scene_seed}")
+
+
 def build_scene(options: dict, cls_map=None, pad: int = 182, max_vehicles: int = 50) -> dict:
     """Host mirror of CarlaBEV.reset(options=...) -> SceneGenerator.build_scene (scene_generator.py:95-194) for
     the generated scene kinds: one reset-options dict -> one pool entry."""
@@ -508,10 +788,12 @@ def build_scene(options: dict, cls_map=None, pad: int = 182, max_vehicles: int =
     scene = o.pop("scene", "rdm")
     seed = int(o.pop("scene_seed", 0))
     common = dict(cls_map=cls_map, pad=pad, max_reset_attempts=o.pop("max_reset_attempts", 10))
+    if o.get("config_file") or str(scene).endswith(".json"):
+        return build_authored_scene(o.pop("config_file", None) or scene, scene_seed=seed, **common, **o)
     if scene == "rdm":
         return build_rdm_scene(seed, max_vehicles=max_vehicles, **common, **o)
     if scene in _SAMPLERS:
-        return build_scripted_scene(scene, seed, level=o.get("level"), **common)
+        return build_scripted_scene(scene, seed, level=o.pop("level", None), **common, **o)
     if scene == "red_light_runner":
         return build_red_light_scene(seed, **common, **o)
     raise KeyError(f"Unknown scenario '{scene}' (authored JSON scenes ship as a pool: pool.load_shipped_pool)")

@@ -158,27 +158,14 @@ class CarlaBEVVectorEnv:
                                    "options={'scene': 'lead_brake' | 'jaywalk', ...}")
             base = int(options.get("scene_seed", options.get("_vector_seed", self.env_cfg.seed)))
             return (base + np.arange(n)) % len(self._scenes)
-        if options.get("config_file") or str(scene).endswith(".json"):
-            # authored scenes (scenarios/__init__.py:210-338): snapshots of the reference's 7 scene files x variations
-            import os as _os
-
-            from .pool import authored_manifest
-
-            name = _os.path.basename(str(options.get("config_file") or scene))
-            vseed = int(options.get("variation_seed", 0))
-            cache = getattr(self, "_shipped_cache", {})
-            if "authored_scenes" not in cache:
-                sc = load_shipped_pool("authored_scenes")
-                cache["authored_scenes"] = (len(self._scenes), len(sc))
-                self._scenes.extend(sc)
-                self._shipped_cache = cache
-                self.engine.upload_pool(pack_pool(self._scenes))
-            base, _ = cache["authored_scenes"]
-            for i, m in enumerate(authored_manifest()):
-                if m["config_file"] == name and m["variation_seed"] == vseed:
-                    return np.full(n, base + i, dtype=np.int64)
-            raise KeyError(f"authored scene {name!r} with variation_seed={vseed} is not in the shipped pool")
-        if scene in ("rdm", "lead_brake", "jaywalk", "red_light_runner"):
+        authored = options.get("config_file") or (scene if str(scene).endswith(".json") else None)
+        if authored is not None and not isinstance(authored, dict) and not os.path.exists(str(authored)):
+            # the reference's own 7 scene files (assets/scenes/*.json) ship with the package, addressed by file name
+            bundled = S.bundled_authored_files()
+            if os.path.basename(str(authored)) not in bundled:
+                raise FileNotFoundError(f"authored scene file {authored!r} not found (bundled: {sorted(bundled)})")
+            options = {**options, "config_file": bundled[os.path.basename(str(authored))]}
+        if authored is not None or scene in ("rdm", "lead_brake", "jaywalk", "red_light_runner"):
             # The reference builds the scene inside reset (carlabev.py:96-148); here the host generator
             # (scenes.py, bit-identical to the reference's post-reset state) fills the device pool on demand.
             # SyncVectorEnv passes the same options to every env: with options["scene_seed"] every env gets the
@@ -195,7 +182,8 @@ class CarlaBEVVectorEnv:
             sel = np.ones(n, bool) if mask is None else np.asarray(mask, bool)
             new = [int(sd) for sd in np.unique(seeds[sel]) if int(sd) not in cache]
             if new:
-                shipped = shipped_pool_for(options)   # snapshots exported from the reference with these options
+                # snapshots exported from the reference with exactly these options (entry i <-> scene_seed i)
+                shipped = None if authored is not None else shipped_pool_for(options)
                 ready = {}
                 if shipped is not None:
                     pool = self._shipped_scenes(shipped)

@@ -67,9 +67,62 @@ def export_authored(variations=4):
     os.makedirs(OUT, exist_ok=True)
     save_pool(os.path.join(OUT, "authored_scenes.npz"), scenes)
     json.dump(manifest, open(os.path.join(OUT, "authored_scenes.json"), "w"), indent=1)
+    # the scene files themselves (DATA assets of the reference), bundled for the host loader and its tests
+    bundle = {os.path.basename(f): json.load(open(f)) for f in files}
+    json.dump(bundle, open(os.path.join(os.path.dirname(OUT), "authored_scene_files.json"), "w"), separators=(",", ":"))
     print(f"authored_scenes: {len(scenes)} scenes from {len(files)} files, actors "
           f"{min(len(s['act_kind']) for s in scenes)}..{max(len(s['act_kind']) for s in scenes)}, "
           f"traffic lights <= {max(len(s['tl_color']) for s in scenes)}")
+    envs.close()
+
+
+OPTION_CASES = [  # reset options beyond the bench configs: presets, parameter overrides, scenario-config files
+    dict(scene="jaywalk", level=3, ego_speed=10.0, cross_delay=1.2, pedestrian_speed=1.6, yield_duration=1.2,
+         scene_seed=3),                                                            # preset jaywalk_debug
+    dict(scene="lead_brake", level=2, ego_speed=12.0, lead_gap=8.0, lead_speed=11.0, brake_delay=2.0,
+         brake_strength=4.0, scene_seed=4),                                        # preset lead_brake_debug
+    dict(scene="red_light_runner", intersection_index=11, ego_speed=10.0, adv_speed=16.0, scene_seed=5),
+    dict(scene="rdm", num_vehicles=25, route_dist_range=[30, 130], scene_seed=6),  # preset rdm_navigation
+    dict(scene="rdm", num_vehicles=6, route_dist_range=[30, 90], ego_route_graph="right_lane", scene_seed=7),
+    dict(scene="rdm", num_vehicles=6, route_dist_range=[30, 90], ego_route_graph="left_lane", scene_seed=8),
+    dict(scene="rdm", num_vehicles=9, route_dist_range=[40, 70], route_seed=5, traffic_seed=9, scene_seed=9,
+         ego_target_speed=9.0),
+    dict(scene="rdm", difficulty_id="rt_easy_v1", traffic_enabled=True, num_vehicles=8, route_dist_range=[30, 80],
+         scene_seed=10),
+    dict(scene="lead_brake", scene_seed=11),                                       # level drawn from scenario_rng
+    dict(scene="jaywalk", scene_seed=12),
+    dict(scene="jaywalk", level=4, anchor_x=848, anchor_y=930, rear_gap=4.0, rear_speed=7.0, cross_offset=1.0,
+         scene_seed=13),
+    dict(scene="lead_brake", level=3, rear_brake_delay=2.2, left_speed=15.0, rear_gap=5.5, scene_seed=14),
+    dict(scene="red_light_runner", anchor_x=300, anchor_y=420, adv_speed=12.0, scene_seed=15),
+    dict(config={"type": "scenario_config", "scenario_id": "lead_brake", "level": 3,
+                 "anchor": {"x": 850, "y": 950}, "parameters": {"ego_speed": 9.0, "lead_gap": 6.0}}, scene_seed=16),
+    dict(config={"scenario": "jaywalk", "kwargs": {"level": 2, "anchor_y": 940, "cross_delay": 2.0}}, scene_seed=17),
+]
+
+
+def export_options():
+    """Snapshots for tests/test_host_logic.py::test_reset_option_variants_match_reference."""
+    import json
+    import tempfile
+
+    cfg = RunConfig(env=EnvConfig(render_mode="rgb_array"), num_envs=1)
+    envs = make_env(cfg)
+    base = envs.envs[0].unwrapped
+    scenes = []
+    for case in OPTION_CASES:
+        opts = dict(case)
+        if "config" in opts:
+            tmp = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+            json.dump(opts.pop("config"), tmp)
+            tmp.close()
+            opts["config_file"] = tmp.name
+        envs.reset(options={**opts, "reset_mask": np.array([True])})
+        scenes.append(extract_scene(base, opts))
+    out = os.path.join(ROOT, "tests", "golden", "option_scenes.npz")
+    save_pool(out, scenes)
+    json.dump(OPTION_CASES, open(os.path.join(ROOT, "tests", "golden", "option_scenes.json"), "w"), indent=1)
+    print(f"option_scenes: {len(scenes)} snapshots, {os.path.getsize(out) / 1e3:.0f} kB")
     envs.close()
 
 
@@ -89,6 +142,8 @@ if __name__ == "__main__":
                env_kwargs=dict(ego_anchor_x_frac=0.5, ego_anchor_y_frac=0.75))
     if which in ("", "authored"):
         export_authored()
+    if which in ("", "options"):
+        export_options()
     if which in ("", "red_light"):
         # BASELINE configs[3]: red_light_runner (first valid 4-way intersection); the adversary's start jitter is
         # unseeded in the reference (quirk C-10), so these are snapshots, not re-derivable from the seed

@@ -210,6 +210,16 @@ def test_vector_env_surface_and_infos():
     envs.step(np.zeros((6, 3), np.float32))
     with pytest.raises(NotImplementedError):
         envs.reset(options={"scene": "rdm", "route_profile": "left_turn"})
+    # authored scene file (bundled, addressed by name) and a typed preset request (config/reset.py mirror)
+    from carlabev_env_b200 import reset as R
+
+    obs, _ = envs.reset(options=R.build_reset_options(R.AuthoredSceneReset("redlightrunner-01.01.json", True, 2)))
+    assert len(envs._scenes[envs._scene_of_env[0]]["tl_color"]) >= 2
+    envs.step(np.zeros((6, 3), np.float32))
+    obs, _ = envs.reset(seed=5, options=R.build_reset_options(R.ScenarioPresetReset("lead_brake_debug")))
+    assert len(set(envs._scene_of_env.tolist())) == 6
+    with pytest.raises(FileNotFoundError):
+        envs.reset(options={"config_file": "no_such_scene.json"})
     envs.close()
 
 

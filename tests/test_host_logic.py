@@ -304,3 +304,90 @@ def test_build_pool_parallel_equals_serial():
     serial = S.build_pool(reqs, workers=1)
     parallel = S.build_pool(reqs, workers=2)
     assert all(_same_scene(a, b) == [] for a, b in zip(serial, parallel))
+
+
+def _jitter_only(ref, got):
+    """act_state0 may differ by the +-1 px start jitter the reference draws from an unseeded generator."""
+    d = np.abs(ref["act_state0"] - got["act_state0"])
+    return d[:, :2].max() <= 2.0 and d[:, 3].max() == 0.0
+
+
+def test_reset_option_variants_match_reference():
+    """Scenario presets, parameter overrides, lane-restricted ego graphs, explicit sub-seeds, drawn levels and
+    scenario-config files: snapshots of the unmodified reference (oracle/export_pools.py options)."""
+    import json
+
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.pool import load_pool
+
+    ref = load_pool(os.path.join(ROOT, "tests", "golden", "option_scenes.npz"))
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "option_scenes.json")))
+    cls = load_map()
+    assert len(ref) == len(cases) >= 15
+    for r, c in zip(ref, cases):
+        o = dict(c)
+        got = S.build_authored_scene(o.pop("config"), cls_map=cls, **o) if "config" in o else S.build_scene(o, cls_map=cls)
+        # `kind` / `level` of a snapshot are the exporter's copy of the options, not reference state
+        bad = _same_scene(r, got, skip=("kind", "level"))
+        if c.get("scene") == "red_light_runner" and bad == ["act_state0"]:
+            assert _jitter_only(r, got)
+            bad = []
+        assert bad == [], c
+    # the named presets resolve to the option sets snapshotted above (scenarios/specs.py:95-146)
+    assert S.scenario_preset_options("jaywalk_debug") == {k: v for k, v in cases[0].items() if k != "scene_seed"}
+    assert S.scenario_preset_options("lead_brake_debug", {"level": 3, "ego_speed": None})["level"] == 3
+    with pytest.raises(KeyError):
+        S.scenario_preset_options("nope")
+    with pytest.raises(ValueError):
+        S.scenario_config_options({"foo": 1})
+
+
+def test_authored_scene_loader_matches_reference_snapshots():
+    """The host loader on the reference's 7 authored scene files x 4 seeded variations == the reference's
+    post-reset snapshots (waypoint jitter, speed / behaviour-parameter / signal-state variation, traffic lights)."""
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.pool import authored_manifest, load_shipped_pool
+
+    files = S.bundled_authored_files()
+    assert len(files) == 7
+    cls = load_map()
+    for r, m in zip(load_shipped_pool("authored_scenes"), authored_manifest()):
+        got = S.build_scene({"config_file": files[m["config_file"]], "variation_enabled": True,
+                             "variation_seed": m["variation_seed"], "scene_seed": m["variation_seed"]}, cls_map=cls)
+        bad = _same_scene(r, got, skip=("level",))
+        if bad == ["act_state0"]:
+            assert _jitter_only(r, got)
+            bad = []
+        assert bad == [], m
+    base = S.build_authored_scene(files["leadbrake-01.02.json"], variation_enabled=False)
+    again = S.build_authored_scene(files["leadbrake-01.02.json"], variation_enabled=False, variation_seed=99)
+    assert _same_scene(base, again) == []      # variation off: the seed is ignored
+    varied = S.build_authored_scene(files["leadbrake-01.02.json"], variation_enabled=True, variation_seed=99)
+    assert _same_scene(base, varied) != []
+
+
+def test_typed_reset_requests():
+    """config/reset.py mirror: typed requests -> the option dicts reset() consumes."""
+    from carlabev_env_b200 import reset as R
+    from carlabev_env_b200 import scenes as S
+
+    o = R.build_reset_options(R.RandomNavigationReset(difficulty_id="rt_hard_v1", scene_seed=5), reset_mask=[1, 0])
+    assert o["scene"] == "rdm" and o["num_vehicles"] == 25 and o["route_dist_range"] == [50, 130]
+    assert o["traffic_enabled"] is True and o["scene_seed"] == 5 and o["reset_mask"].tolist() == [True, False]
+    assert "route_profile" not in o and o["ego_route_graph"] == "full_vehicle"
+    p = R.build_reset_options(R.ScenarioPresetReset("lead_brake_debug", {"level": 3}))
+    assert p["scene"] == "lead_brake" and p["level"] == 3 and p["lead_gap"] == 8.0
+    a = R.build_reset_options(R.AuthoredSceneReset("jaywalk-01.01.json", True, 3))
+    assert a == {"config_file": "jaywalk-01.01.json", "variation_enabled": True, "variation_seed": 3}
+    c = R.build_reset_options(R.ScenarioConfigReset("jaywalk", level=2, anchor_y=940, parameters={"ego_speed": 9.0}))
+    assert c == {"ego_speed": 9.0, "scene": "jaywalk", "level": 2, "anchor_y": 940}
+    with pytest.raises(TypeError):
+        R.build_reset_options(object())
+    with pytest.raises(KeyError):
+        R.build_reset_options(R.RandomNavigationReset(difficulty_id="nope"))
+    # the dicts feed the host generator unchanged
+    s1 = S.build_scene({k: v for k, v in o.items() if k != "reset_mask"}, cls_map=load_map())
+    s2 = S.build_scene({"scene": "rdm", "difficulty_id": "rt_hard_v1", "scene_seed": 5}, cls_map=load_map())
+    assert _same_scene(s1, s2) == []
+    s3 = S.build_scene({**c, "scene_seed": 2})
+    assert float(s3["ego_state0"][3]) == pytest.approx(9.0 / (40.0 / 128.0))
