@@ -49,7 +49,7 @@ class CarlaBEVVectorEnv:
 
     def __init__(self, cfg: RunConfig, *, scenes=None, autoreset: str = "disabled", device=None, ring_slots=None,
                  ring_budget_bytes=None, to_numpy: bool = False, raw_rgb: bool = False, seed=None,
-                 host_infos: bool = True):
+                 host_infos: bool = True, eval: bool = False):  # noqa: A002
         import torch
 
         self.torch = torch
@@ -115,6 +115,13 @@ class CarlaBEVVectorEnv:
         self._scene_of_env = np.zeros(self.num_envs, dtype=np.int64)
         self.current_hero = None
         self._generated, self._shipped_lists = {}, {}
+        self.recorder, self._rec_pending_reset = None, False
+        if getattr(cfg, "capture_video", False):     # env 0 only, like make_carlabev_env (envs/__init__.py:93-100)
+            from .recorder import FrameRecorder
+
+            self.recorder = FrameRecorder(cfg, eval=eval)
+            self.engine.keep_fov(True)
+            self.host_infos = True                   # the recorder needs env 0's done flag on the host
 
     @staticmethod
     def _crop_size(env) -> int:
@@ -152,13 +159,13 @@ class CarlaBEVVectorEnv:
                 raise ValueError("scene_ids outside the scene pool")
             return ids
         scene = options.get("scene")
-        if scene is None or scene == "pool":
+        authored = options.get("config_file") or (scene if str(scene).endswith(".json") else None)
+        if authored is None and (scene is None or scene == "pool"):
             if not self._scenes:
                 raise RuntimeError("no scene pool: pass scenes=... / call set_scene_pool(), or reset with "
                                    "options={'scene': 'lead_brake' | 'jaywalk', ...}")
             base = int(options.get("scene_seed", options.get("_vector_seed", self.env_cfg.seed)))
             return (base + np.arange(n)) % len(self._scenes)
-        authored = options.get("config_file") or (scene if str(scene).endswith(".json") else None)
         if authored is not None and not isinstance(authored, dict) and not os.path.exists(str(authored)):
             # the reference's own 7 scene files (assets/scenes/*.json) ship with the package, addressed by file name
             bundled = S.bundled_authored_files()
@@ -229,6 +236,8 @@ class CarlaBEVVectorEnv:
         else:
             self._needs_reset[m] = False
             self._scene_of_env[m] = ids[m]
+        if self.recorder is not None and (m is None or m[0]):
+            self.recorder.on_reset(self.engine.fov()[0].cpu().numpy())
         infos = {}
         return self._out_obs(obs), infos
 
@@ -256,6 +265,8 @@ class CarlaBEVVectorEnv:
         self._done_host.copy_(eng.terminated | eng.truncated, non_blocking=True)
         t.cuda.current_stream(self.device).synchronize()
         done_host = self._done_host.numpy().astype(bool)
+        if self.recorder is not None:
+            self._record_step(bool(done_host[0]))
         if done_host.any():
             infos.update(self._terminal_infos(done_host))
             if self.autoreset == "disabled":
@@ -289,6 +300,15 @@ class CarlaBEVVectorEnv:
         return {"episode_info": episode_info, "_episode_info": mask,
                 "episode": {"r": r, "_r": mask, "l": ln, "_l": mask}, "_episode": mask}
 
+    def _record_step(self, done0):
+        rec = self.recorder
+        if self.autoreset == "next_step" and self._rec_pending_reset:
+            # this step consumed env 0's device auto-reset: its frame is the reset frame of a new episode
+            rec.on_reset(self.engine.fov()[0].cpu().numpy())
+        elif rec.frames is not None:
+            rec.on_step(self.engine.fov()[0].cpu().numpy(), done0)
+        self._rec_pending_reset = done0 and self.autoreset == "next_step"
+
     def _out_obs(self, obs):
         return obs.cpu().numpy() if self.to_numpy else obs
 
@@ -304,6 +324,8 @@ class CarlaBEVVectorEnv:
         return self.engine.read_stats(reset)
 
     def close(self):
+        if self.recorder is not None:
+            self.recorder.flush()
         self.engine.close()
 
 
@@ -315,4 +337,4 @@ def make_env(cfg=None, eval: bool = False, **engine_kwargs) -> CarlaBEVVectorEnv
         cfg = validate_run_config({"env": cfg})
     else:
         cfg = validate_run_config(cfg)
-    return CarlaBEVVectorEnv(cfg, **engine_kwargs)
+    return CarlaBEVVectorEnv(cfg, eval=eval, **engine_kwargs)

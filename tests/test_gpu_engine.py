@@ -1,6 +1,8 @@
 """GPU tests of the engine beyond golden replay: batched parity with the oracle on fresh scenes, the
 observation ring (wrap + mirror), masked reset, device auto-reset, the VectorEnv surface, error paths and
 size-independent properties at the benchmark size (4096 envs)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -599,3 +601,42 @@ def test_raster_parity_over_all_headings(anchor):
             n_generic += not inside
     print(f"anchor {anchor}: {n} headings, {n_generic} on the generic (range-tested) path")
     eng.close()
+
+
+def test_frame_recorder_env0(tmp_path):
+    """capture_video: env 0's RGB field of view after reset and after every step of the selected episodes
+    (RecordVideo's role in wrap_env, envs/__init__.py:40-60), checked against the oracle's frames."""
+    from carlabev_env_b200 import RunConfig, EnvConfig, make_env
+    from oracle import raster
+    from oracle.env import OracleEnv
+
+    scenes = _scenes([("lead_brake", 1), ("jaywalk", 2)])
+    cfg = RunConfig(env=EnvConfig(obs_mode="bev_semantic", action_mode="continuous"), num_envs=2, capture_video=True,
+                    video_output_dir=str(tmp_path), video_episode_indices=[0, 1], video_name_prefix="t")
+    envs = make_env(cfg, scenes=scenes)
+    ora = OracleEnv(load_map(), action_mode="continuous")
+    ora.reset(scenes[0])
+    want = [[ora.last_rgb]]
+    envs.reset(options={"scene_ids": np.array([0, 0])})       # twin envs: both finish on the same step
+    act = np.array([[1.0, 0.0, 0.0], [1.0, 0.0, 0.0]], np.float32)
+    for ep in range(2):
+        for _ in range(400):
+            _, _, term, trunc, _ = envs.step(act)
+            _, _, o_term, o_trunc, _ = ora.step(act[0])
+            want[-1].append(ora.last_rgb)
+            if bool(term[0] | trunc[0]):
+                assert o_term or o_trunc
+                break
+        else:
+            raise AssertionError("episode did not end")
+        if ep == 0:
+            envs.reset(options={"scene_ids": np.array([0, 0]), "reset_mask": (term | trunc).cpu().numpy()})
+            ora.reset(scenes[0])
+            want.append([ora.last_rgb])
+    envs.close()
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["t-episode-0.npy", "t-episode-1.npy"]
+    for f, w in zip(files, want):
+        got = np.load(os.path.join(tmp_path, f))
+        assert got.shape == (len(w), 128, 128, 3) and got.dtype == np.uint8
+        assert np.array_equal(got, np.stack(w))
