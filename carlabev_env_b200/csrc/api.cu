@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -136,15 +138,70 @@ extern "C" {
 int cbev_version(void) { return CBEV_VERSION; }
 const char* cbev_last_error(void) { return g_err; }
 
+// OpenCV computeResizeAreaTab for one axis (modules/imgproc/src/resize.cpp, 4.x): for every destination index the
+// source taps it covers and their float32 weights, in OpenCV's order.  Checked against cv2 itself in
+// tests/test_oracle_contracts.py through the oracle's identical table (oracle/raster.py:_area_table).
+static void area_table(int ssize, int dsize, std::vector<int32_t>& off, std::vector<int32_t>& si,
+                       std::vector<float>& alpha) {
+  const double scale = (double)ssize / dsize;
+  off.assign(1, 0);
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cell = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) { si.push_back(sx1 - 1); alpha.push_back((float)((sx1 - fsx1) / cell)); }
+    for (int sx = sx1; sx < sx2; ++sx) { si.push_back(sx); alpha.push_back((float)(1.0 / cell)); }
+    if (fsx2 - sx2 > 1e-3) {
+      si.push_back(sx2);
+      alpha.push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell));
+    }
+    off.push_back((int32_t)si.size());
+  }
+}
+
+// rs_tab = [nx, ny, xoff[ow+1], yoff[oh+1], xsi[nx], ysi[ny], xalpha[nx], yalpha[ny]]
+static int build_resize_tables(cbev_engine* e) {
+  const int S = e->cfg.fov_size, oh = e->cfg.obs_h, ow = e->cfg.obs_w;
+  e->rs_words = 0;
+  if (e->cfg.obs_mode == CBEV_OBS_RGB || (oh == 96 && ow == 96)) { e->rs_mode = CBEV_RS_FAST96; return CBEV_OK; }
+  if (oh == S && ow == S) e->rs_mode = CBEV_RS_COPY;
+  else if (2 * oh == S && 2 * ow == S) e->rs_mode = CBEV_RS_HALF;
+  else e->rs_mode = CBEV_RS_TABLE;
+  std::vector<int32_t> xo, yo, xs, ys;
+  std::vector<float> xa, ya;
+  area_table(S, ow, xo, xs, xa);
+  area_table(S, oh, yo, ys, ya);
+  std::vector<int32_t> tab;
+  tab.push_back((int32_t)xs.size());
+  tab.push_back((int32_t)ys.size());
+  tab.insert(tab.end(), xo.begin(), xo.end());
+  tab.insert(tab.end(), yo.begin(), yo.end());
+  tab.insert(tab.end(), xs.begin(), xs.end());
+  tab.insert(tab.end(), ys.begin(), ys.end());
+  for (float a : xa) { int32_t b; memcpy(&b, &a, 4); tab.push_back(b); }
+  for (float a : ya) { int32_t b; memcpy(&b, &a, 4); tab.push_back(b); }
+  e->rs_words = (int32_t)tab.size();
+  return dev_upload(&e->rs_tab, tab.data(), tab.size());
+}
+
 int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   if (!cfg || !out) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
   *out = nullptr;
   if (cfg->num_envs < 1) { cbev_set_error("num_envs must be >= 1"); return CBEV_ERR_ARG; }
   if (cfg->fov_size != 128) { cbev_set_error("only size=128 (Town01-128 map scale) is implemented, got %d", cfg->fov_size); return CBEV_ERR_ARG; }
   if (cfg->obs_mode < 0 || cfg->obs_mode > 2) { cbev_set_error("bad obs_mode %d", cfg->obs_mode); return CBEV_ERR_ARG; }
-  if (cfg->obs_mode != CBEV_OBS_RGB && (cfg->obs_h != 96 || cfg->obs_w != 96)) {
-    cbev_set_error("only obs_size=(96, 96) is implemented (cv2 INTER_AREA 128->96), got (%d, %d)", cfg->obs_h, cfg->obs_w);
-    return CBEV_ERR_ARG;
+  if (cfg->obs_mode != CBEV_OBS_RGB) {
+    // ResizeObservation = cv2.resize(INTER_AREA) of the 128 x 128 frame; enlarging takes OpenCV's bilinear branch
+    // (not built), and the observation planes are streamed with 16-byte stores
+    const int px = cfg->obs_h * cfg->obs_w;
+    if (cfg->obs_h < 8 || cfg->obs_w < 8 || cfg->obs_h > 128 || cfg->obs_w > 128 ||
+        px % (cfg->obs_mode == CBEV_OBS_SEMANTIC ? 4 : 16) != 0) {
+      cbev_set_error("obs_size must be within 8..128 per side with height*width a multiple of %d, got (%d, %d)",
+                     cfg->obs_mode == CBEV_OBS_SEMANTIC ? 4 : 16, cfg->obs_h, cfg->obs_w);
+      return CBEV_ERR_ARG;
+    }
   }
   if (cfg->obs_mode == CBEV_OBS_SEMANTIC && channels_of(cfg->mask_mode) < 0) { cbev_set_error("bad mask_mode %d", cfg->mask_mode); return CBEV_ERR_ARG; }
   if (cfg->frame_stack < 1) { cbev_set_error("frame_stack must be >= 1"); return CBEV_ERR_ARG; }
@@ -206,6 +263,7 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   rc |= dev_alloc(&e->desc, N * CBEV_DESC_WORDS);
   rc |= dev_alloc(&e->fov, N * (size_t)cfg->fov_size * cfg->fov_size);
   rc |= dev_alloc(&e->gstats, (size_t)CBEV_STATS_FIELDS);
+  rc |= build_resize_tables(e);
   rc |= dev_alloc((uint8_t**)&e->h_reward_dev, N * 10);  // one block: reward f64[N] | terminated u8[N] | truncated u8[N]
   e->h_term_dev = (uint8_t*)e->h_reward_dev + N * 8;
   e->h_trunc_dev = e->h_term_dev + N;
@@ -220,7 +278,7 @@ int cbev_destroy(cbev_handle e) {
   if (!e) return CBEV_OK;
   free_pool(e->pool);
   free_state(e->st);
-  dev_free(e->fov_mask);
+  dev_free(e->fov_mask); dev_free(e->rs_tab);
   dev_free(e->map); dev_free(e->desc); dev_free(e->rects); dev_free(e->fov); dev_free(e->gstats);
   dev_free(e->h_reward_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }

@@ -80,6 +80,12 @@ struct SimParams {
   cbev_config cfg;  // reward parameters
 };
 
+// ResizeObservation variants (cv2.resize INTER_AREA from the 128 x 128 field of view)
+#define CBEV_RS_FAST96 0  /* (96, 96): 4x4-block two-pass kernel, weights in 1/16            */
+#define CBEV_RS_TABLE 1   /* any size <= 128: OpenCV's float32 area tables                    */
+#define CBEV_RS_HALF 2    /* (64, 64): OpenCV's 2x2 fast path, (a + b + c + d + 2) >> 2        */
+#define CBEV_RS_COPY 3    /* (128, 128): cv2.resize returns a copy                            */
+
 struct cbev_engine {
   cbev_config cfg;
   int device = 0;
@@ -95,6 +101,8 @@ struct cbev_engine {
   int32_t* desc = nullptr;         // [N][CBEV_DESC_WORDS]
   uint32_t* rects = nullptr;       // [N][max_rects]
   uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)
+  int32_t rs_mode = 0, rs_words = 0;  // CBEV_RS_*: how ResizeObservation is computed for this obs_size
+  int32_t* rs_tab = nullptr;          // device: OpenCV area tables of both axes (generic obs sizes)
   uint8_t* fov_mask = nullptr;     // [S][S] 0x00 / 0xff corner mask (fov_masked) or null
   void* ring = nullptr;
   int64_t ring_bytes = 0, frame_bytes = 0;

@@ -80,6 +80,8 @@ struct RenderParams {
   uint8_t* fov_out;  // [N][S][S] palette-index frames (nullable)
   const uint8_t* fov_mask;  // [S][S] 0x00 / 0xff or null (fov_masked)
   void* ring;
+  int32_t obs_h, obs_w, rs_mode, rs_words;  // rs_mode: CBEV_RS_* (engine.h); rs_words = size of rs_tab
+  const int32_t* rs_tab;                    // cv2 area tables of both axes (api.cu: build_resize_tables)
 };
 
 // cv2 INTER_AREA 128 -> 96: dst pixel d covers src taps s0 = floor(4d/3), s0+1 with weights
@@ -123,7 +125,24 @@ __device__ __forceinline__ uint32_t resolve_px(uint32_t c00, uint32_t c01, uint3
   return (uint32_t)(int)g & 255u;
 }
 
-template <int OBS_MODE, int CHANNELS>
+// exact colour equality of a resized pixel -> channel bitmask (semantic) or gray level (GrayscaleObservation)
+template <int OBS_MODE>
+__device__ __forceinline__ uint32_t classify_key(uint32_t key, const uint32_t* s_key, const uint8_t* s_cm) {
+  if (OBS_MODE == CBEV_OBS_SEMANTIC) {
+    uint32_t cls = CBEV_PAL_COUNT;
+#pragma unroll
+    for (int q = 0; q < CBEV_PAL_TL_YELLOW; ++q) cls = (key == s_key[q]) ? q : cls;
+    return s_cm[cls];
+  }
+  const double g = __dadd_rn(__dadd_rn(__dmul_rn((double)(key & 255u), 0.2125),
+                                       __dmul_rn((double)((key >> 8) & 255u), 0.7154)),
+                             __dmul_rn((double)(key >> 16), 0.0721));
+  return (uint32_t)(int)g & 255u;
+}
+
+// GEN = false: the 128 -> 96 x 96 specialisation (4x4-block two-pass resize).  GEN = true: any obs_size <= 128 through
+// OpenCV's area tables (float32 accumulate in OpenCV's order), the 2x2 integer average for 64 x 64, or a copy for 128.
+template <int OBS_MODE, int CHANNELS, bool GEN>
 __global__ void __launch_bounds__(RT, 4)
 k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -316,12 +335,64 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     return;
   }
 
+  const int OH = GEN ? P.obs_h : 96, OW = GEN ? P.obs_w : 96;
+  uint8_t* s_out = s_region;                        // OH x OW bytes: channel bitmask (semantic) or gray level
+  if (GEN) {
+    // ---- 4g. cv2.resize(INTER_AREA) for any obs_size <= 128 (ResizeObservation, envs/__init__.py:62) ----
+    int32_t* s_tab = (int32_t*)(s_count + 4);
+    for (int u = tid; u < P.rs_words; u += RT) s_tab[u] = P.rs_tab[u];
+    __syncthreads();
+    const int nx = s_tab[0], ny = s_tab[1];
+    const int32_t* xoff = s_tab + 2;
+    const int32_t* yoff = xoff + OW + 1;
+    const int32_t* xsi = yoff + OH + 1;
+    const int32_t* ysi = xsi + nx;
+    const float* xal = (const float*)(ysi + ny);
+    const float* yal = xal + nx;
+    for (int o = tid; o < OH * OW; o += RT) {
+      const int dy = o / OW, dx = o - dy * OW;
+      uint32_t key;
+      if (P.rs_mode == CBEV_RS_COPY) {
+        key = s_key[s_fov[dy * S + dx]];
+      } else if (P.rs_mode == CBEV_RS_HALF) {
+        // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
+        const uint8_t* q = s_fov + 2 * dy * S + 2 * dx;
+        const uint32_t c0 = q[0], c1 = q[1], c2 = q[S], c3 = q[S + 1];
+        const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
+        const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
+        key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
+      } else {
+        // ResizeArea_Invoker: buf = sum_x S * alpha (from 0, in table order); sum = sum_y beta * buf; float32, no FMA
+        float sr = 0.f, sg = 0.f, sb = 0.f;
+        const int y0 = yoff[dy], y1 = yoff[dy + 1], x0 = xoff[dx], x1 = xoff[dx + 1];
+        for (int j = y0; j < y1; ++j) {
+          const uint8_t* row = s_fov + ysi[j] * S;
+          float br = 0.f, bg = 0.f, bb = 0.f;
+          for (int k = x0; k < x1; ++k) {
+            const uint32_t kk = s_key[row[xsi[k]]];
+            const float a = xal[k];
+            br = __fadd_rn(br, __fmul_rn((float)(kk & 255u), a));
+            bg = __fadd_rn(bg, __fmul_rn((float)((kk >> 8) & 255u), a));
+            bb = __fadd_rn(bb, __fmul_rn((float)(kk >> 16), a));
+          }
+          const float beta = yal[j];
+          sr = __fadd_rn(sr, __fmul_rn(beta, br));
+          sg = __fadd_rn(sg, __fmul_rn(beta, bg));
+          sb = __fadd_rn(sb, __fmul_rn(beta, bb));
+        }
+        const int R = min(max(__float2int_rn(sr), 0), 255), G = min(max(__float2int_rn(sg), 0), 255),
+                  B = min(max(__float2int_rn(sb), 0), 255);
+        key = (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
+      }
+      s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
+    }
+    __syncthreads();
+  } else {
   // ---- 4. area resize 128 -> 96 + colour equality -> one byte per output pixel ----
   // Every 4x4 source block maps to a 3x3 output block (period of the 4/3 scale on both axes).
   // Pass A: a block whose 16 texels are equal resolves to one table lookup for all 9 outputs; the other
   // blocks go to a worklist.  Pass B: the worklist is processed one output pixel per thread (no divergence).
   constexpr int O = 96;
-  uint8_t* s_out = s_region;                        // 96x96 bytes: channel bitmask (semantic) or gray level
   uint16_t* s_list = (uint16_t*)(s_region + O * O);  // up to 32*32 mixed blocks
   {
     const int br = tid >> 3, j = tid & 7;  // 32 block rows x 8 strips of 4 blocks (RT == 256)
@@ -374,6 +445,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     }
   }
   __syncthreads();
+  }
 
   // ---- 5. expand + stream out ----
   for (int slot = first; slot <= P.head; ++slot) {
@@ -387,18 +459,19 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       uint8_t* base = (uint8_t*)P.ring + ((size_t)env * P.ring_slots + sl) * P.frame_bytes;
       if (OBS_MODE == CBEV_OBS_SEMANTIC) {
         float* fb = (float*)base;
-        for (int q = tid; q < O * O / 4; q += RT) {
+        const int plane = OH * OW;
+        for (int q = tid; q < plane / 4; q += RT) {
           const uint32_t m4 = ((const uint32_t*)s_out)[q];
 #pragma unroll
           for (int c = 0; c < CHANNELS; ++c) {
             // bit c of each of the 4 pixels -> 4-bit index (multiply gathers the bits into the top byte)
             const uint32_t t = (m4 >> c) & 0x01010101u;
             const float4 v = s_lut[(t * 0x01020408u) >> 24];
-            st_f4(fb + c * (O * O) + 4 * q, v.x, v.y, v.z, v.w);
+            st_f4(fb + c * plane + 4 * q, v.x, v.y, v.z, v.w);
           }
         }
       } else {
-        for (int q = tid; q < O * O / 16; q += RT) st_u4(base + 16 * q, ((const uint4*)s_out)[q]);
+        for (int q = tid; q < OH * OW / 16; q += RT) st_u4(base + 16 * q, ((const uint4*)s_out)[q]);
       }
     }
   }
@@ -407,8 +480,8 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
 // ---- temporal fusion of the stacked masks (wrappers/rgb_to_semantic.py:152-193) ---------------------
 // One thread per float4 of one output plane; planes are gathered from the ring window.
 __global__ void __launch_bounds__(256)
-k_fuse(const float* __restrict__ ring, float* __restrict__ out, int N, int L, int C, int head, int veh, int mode) {
-  constexpr int HW4 = 96 * 96 / 4;
+k_fuse(const float* __restrict__ ring, float* __restrict__ out, int N, int L, int C, int head, int veh, int mode,
+       int HW4) {
   const int Cout = mode == CBEV_FUSE_VEHICLE_TEMPORAL ? C - 1 + 3 : C;
   const long long total = (long long)N * Cout * HW4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -468,9 +541,9 @@ void upload_tables() {
   cudaMemcpyToSymbol(c_chan_mask, cm, sizeof(cm));
 }
 
-template <int MODE, int CH>
-int launch(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
-  auto kern = k_render<MODE, CH>;
+template <int MODE, int CH, bool GEN>
+int launch2(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
+  auto kern = k_render<MODE, CH, GEN>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return 1;
@@ -478,6 +551,12 @@ int launch(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
   }
   kern<<<P.N, RT, smem, s>>>(P, *reinterpret_cast<const CUtensorMap*>(e->tmap), e->cfg.mask_mode);
   return 0;
+}
+
+template <int MODE, int CH>
+int launch(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
+  if (MODE != CBEV_OBS_RGB && P.rs_mode != CBEV_RS_FAST96) return launch2<MODE, CH, true>(e, P, smem, s);
+  return launch2<MODE, CH, false>(e, P, smem, s);
 }
 
 }  // namespace
@@ -510,10 +589,17 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   size_t tile = (size_t)P.crop * P.box_w;
   if (e->cfg.obs_mode == CBEV_OBS_RGB && tile < (size_t)S * S * 3) tile = (size_t)S * S * 3;  // RGB staging
   if (tile < 96 * 96 + 2 * 1024 + 64) tile = 96 * 96 + 2 * 1024 + 64;  // output bytes + mixed-block worklist
+  if (tile < (size_t)e->cfg.obs_h * e->cfg.obs_w) tile = (size_t)e->cfg.obs_h * e->cfg.obs_w;
   tile = ((tile + 127) / 128) * 128;
   P.tile_bytes = (int32_t)tile;
   P.pad0 = e->debug_flags;  // bit0: force the generic (range-tested) rotate path
-  size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16;
+  P.obs_h = e->cfg.obs_h;
+  P.obs_w = e->cfg.obs_w;
+  P.rs_mode = e->rs_mode;
+  P.rs_words = e->rs_words;
+  P.rs_tab = e->rs_tab;
+  size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16 +
+                (e->rs_mode == CBEV_RS_FAST96 ? 0 : 16 + (size_t)e->rs_words * 4);
   int rc = 1;
   if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, s);
   else if (e->cfg.obs_mode == CBEV_OBS_GRAY) rc = launch<CBEV_OBS_GRAY, 1>(e, P, smem, s);
@@ -539,10 +625,11 @@ int cbev_launch_fuse(cbev_engine* e, int32_t mode, float* out, cudaStream_t s) {
   if (veh < 0) return 1;
   const int C = e->channels;
   const int Cout = mode == CBEV_FUSE_VEHICLE_TEMPORAL ? C - 1 + 3 : C;
-  long long total = (long long)e->N * Cout * (96 * 96 / 4);
+  const int HW4 = e->cfg.obs_h * e->cfg.obs_w / 4;
+  long long total = (long long)e->N * Cout * HW4;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  k_fuse<<<blocks, 256, 0, s>>>((const float*)e->ring, out, e->N, e->cfg.ring_slots, C, e->head, veh, mode);
+  k_fuse<<<blocks, 256, 0, s>>>((const float*)e->ring, out, e->N, e->cfg.ring_slots, C, e->head, veh, mode, HW4);
   e->launches += 1;
   return 0;
 }

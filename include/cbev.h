@@ -123,7 +123,7 @@ typedef struct {
   int32_t fov_size;          /* EnvConfig.size, 128                                  */
   double anchor_x_frac;      /* EnvConfig.ego_anchor_x_frac (fov.py:30-36)           */
   double anchor_y_frac;
-  int32_t obs_h, obs_w;      /* EnvConfig.obs_size (96, 96)                          */
+  int32_t obs_h, obs_w;      /* EnvConfig.obs_size: (96, 96) default; any 8..128 per side (cv2 INTER_AREA), h*w % 4 == 0 (masks) / % 16 == 0 (gray) */
   int32_t obs_mode;          /* CBEV_OBS_*                                           */
   int32_t mask_mode;         /* CBEV_MASK_*                                          */
   int32_t frame_stack;       /* EnvConfig.frame_stack                                */

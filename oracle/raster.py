@@ -252,10 +252,17 @@ def _area_table(ssize, dsize):
 
 
 def resize_area(img, out_hw):
-    """gymnasium ResizeObservation -> cv2.resize(..., INTER_AREA) for non-integer scale
-    (envs/__init__.py:62).  float32 accumulate, round-half-even."""
+    """gymnasium ResizeObservation -> cv2.resize(..., INTER_AREA) when shrinking (envs/__init__.py:62):
+    equal size -> copy; exactly half on both axes -> OpenCV's 2x2 integer path (a + b + c + d + 2) >> 2;
+    everything else (integer or fractional scale) -> area tables, float32 accumulate, round-half-even.
+    Pinned on cv2 itself for 20 sizes in tests/test_oracle_contracts.py."""
     sh, sw = img.shape[:2]
     dh, dw = out_hw
+    if (dh, dw) == (sh, sw):
+        return img.copy()
+    if (2 * dh, 2 * dw) == (sh, sw):
+        s = img.astype(np.int32)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
     xt, yt = _area_table(sw, dw), _area_table(sh, dh)
     src = img.astype(np.float32)
     tmp = np.zeros((sh, dw) + img.shape[2:], dtype=np.float32)

@@ -640,3 +640,59 @@ def test_frame_recorder_env0(tmp_path):
         got = np.load(os.path.join(tmp_path, f))
         assert got.shape == (len(w), 128, 128, 3) and got.dtype == np.uint8
         assert np.array_equal(got, np.stack(w))
+
+
+@pytest.mark.parametrize("obs_size,mode", [((84, 84), "semantic"), ((64, 64), "semantic"), ((128, 128), "semantic"),
+                                           ((112, 100), "semantic"), ((84, 84), "gray"), ((64, 64), "gray"),
+                                           ((48, 64), "gray"), ((32, 32), "semantic")])
+def test_other_observation_sizes(obs_size, mode):
+    """EnvConfig.obs_size other than (96, 96): ResizeObservation through OpenCV's area tables (float32, OpenCV's
+    accumulation order), its 2x2 integer path for (64, 64) and the plain copy for (128, 128) -- bit-exact masks /
+    gray levels against the oracle (itself pinned on cv2 for these sizes)."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import load_shipped_pool
+    from oracle.env import OracleEnv
+
+    scenes = _scenes([("lead_brake", 3), ("jaywalk", 4), ("jaywalk", 3)], seed0=1300) + load_shipped_pool("rdm_rt_medium_v1")[:3]
+    n = len(scenes)
+    gray = mode == "gray"
+    eng = _engine(n, scenes, obs_size=obs_size, max_actors=20, obs_mode=E.OBS_GRAY if gray else E.OBS_SEMANTIC,
+                  mask_mode="7-class")
+    oracles = [OracleEnv(load_map(), action_mode="continuous", obs_size=obs_size, semantic_mask_ch="7-class",
+                         obs_mode="bev_rgb" if gray else "bev_semantic") for _ in range(n)]
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    C = 4 if gray else 4 * 7
+    assert obs.shape == (n, C, *obs_size)
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i])), (i, "reset")
+    rng = np.random.default_rng(5)
+    alive = np.ones(n, bool)
+    for t in range(30):
+        a = _rand_actions(rng, n)
+        eng.step(torch.from_numpy(a).cuda())
+        obs = eng.obs().cpu().numpy()
+        for i in range(n):
+            if alive[i]:
+                o, _, te, tr, _ = oracles[i].step(a[i])
+                assert np.array_equal(obs[i], o), (t, i)
+                alive[i] = not (te or tr)
+    if not gray:  # the fusion kernel follows the observation size too
+        from oracle import raster
+
+        obs = eng.obs().cpu().numpy().reshape(n, 4, 7, *obs_size)
+        for name, fn in (("vehicle_temporal", raster.fuse_vehicle_temporal), ("vehicle_weighted", raster.fuse_vehicle_weighted)):
+            got = eng.fuse(name).cpu().numpy()
+            for i in range(n):
+                assert np.array_equal(got[i], fn(obs[i], "7-class")), (name, i)
+    eng.close()
+
+
+def test_observation_size_errors():
+    from carlabev_env_b200 import engine as E
+
+    scenes = _scenes([("lead_brake", 1)])
+    for bad in [(96, 130), (4, 4), (50, 51)]:
+        with pytest.raises(E.CbevError):
+            _engine(1, scenes, obs_size=bad)

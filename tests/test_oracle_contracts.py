@@ -28,6 +28,26 @@ def test_area_resize_matches_cv2():
         assert np.array_equal(raster.resize_area(img, (96, 96)), cv2.resize(img, (96, 96), interpolation=cv2.INTER_AREA))
 
 
+@pytest.mark.parametrize("size", [(128, 128), (64, 64), (32, 32), (16, 16), (84, 84), (100, 100), (112, 112), (72, 72),
+                                  (48, 48), (80, 80), (84, 96), (64, 96), (96, 64), (64, 128), (128, 64), (120, 120),
+                                  (127, 127), (90, 60), (42, 42), (8, 8)])
+def test_area_resize_any_obs_size_matches_cv2(size):
+    """EnvConfig.obs_size is free in the reference: copy / 2x2 integer path / area tables, each against cv2."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(size[0] * 131 + size[1])
+    for k in range(4):
+        if k % 2 == 0:
+            img = raster.PALETTE[rng.integers(0, 10, (128, 128))]
+        else:
+            idx = np.ones((128, 128), dtype=np.int64)
+            for _ in range(40):
+                x, y, w, h = rng.integers(0, 120), rng.integers(0, 120), rng.integers(1, 40), rng.integers(1, 40)
+                idx[y:y + h, x:x + w] = rng.integers(0, 10)
+            img = raster.PALETTE[idx]
+        want = cv2.resize(img, (size[1], size[0]), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(raster.resize_area(img, size), want)
+
+
 def test_mask_coincidence_is_kept():
     # 1/2 white + 1/4 gray150 + 1/4 sidewalk220 = 220 = SIDEWALK (SURVEY.md A.7): the blend path must report it
     img = np.zeros((128, 128, 3), np.uint8)
