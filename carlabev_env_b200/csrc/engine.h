@@ -101,6 +101,7 @@ struct cbev_engine {
   int32_t* desc = nullptr;         // [N][CBEV_DESC_WORDS]
   uint32_t* rects = nullptr;       // [N][max_rects]
   uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)
+  unsigned long long* trace = nullptr;  // [N][8] phase timestamps (debug flag 4)
   int32_t rs_mode = 0, rs_words = 0;  // CBEV_RS_*: how ResizeObservation is computed for this obs_size
   int32_t* rs_tab = nullptr;          // device: OpenCV area tables of both axes (generic obs sizes)
   uint8_t* fov_mask = nullptr;     // [S][S] 0x00 / 0xff corner mask (fov_masked) or null

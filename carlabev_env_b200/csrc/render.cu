@@ -69,6 +69,19 @@ __device__ __forceinline__ void st_u4(void* p, uint4 v) {
                : "memory");
 }
 
+// bulk (TMA) stores shared -> global: the copy engine drains the staged planes while the warps go on, so the
+// observation stream does not sit in the LSU queues that the on-chip phases of the co-resident CTAs also use
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct RenderParams {
   int32_t N, env_lo, fov, crop, box_w, anchor_x, anchor_y;
   int32_t frame_stack, ring_slots, head, mirror;  // mirror = slot offset (L - F + 1)
@@ -82,7 +95,21 @@ struct RenderParams {
   void* ring;
   int32_t obs_h, obs_w, rs_mode, rs_words;  // rs_mode: CBEV_RS_* (engine.h); rs_words = size of rs_tab
   const int32_t* rs_tab;                    // cv2 area tables of both axes (api.cu: build_resize_tables)
+  unsigned long long* trace;                // [N][8] phase timestamps or null (cbev_debug_read_trace)
 };
+
+__device__ __forceinline__ void trace_mark(const RenderParams& P, int env, int slot) {
+  if (P.trace != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[(size_t)env * 8 + slot] = t;
+    if (slot == 0) {
+      unsigned sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      P.trace[(size_t)env * 8 + 6] = sm;
+    }
+  }
+}
 
 // cv2 INTER_AREA 128 -> 96: dst pixel d covers src taps s0 = floor(4d/3), s0+1 with weights
 // (3-ph, 1+ph)/4, ph = d % 3.  Product weights are in 1/16 units; sums are exact.
@@ -162,12 +189,23 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   uint8_t* s_cm = (uint8_t*)(s_bar + 2);     // channel bits per palette index for this mask mode
   float4* s_lut = (float4*)(s_cm + 16);      // 16 x float4: 4 mask bits -> four 0.0f / 1.0f values
   int* s_count = (int*)(s_lut + 16);
+  uint32_t* s_rects = (uint32_t*)(s_count + 4);  // draw list (max_rects words); the resize tables follow (GEN)
 
   const int env = P.env_lo + blockIdx.x;
   const int tid = threadIdx.x;
   const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
   const int flags = d[RD_FLAGS];
   if (flags & 2) return;  // masked-out env of a partial reset
+  if ((P.pad0 & 32) && blockIdx.x < 592) {  // timing probe: stagger the first wave (bits 8..15 = delay in 0.25 us)
+    const unsigned ns = (blockIdx.x / 148) * ((P.pad0 >> 8) & 255) * 250u;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+  }
+  trace_mark(P, env, 0);
 
   if (tid == 0) {
     mbar_init(s_bar, 1);
@@ -188,26 +226,52 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   if (tid < 16)
     s_lut[tid] = make_float4((tid & 1) ? 1.0f : 0.0f, (tid & 2) ? 1.0f : 0.0f, (tid & 4) ? 1.0f : 0.0f,
                              (tid & 8) ? 1.0f : 0.0f);
+  // the draw list travels while the tile is in flight: one coalesced load instead of one dependent global
+  // load per rectangle after the tile has landed (under the store traffic of the other CTAs each costs ~0.6 us)
+  const int nrects = d[RD_NRECTS];
+  {
+    // speculative: every slot of the list is fetched without waiting for the count (no dependent load)
+    const uint32_t* rl = P.rects + (size_t)env * P.max_rects;
+    for (int r = tid; r < P.max_rects; r += RT) s_rects[r] = rl[r];
+  }
   __syncthreads();
   mbar_wait(s_bar, 0);
   s_tile += s_desc[RD_OX] & 15;  // crop pixel (x, y) lives at s_tile[y * pitch + x]
+  trace_mark(P, env, 1);
 
   // ---- 2. draw list, in order (later rects overwrite earlier ones) ----
-  const int nrects = s_desc[RD_NRECTS];
+  // Runs of consecutive rects with the same colour (the route targets are one long run) are painted in parallel,
+  // one rect per lane: overlapping rects of one run write the same value, so their order does not matter; runs
+  // follow each other in list order, which is all "later overwrites earlier" needs.
   if (nrects > 0) {
     if (tid < 32) {
-      const uint32_t* rl = P.rects + (size_t)env * P.max_rects;
-      for (int r = 0; r < nrects; ++r) {
-        uint32_t pk = rl[r];
-        int x0 = pk & 255, y0 = (pk >> 8) & 255, w = ((pk >> 16) & 63) + 1, h = ((pk >> 22) & 63) + 1;
-        uint8_t pal = (uint8_t)(pk >> 28);
-        for (int i = tid; i < w * h; i += 32) s_tile[(y0 + i / w) * pitch + x0 + i % w] = pal;
+      int r = 0;
+      while (r < nrects) {
+        const uint32_t pal = s_rects[r] >> 28;
+        int e = r;
+        for (;;) {  // end of the run that starts at r
+          const int idx = e + tid;
+          const unsigned same = __ballot_sync(0xffffffffu, idx < nrects && (s_rects[idx] >> 28) == pal);
+          if (same == 0xffffffffu) { e += 32; continue; }
+          e += __ffs(~same) - 1;
+          break;
+        }
+        for (int q = r + tid; q < e; q += 32) {
+          const uint32_t pk = s_rects[q];
+          const int x0 = pk & 255, y0 = (pk >> 8) & 255, w = ((pk >> 16) & 63) + 1, h = ((pk >> 22) & 63) + 1;
+          uint8_t* row = s_tile + y0 * pitch + x0;
+          for (int yy = 0; yy < h; ++yy, row += pitch)
+            for (int xx = 0; xx < w; ++xx) row[xx] = (uint8_t)pal;
+        }
         __syncwarp();
+        r = e;
       }
     }
+    trace_mark(P, env, 7);
     __syncthreads();
   }
 
+  trace_mark(P, env, 2);
   // ---- 3. rotate + compose + ego square -> 128x128 palette-index FOV ----
   {
     const int mode = s_desc[RD_MODE], turns = s_desc[RD_TURNS];
@@ -231,19 +295,28 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       }
     }
     if (fast && mode == 1) {
-      for (int u = tid; u < S * S / 4; u += RT) {
-        const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
-        const int ryp = oy - top, rxp = ox0 - left;
-        int dx = rax + isin * (rcy - ryp) + rxp * icos;
-        int dy = ray - icos * (rcy - ryp) + rxp * isin;
-        uint32_t packed = 0;
+      // 16 samples (4 words of 4 pixels) per iteration: all loads are issued before the first store, so the
+      // shared-memory latency is paid once per 16 pixels instead of once per 4 (tile and fov may alias for the compiler)
+      for (int u0 = tid; u0 < S * S / 4; u0 += 4 * RT) {
+        uint32_t packed[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          packed |= (uint32_t)s_tile[(dy >> 16) * pitch + (dx >> 16)] << (8 * k);
-          dx += icos;
-          dy += isin;
+        for (int g = 0; g < 4; ++g) {
+          const int u = u0 + g * RT;
+          const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+          const int ryp = oy - top, rxp = ox0 - left;
+          int dx = rax + isin * (rcy - ryp) + rxp * icos;
+          int dy = ray - icos * (rcy - ryp) + rxp * isin;
+          uint32_t pk = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            pk |= (uint32_t)s_tile[(dy >> 16) * pitch + (dx >> 16)] << (8 * k);
+            dx += icos;
+            dy += isin;
+          }
+          packed[g] = pk;
         }
-        ((uint32_t*)s_fov)[u] = packed;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ((uint32_t*)s_fov)[u0 + g * RT] = packed[g];
       }
     } else if (fast) {
       // exact 90-degree turns (rotate90): src = base + x * step_x + y * step_y
@@ -307,6 +380,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     }
   }
   __syncthreads();
+  trace_mark(P, env, 3);
   if (P.fov_out != nullptr) {
     uint4* dst = (uint4*)(P.fov_out + (size_t)env * S * S);
     for (int u = tid; u < S * S / 16; u += RT) dst[u] = ((const uint4*)s_fov)[u];
@@ -339,7 +413,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   uint8_t* s_out = s_region;                        // OH x OW bytes: channel bitmask (semantic) or gray level
   if (GEN) {
     // ---- 4g. cv2.resize(INTER_AREA) for any obs_size <= 128 (ResizeObservation, envs/__init__.py:62) ----
-    int32_t* s_tab = (int32_t*)(s_count + 4);
+    int32_t* s_tab = (int32_t*)(s_rects + ((P.max_rects + 3) & ~3));
     for (int u = tid; u < P.rs_words; u += RT) s_tab[u] = P.rs_tab[u];
     __syncthreads();
     const int nx = s_tab[0], ny = s_tab[1];
@@ -448,6 +522,44 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   }
 
   // ---- 5. expand + stream out ----
+  trace_mark(P, env, 4);
+  if (P.pad0 & 8) return;  // timing probe: no observation stores
+  if (!GEN && OBS_MODE == CBEV_OBS_SEMANTIC && (P.pad0 & 16)) {  // experiment (profiles/README.md): slower than direct stores
+    // Expand one third of a channel plane (12 KB) at a time into a double-buffered staging area in the dead tile
+    // region and hand it to the copy engine, once per ring slot the frame belongs to (a reset frame fills the whole
+    // window, frames near the wrap are mirrored): the expansion is done once whatever the number of destinations.
+    constexpr int PLANE4 = 96 * 96 / 4, K = 3, CH4 = PLANE4 / K;
+    float4* s_stage = (float4*)(s_region + 96 * 96);
+    uint8_t* env_base = (uint8_t*)P.ring + (size_t)env * P.ring_slots * P.frame_bytes;
+#pragma unroll 1
+    for (int i = 0; i < CHANNELS * K; ++i) {
+      float4* buf = s_stage + (i & 1) * CH4;
+      if (i >= 2) {  // the group that last read this buffer (chunk i - 2) must have been drained
+        if (tid == 0) bulk_wait_read<1>();
+        __syncthreads();
+      }
+      const int c = i / K, part = i - c * K;
+#pragma unroll
+      for (int q = tid; q < CH4; q += RT) {
+        const uint32_t t = (((const uint32_t*)s_out)[part * CH4 + q] >> c) & 0x01010101u;
+        buf[q] = s_lut[(t * 0x01020408u) >> 24];
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const size_t off = ((size_t)c * PLANE4 + (size_t)part * CH4) * 16;
+        for (int slot = first; slot <= P.head; ++slot) {
+          bulk_store(env_base + (size_t)slot * P.frame_bytes + off, buf, CH4 * 16);
+          const int sl = slot - P.mirror;
+          if (P.mirror > 0 && sl >= 0) bulk_store(env_base + (size_t)sl * P.frame_bytes + off, buf, CH4 * 16);
+        }
+        bulk_commit();
+      }
+    }
+    if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the reads of the copy engine
+    trace_mark(P, env, 5);
+    return;
+  }
   for (int slot = first; slot <= P.head; ++slot) {
 #pragma unroll 1
     for (int rep = 0; rep < 2; ++rep) {
@@ -475,6 +587,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       }
     }
   }
+  trace_mark(P, env, 5);
 }
 
 // ---- temporal fusion of the stacked masks (wrappers/rgb_to_semantic.py:152-193) ---------------------
@@ -588,7 +701,7 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   const int S = P.fov;
   size_t tile = (size_t)P.crop * P.box_w;
   if (e->cfg.obs_mode == CBEV_OBS_RGB && tile < (size_t)S * S * 3) tile = (size_t)S * S * 3;  // RGB staging
-  if (tile < 96 * 96 + 2 * 1024 + 64) tile = 96 * 96 + 2 * 1024 + 64;  // output bytes + mixed-block worklist
+  if (tile < 96 * 96 + 2 * 12288) tile = 96 * 96 + 2 * 12288;  // output bytes + worklist / 2 x 12 KB store staging
   if (tile < (size_t)e->cfg.obs_h * e->cfg.obs_w) tile = (size_t)e->cfg.obs_h * e->cfg.obs_w;
   tile = ((tile + 127) / 128) * 128;
   P.tile_bytes = (int32_t)tile;
@@ -598,8 +711,9 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.rs_mode = e->rs_mode;
   P.rs_words = e->rs_words;
   P.rs_tab = e->rs_tab;
+  P.trace = (e->debug_flags & 4) ? e->trace : nullptr;
   size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16 +
-                (e->rs_mode == CBEV_RS_FAST96 ? 0 : 16 + (size_t)e->rs_words * 4);
+                (size_t)((e->max_rects + 3) & ~3) * 4 + (e->rs_mode == CBEV_RS_FAST96 ? 0 : (size_t)e->rs_words * 4);
   int rc = 1;
   if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, s);
   else if (e->cfg.obs_mode == CBEV_OBS_GRAY) rc = launch<CBEV_OBS_GRAY, 1>(e, P, smem, s);

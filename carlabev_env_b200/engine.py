@@ -37,7 +37,7 @@ SG_MAX = 12
 EXPORTS = ("cbev_version", "cbev_last_error", "cbev_create", "cbev_destroy", "cbev_upload_map",
            "cbev_upload_scene_pool", "cbev_frame_bytes", "cbev_bind_obs_ring", "cbev_reset", "cbev_step",
            "cbev_step_host", "cbev_obs_head", "cbev_get_state", "cbev_set_ego_state", "cbev_copy_fov",
-           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse", "cbev_debug_rerender", "cbev_set_debug_flags")
+           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse", "cbev_debug_rerender", "cbev_set_debug_flags", "cbev_debug_read_trace")
 
 
 class CbevConfig(C.Structure):
@@ -115,6 +115,7 @@ def load_library(build_if_missing: bool = True):
     lib.cbev_set_ego_state.argtypes = [_P, _P]
     lib.cbev_copy_fov.argtypes = [_P, _P, _P]
     lib.cbev_keep_fov.argtypes = [_P, C.c_int32]
+    lib.cbev_debug_read_trace.argtypes = [_P, _P]
     lib.cbev_upload_fov_mask.argtypes = [_P, _P]
     lib.cbev_fuse.argtypes = [_P, C.c_int32, _P, _P]
     lib.cbev_debug_rerender.argtypes = [_P, C.c_int32, _P]
@@ -356,6 +357,12 @@ class Engine:
 
     def set_debug_flags(self, flags: int):
         _check(self.lib, self.lib.cbev_set_debug_flags(self.handle, int(flags)))
+
+    def read_trace(self):
+        """Per-CTA phase timestamps of the last raster launch, uint64 [N, 8] (set_debug_flags(4) first)."""
+        out = np.zeros((self.N, 8), dtype=np.uint64)
+        _check(self.lib, self.lib.cbev_debug_read_trace(self.handle, out.ctypes.data))
+        return out
 
     def keep_fov(self, on=True):
         _check(self.lib, self.lib.cbev_keep_fov(self.handle, int(on)))

@@ -283,6 +283,11 @@ int cbev_set_debug_flags(cbev_handle h, int32_t flags);
 /* Diagnostic: re-run the raster kernel `times` times on the current descriptors (timing experiments). */
 int cbev_debug_rerender(cbev_handle h, int32_t times, void* stream);
 
+/* Diagnostic: per-CTA phase timestamps of the last raster launch (enable with debug flag 4 before the step).
+ * host_out: uint64[N][8] = globaltimer ns at {start, tile landed, draw list done, rotate done, resize done,
+ * stores issued}, SM id, unused. */
+int cbev_debug_read_trace(cbev_handle h, uint64_t* host_out);
+
 /* ABI self-check: sizeof(cbev_config), sizeof(cbev_pool_desc), sizeof(cbev_step_out). */
 int cbev_abi_sizes(int32_t* config_bytes, int32_t* pool_desc_bytes, int32_t* step_out_bytes);
 
