@@ -368,6 +368,12 @@ def run_ours(args):
         sim_avg_ms = sim_ms / n_prof_steps
         alg_bytes = N * frame_bytes
         achieved = alg_bytes / (render_avg_ms * 1e-3) / 1e9 if render_avg_ms > 0 else 0.0
+        # bytes the kernel really writes per launch: every env's new frame, F - 1 more copies for an env that reset
+        # (FrameStackObservation pads the window with the reset frame) and the mirrored frames near the ring wrap
+        resets_per_env_step = stats["episodes"] / stats["env_steps"] if stats.get("env_steps") else 0.0
+        Fs = 4
+        mirror_share = (Fs - 1) / max(eng.L - Fs + 1, 1) if W["obs"] == "semantic" else 0.0
+        written = alg_bytes * (1.0 + (Fs - 1) * resets_per_env_step + mirror_share) if W["obs"] == "semantic" else alg_bytes
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(steps_per_env=args.cpu_steps)
@@ -392,6 +398,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "kernel": "k_render",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "written_bytes_per_launch": written,
+                         "written_gbs": written / (render_avg_ms * 1e-3) / 1e9 if render_avg_ms > 0 else None,
+                         "written_note": "algorithmic bytes + (F-1) extra copies of every reset frame + ring-wrap mirrors "
+                                         "(estimated from the episode counter); frac uses the algorithmic bytes only",
                          "kernel_ms": render_avg_ms, "sim_kernel_ms": sim_avg_ms, "profiled_steps": n_prof_steps,
                          "launches_per_step": 2 * pairs_per_step,
                          "step_fraction_render": render_avg_ms / (ms / args.steps) if ms else None},

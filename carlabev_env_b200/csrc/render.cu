@@ -196,15 +196,6 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
   const int flags = d[RD_FLAGS];
   if (flags & 2) return;  // masked-out env of a partial reset
-  if ((P.pad0 & 32) && blockIdx.x < 592) {  // timing probe: stagger the first wave (bits 8..15 = delay in 0.25 us)
-    const unsigned ns = (blockIdx.x / 148) * ((P.pad0 >> 8) & 255) * 250u;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-      __nanosleep(200);
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    } while (t1 - t0 < ns);
-  }
   trace_mark(P, env, 0);
 
   if (tid == 0) {
