@@ -502,7 +502,7 @@ __device__ __forceinline__ void actor_chunk_step(const SimParams& P, const PoolD
 // runs uniformly on the G lanes of a group, so a smaller G wastes less of the fp64 pipe; G = 32 is used when scenes
 // carry many actors (lanes = actors), G = 8 for the scripted scenarios (<= 8 actors).
 template <int G>
-__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, G == 32 ? CBEV_SIM_BLOCKS_PER_SM : 3)
+__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, G == 32 ? CBEV_SIM_BLOCKS_PER_SM : 4)
 k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, cbev_step_out out,
       int32_t* __restrict__ desc, uint32_t* __restrict__ rects, double* __restrict__ gstats) {
   constexpr int EPW = 32 / G;  // environments per warp
