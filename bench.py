@@ -43,43 +43,63 @@ def measured_peak_gbs():
 
 
 # ------------------------------------------------------------------------------------ scene pool
-def _pool_worker(indices):
-    from carlabev_env_b200.scenes import build_scripted_scene
-    from carlabev_env_b200.vector_env import load_town01_map
+def _pool_cache_dir():
+    import tempfile
 
-    cls = load_town01_map()
-    return [build_scripted_scene("lead_brake", i, level=1 + i % 3, cls_map=cls) for i in indices]
+    d = os.path.join(tempfile.gettempdir(), "cbev_bench_pools")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def _log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')} rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
+def _shared_pool(tag, n, make):
+    """Scene pool `tag` of n scenes, generated once per box: rank 0 builds it on the host cores and publishes the
+    file atomically; the other ranks only ever wait for that file (no collective is pending while the host works,
+    nobody generates twice) and fail loudly if it does not appear."""
+    from carlabev_env_b200.pool import load_pool, save_pool
+
+    path = os.path.join(_pool_cache_dir(), f"pool_{tag}_{n}.npz")
+    rank = int(os.environ.get("RANK", "0"))
+    if os.path.exists(path):
+        try:
+            return load_pool(path)
+        except Exception as ex:  # noqa: BLE001
+            _log(f"cached pool {path} unreadable ({ex}); rebuilding")
+    if rank == 0:
+        t0 = time.time()
+        scenes = make()
+        tmp = f"{path}.{os.getpid()}.tmp.npz"
+        try:
+            save_pool(tmp, scenes)
+            os.replace(tmp, path)
+        except Exception as ex:  # noqa: BLE001
+            _log(f"could not cache the pool at {path}: {ex}")
+            if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                raise
+        _log(f"pool {tag}: {n} scenes generated in {time.time() - t0:.1f} s")
+        return scenes
+    deadline = time.time() + 900.0
+    while not os.path.exists(path):
+        if time.time() > deadline:
+            raise RuntimeError(f"rank {rank}: pool file {path} did not appear within 900 s")
+        time.sleep(0.5)
+    return load_pool(path)
 
 
 def build_pool(n_scenes, cache=True):
     """lead_brake pool: level = 1 + i % 3, scene_seed = i (host generator, carlabev_env_b200/scenes.py)."""
-    from carlabev_env_b200.pool import load_pool, save_pool
-    path = os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else ".",
-                        f".pool_lead_brake_{n_scenes}.npz")
-    if cache and os.path.exists(path):
-        try:
-            return load_pool(path)
-        except Exception:  # noqa: BLE001
-            pass
-    workers = min(os.cpu_count() or 1, 32)
-    if n_scenes >= 512 and workers > 1:
-        import multiprocessing as mp
+    from carlabev_env_b200.scenes import build_pool as build
 
-        chunks = [list(range(w, n_scenes, workers)) for w in range(workers)]
-        with mp.get_context("spawn").Pool(workers) as pool:
-            parts = pool.map(_pool_worker, chunks)
-        scenes = [None] * n_scenes
-        for idx, part in zip(chunks, parts):
-            for i, sc in zip(idx, part):
-                scenes[i] = sc
-    else:
-        scenes = _pool_worker(list(range(n_scenes)))
-    if cache:
-        try:
-            save_pool(path, scenes)
-        except Exception:  # noqa: BLE001
-            pass
-    return scenes
+    reqs = [dict(scene="lead_brake", level=1 + i % 3, scene_seed=i) for i in range(n_scenes)]
+    return _shared_pool("lead_brake", n_scenes, lambda: build(reqs, workers=_host_workers()))
+
+
+def _host_workers():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return max(1, min((os.cpu_count() or 1) - (world - 1), 32))
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -208,23 +228,10 @@ WORKLOADS = {
 
 def _cached_pool(tag, requests, pad=182):
     """Pool generated on the host cores by carlabev_env_b200.scenes.build_pool (bit-identical to the reference's
-    post-reset state for the same options and scene_seed), cached next to the bench outputs."""
-    from carlabev_env_b200.pool import load_pool, save_pool
+    post-reset state for the same options and scene_seed)."""
     from carlabev_env_b200.scenes import build_pool as build
 
-    path = os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else ".",
-                        f".pool_{tag}_{len(requests)}.npz")
-    if os.path.exists(path):
-        try:
-            return load_pool(path)
-        except Exception:  # noqa: BLE001
-            pass
-    scenes = build(requests, pad=pad)
-    try:
-        save_pool(path, scenes)
-    except Exception:  # noqa: BLE001
-        pass
-    return scenes
+    return _shared_pool(tag, len(requests), lambda: build(requests, pad=pad, workers=_host_workers()))
 
 
 def workload_pool(name, args):
@@ -263,7 +270,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     W = WORKLOADS[args.workload]
     N = args.envs or W["envs"]
-    scenes = workload_pool(args.workload, args)
+    scenes = workload_pool(args.workload, args)  # rank 0 generates, the other ranks wait for its file
+    _log(f"pool ready: {len(scenes)} scenes")
     a_mean = float(np.mean([len(s["act_kind"]) for s in scenes]))
     a_max = int(max(len(s["act_kind"]) for s in scenes))
     discrete = W["actions"] == "discrete"
