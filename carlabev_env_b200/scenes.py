@@ -213,6 +213,79 @@ def _route_length_m(rx, ry) -> float:
     return float(total) * MPP
 
 
+def route_profile_metrics(ax, ay, turn_rate_thresh=0.12, min_turn_segment_m=4.0) -> dict:
+    """compute_route_profile_metrics (src/control/route_profile.py:57-159): turning rate of the smoothed route
+    [rad/m] labelled left (+) / right (-) / straight, turn segments of at least 4 m, profile name."""
+    straight = dict(straight_fraction=1.0, left_turn_fraction=0.0, right_turn_fraction=0.0, turn_count=0,
+                    has_left_turn=False, has_right_turn=False, intersection_like=False, route_profile="mostly_straight")
+    cx, cy, cyaw = smooth_and_compute(ax, ay, window=11, poly=3)
+    cx, cy = np.asarray(cx, dtype=float), np.asarray(cy, dtype=float)
+    cyaw = np.unwrap(np.asarray(cyaw, dtype=float))
+    if cx.size < 2 or cy.size < 2 or cyaw.size < 2:
+        return straight
+    ds_m = np.hypot(np.diff(cx), np.diff(cy)) * MPP
+    valid = ds_m > 1e-6
+    if not np.any(valid):
+        return straight
+    dtheta = np.diff(cyaw)
+    dtheta = (dtheta + np.pi) % (2.0 * np.pi) - np.pi
+    ds_valid = ds_m[valid]
+    turn_rate = dtheta[valid] / ds_valid
+    labels = np.where(turn_rate > turn_rate_thresh, 1, np.where(turn_rate < -turn_rate_thresh, -1, 0))
+    total = float(ds_valid.sum())
+    if total <= 1e-9:
+        return straight
+    segments, cur_sign, cur_len = [], 0, 0.0       # _normalize_turn_segments (:21-54)
+    for sign, seg in zip(labels, ds_valid):
+        sign = int(sign)
+        if sign == 0:
+            if cur_sign != 0 and cur_len >= min_turn_segment_m:
+                segments.append(cur_sign)
+            cur_sign, cur_len = 0, 0.0
+        elif sign == cur_sign:
+            cur_len += float(seg)
+        else:
+            if cur_sign != 0 and cur_len >= min_turn_segment_m:
+                segments.append(cur_sign)
+            cur_sign, cur_len = sign, float(seg)
+    if cur_sign != 0 and cur_len >= min_turn_segment_m:
+        segments.append(cur_sign)
+    turn_count = len(segments)
+    has_left, has_right = any(sg > 0 for sg in segments), any(sg < 0 for sg in segments)
+    sf = float(ds_valid[labels == 0].sum()) / total
+    lf = float(ds_valid[labels == 1].sum()) / total
+    rf = float(ds_valid[labels == -1].sum()) / total
+    if turn_count == 0 or sf >= 0.9:
+        name = "mostly_straight"
+    elif turn_count == 1 and lf >= rf:
+        name = "single_left"
+    elif turn_count == 1 and rf > lf:
+        name = "single_right"
+    elif turn_count >= 2:
+        name = "multi_turn"
+    else:
+        name = "mixed"
+    return dict(straight_fraction=sf, left_turn_fraction=lf, right_turn_fraction=rf, turn_count=turn_count,
+                has_left_turn=has_left, has_right_turn=has_right,
+                intersection_like=turn_count >= 2 or (has_left and has_right), route_profile=name)
+
+
+def matches_route_profile(m, route_profile=None, min_turns=None, max_turns=None, intersection_required=None) -> bool:
+    """src/control/route_profile.py:162-182."""
+    if route_profile is not None and route_profile != "any" and m.get("route_profile") != route_profile:
+        return False
+    turns = int(m.get("turn_count", 0))
+    if min_turns is not None and turns < min_turns:
+        return False
+    if max_turns is not None and turns > max_turns:
+        return False
+    if intersection_required is True and not bool(m.get("intersection_like", False)):
+        return False
+    if intersection_required is False and bool(m.get("intersection_like", False)):
+        return False
+    return True
+
+
 def _assemble(agent, specs, len_route, hero_np_rng, actor_np_rngs, kind, level, scene_seed, lights=()) -> dict:
     """Scene.load_scene (scenes/scene.py:61-88) on a sampled actor dict -> pool entry: int32 ego route, hero spawn
     with its start jitter, then ActorManager.reset_all (vehicles, then pedestrians; each Controller.set_route draws
@@ -307,9 +380,10 @@ _EGO_GRAPHS = {"full_vehicle": ("vehicle-full", "vehicle"), "right_lane": ("vehi
                "left_lane": ("vehicle-L", "L")}  # scene_generator.py:252-268
 
 
-def _ego_route_in_range(graph, node_cls, lo_m, hi_m, rng, max_attempts=100):
-    """find_route_in_range (scenes/utils.py:121-214) without route-profile filters: two random nodes, shortest
-    path thinned at 10 raw px, waypoints of path[1:] in surface pixels, accepted when lo <= length [m] <= hi."""
+def _ego_route_in_range(graph, node_cls, lo_m, hi_m, rng, max_attempts=100, filters=None):
+    """find_route_in_range (scenes/utils.py:121-214): two random nodes, shortest path thinned at 10 raw px,
+    waypoints of path[1:] in surface pixels, accepted when lo <= length [m] <= hi and the route-profile filters
+    (route_profile / min_turns / max_turns / intersection_required) hold."""
     for _ in range(max_attempts):
         a = graph.random_node(node_cls, rng)
         b = graph.random_node(node_cls, rng)
@@ -322,12 +396,15 @@ def _ego_route_in_range(graph, node_cls, lo_m, hi_m, rng, max_attempts=100):
         rx, ry = [p[0] for p in pts], [p[1] for p in pts]
         total = _route_length_m(rx, ry)
         if lo_m <= total <= hi_m:
+            if filters and not matches_route_profile(route_profile_metrics(rx, ry), **filters):
+                continue
             return rx, ry, total
     return None
 
 
 def sample_rdm(bundle, num_vehicles, dist_range, ego_target_speed=12.0, ego_route_graph="full_vehicle",
-               traffic_enabled=True, max_route_attempts=20):
+               traffic_enabled=True, max_route_attempts=20, route_profile=None, route_profile_mix=None, min_turns=None,
+               max_turns=None, intersection_required=None):
     """SceneGenerator.generate_random (managers/scene_generator.py:196-330) + get_actor (:333-344)."""
     from .lanegraph import load_graph
 
@@ -336,9 +413,21 @@ def sample_rdm(bundle, num_vehicles, dist_range, ego_target_speed=12.0, ego_rout
                          "Expected one of: full_vehicle, right_lane, left_lane.")
     key, node_cls = _EGO_GRAPHS[ego_route_graph]
     graph = load_graph(key)
+    if route_profile_mix:  # _sample_route_profile (scene_generator.py:78-93): one weighted draw from route_rng
+        labels = list(route_profile_mix.keys())
+        weights = [float(route_profile_mix[k]) for k in labels]
+        if any(w < 0.0 for w in weights):
+            raise ValueError(f"route_profile_mix must use non-negative weights: {route_profile_mix}")
+        if sum(weights) <= 0.0:
+            raise ValueError(f"route_profile_mix must contain at least one positive weight: {route_profile_mix}")
+        route_profile = bundle.route_rng.choices(labels, weights=weights, k=1)[0]
+    filters = dict(route_profile=route_profile, min_turns=min_turns, max_turns=max_turns,
+                   intersection_required=intersection_required)
+    if all(v is None for v in filters.values()):
+        filters = None
     ego = None
     for _ in range(max_route_attempts):
-        ego = _ego_route_in_range(graph, node_cls, dist_range[0], dist_range[1], bundle.route_rng)
+        ego = _ego_route_in_range(graph, node_cls, dist_range[0], dist_range[1], bundle.route_rng, filters=filters)
         if ego is not None and len(ego[0]) > 1:
             break
         ego = None
@@ -370,10 +459,8 @@ def build_rdm_scene(scene_seed: int, difficulty_id: str | None = None, num_vehic
     expands like build_random_navigation_options (config/reset.py:104-116).  Vehicles draw lanes / nodes from
     traffic_rng and start jitter from traffic_np_rng, the ego route from route_rng, the hero jitter from
     route_np_rng (src/randomness.py)."""
-    bad = [k for k in ("route_profile", "route_profile_mix", "min_turns", "max_turns", "intersection_required")
-           if unsupported.get(k) is not None]
-    if bad:
-        raise NotImplementedError(f"route-profile filters are not built (SURVEY.md section 2, out of scope): {bad}")
+    prof = {k: unsupported.get(k) for k in ("route_profile", "route_profile_mix", "min_turns", "max_turns",
+                                             "intersection_required")}
     if difficulty_id is not None:
         from .config import get_difficulty_spec
 
@@ -389,7 +476,7 @@ def build_rdm_scene(scene_seed: int, difficulty_id: str | None = None, num_vehic
         agent, specs, len_route = sample_rdm(bundle, num_vehicles, route_dist_range,
                                              12.0 if ego_target_speed is None else ego_target_speed,
                                              ego_route_graph, True if traffic_enabled is None else traffic_enabled,
-                                             20 if max_route_attempts is None else int(max_route_attempts))
+                                             20 if max_route_attempts is None else int(max_route_attempts), **prof)
         return _assemble(agent, specs, len_route, bundle.route_np_rng, [bundle.traffic_np_rng] * len(specs),
                          "rdm", 0, scene_seed)
 

@@ -98,6 +98,17 @@ OPTION_CASES = [  # reset options beyond the bench configs: presets, parameter o
     dict(config={"type": "scenario_config", "scenario_id": "lead_brake", "level": 3,
                  "anchor": {"x": 850, "y": 950}, "parameters": {"ego_speed": 9.0, "lead_gap": 6.0}}, scene_seed=16),
     dict(config={"scenario": "jaywalk", "kwargs": {"level": 2, "anchor_y": 940, "cross_delay": 2.0}}, scene_seed=17),
+    # route-profile filters of the random-navigation reset (src/control/route_profile.py)
+    dict(scene="rdm", num_vehicles=3, route_dist_range=[30, 130], route_profile="single_left", scene_seed=20),
+    dict(scene="rdm", num_vehicles=3, route_dist_range=[30, 130], route_profile="single_right", scene_seed=21),
+    dict(scene="rdm", num_vehicles=3, route_dist_range=[30, 130], route_profile="mostly_straight", scene_seed=22),
+    dict(scene="rdm", num_vehicles=2, route_dist_range=[40, 130], min_turns=1, max_turns=2, scene_seed=23),
+    dict(scene="rdm", num_vehicles=2, route_dist_range=[40, 130], intersection_required=True, scene_seed=24),
+    dict(scene="rdm", num_vehicles=2, route_dist_range=[30, 130], intersection_required=False, scene_seed=25),
+    dict(scene="rdm", num_vehicles=2, route_dist_range=[30, 130],
+         route_profile_mix={"mostly_straight": 0.5, "single_left": 0.25, "single_right": 0.25}, scene_seed=26),
+    dict(scene="rdm", num_vehicles=2, route_dist_range=[30, 130],
+         route_profile_mix={"mostly_straight": 0.5, "single_left": 0.25, "single_right": 0.25}, scene_seed=27),
 ]
 
 

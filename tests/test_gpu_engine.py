@@ -210,8 +210,10 @@ def test_vector_env_surface_and_infos():
     assert max(len(envs._scenes[i]["act_kind"]) for i in envs._scene_of_env) <= 3
     obs, _ = envs.reset(options={"scene": "red_light_runner", "scene_seed": 77})
     envs.step(np.zeros((6, 3), np.float32))
-    with pytest.raises(NotImplementedError):
-        envs.reset(options={"scene": "rdm", "route_profile": "left_turn"})
+    with pytest.raises(RuntimeError):
+        envs.reset(options={"scene": "rdm", "route_profile": "left_turn", "max_route_attempts": 1, "scene_seed": 1})
+    obs, _ = envs.reset(seed=20, options={"scene": "rdm", "num_vehicles": 2, "route_profile": "single_left",
+                                          "route_dist_range": [30, 130]})
     # authored scene file (bundled, addressed by name) and a typed preset request (config/reset.py mirror)
     from carlabev_env_b200 import reset as R
 

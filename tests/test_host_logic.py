@@ -286,8 +286,14 @@ def test_build_pool_workers_and_option_errors():
     assert all(_same_scene(a, b) == [] for a, b in zip(serial, again))
     with pytest.raises(KeyError):
         S.build_scene({"scene": "rdm", "difficulty_id": "nope"})
-    with pytest.raises(NotImplementedError):
-        S.build_scene({"scene": "rdm", "route_profile": "left_turn"})
+    with pytest.raises(RuntimeError):   # a profile no route can have: the search gives up like the reference's
+        S.build_scene({"scene": "rdm", "route_profile": "left_turn", "max_route_attempts": 1})
+    with pytest.raises(ValueError):
+        S.build_scene({"scene": "rdm", "route_profile_mix": {"single_left": -1.0}})
+    m = S.route_profile_metrics([100.0 + 4 * i for i in range(30)], [200.0] * 30)
+    assert m["route_profile"] == "mostly_straight" and m["turn_count"] == 0 and not m["intersection_like"]
+    assert S.matches_route_profile(m, route_profile="any", max_turns=0, intersection_required=False)
+    assert not S.matches_route_profile(m, min_turns=1)
     with pytest.raises(ValueError):
         S.build_scene({"scene": "rdm", "ego_route_graph": "sidewalk"})
     with pytest.raises(KeyError):
@@ -313,8 +319,9 @@ def _jitter_only(ref, got):
 
 
 def test_reset_option_variants_match_reference():
-    """Scenario presets, parameter overrides, lane-restricted ego graphs, explicit sub-seeds, drawn levels and
-    scenario-config files: snapshots of the unmodified reference (oracle/export_pools.py options)."""
+    """Scenario presets, parameter overrides, lane-restricted ego graphs, explicit sub-seeds, drawn levels,
+    scenario-config files and route-profile filters (route_profile / route_profile_mix / min_turns / max_turns /
+    intersection_required): snapshots of the unmodified reference (oracle/export_pools.py options)."""
     import json
 
     from carlabev_env_b200 import scenes as S
@@ -323,7 +330,7 @@ def test_reset_option_variants_match_reference():
     ref = load_pool(os.path.join(ROOT, "tests", "golden", "option_scenes.npz"))
     cases = json.load(open(os.path.join(ROOT, "tests", "golden", "option_scenes.json")))
     cls = load_map()
-    assert len(ref) == len(cases) >= 15
+    assert len(ref) == len(cases) >= 23
     for r, c in zip(ref, cases):
         o = dict(c)
         got = S.build_authored_scene(o.pop("config"), cls_map=cls, **o) if "config" in o else S.build_scene(o, cls_map=cls)
