@@ -935,3 +935,42 @@ def _spawn_valid(s, cls_map, pad) -> bool:
 def build_scripted_pool(kind_level_seed, cls_map=None, pad: int = 182) -> list[dict]:
     """[(kind, level | None, scene_seed), ...] -> list of pool entries."""
     return [build_scripted_scene(k, seed, level=lv, cls_map=cls_map, pad=pad) for k, lv, seed in kind_level_seed]
+
+
+def _main(argv=None):
+    """python -m carlabev_env_b200.scenes --scene rdm --difficulty-id rt_hard_v1 --count 4096 --out pool.npz"""
+    import argparse
+    import json
+    import time
+
+    from .pool import save_pool
+
+    ap = argparse.ArgumentParser(description="Generate a scene pool on the host cores (entry i has scene_seed = seed0 + i).")
+    ap.add_argument("--scene", default="rdm", help="rdm | lead_brake | jaywalk | red_light_runner | path to an authored / scenario-config JSON")
+    ap.add_argument("--count", type=int, default=256)
+    ap.add_argument("--seed0", type=int, default=0)
+    ap.add_argument("--difficulty-id", default=None)
+    ap.add_argument("--level", type=int, default=None)
+    ap.add_argument("--options", default="{}", help="JSON dict of further reset options (num_vehicles, route_dist_range, ...)")
+    ap.add_argument("--pad", type=int, default=182, help="crop size of the camera (182 centred, 230 lookahead_75)")
+    ap.add_argument("--workers", type=int, default=None)
+    ap.add_argument("--out", required=True)
+    a = ap.parse_args(argv)
+    base = dict(json.loads(a.options))
+    if a.scene.endswith(".json"):
+        base["config_file"] = a.scene
+    else:
+        base["scene"] = a.scene
+    if a.difficulty_id is not None:
+        base["difficulty_id"] = a.difficulty_id
+    if a.level is not None:
+        base["level"] = a.level
+    t0 = time.time()
+    scenes = build_pool([{**base, "scene_seed": a.seed0 + i} for i in range(a.count)], pad=a.pad, workers=a.workers)
+    save_pool(a.out, scenes)
+    print(f"{a.out}: {len(scenes)} scenes, actors {min(len(s['act_kind']) for s in scenes)}.."
+          f"{max(len(s['act_kind']) for s in scenes)}, {time.time() - t0:.1f} s")
+
+
+if __name__ == "__main__":
+    _main()

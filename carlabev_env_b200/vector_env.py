@@ -49,14 +49,22 @@ class CarlaBEVVectorEnv:
 
     def __init__(self, cfg: RunConfig, *, scenes=None, autoreset: str = "disabled", device=None, ring_slots=None,
                  ring_budget_bytes=None, to_numpy: bool = False, raw_rgb: bool = False, seed=None,
-                 host_infos: bool = True, eval: bool = False):  # noqa: A002
+                 host_infos: bool = True, eval: bool = False, shard=None):  # noqa: A002
         import torch
 
         self.torch = torch
         self.cfg = cfg
         env = cfg.env
         self.env_cfg = env
+        # shard = (rank, world_size): this process owns the contiguous env range [lo, hi) of cfg.num_envs
+        # (distributed.shard_range); env i of the shard behaves like env lo + i of the unsharded VectorEnv
+        self.env_offset = 0
         self.num_envs = int(cfg.num_envs)
+        if shard is not None:
+            from .distributed import shard_range
+
+            lo, hi = shard_range(int(cfg.num_envs), int(shard[0]), int(shard[1]))
+            self.env_offset, self.num_envs = lo, hi - lo
         self.to_numpy = to_numpy
         self.host_infos = host_infos or autoreset == "disabled"  # masked-reset bookkeeping needs the done flags
         self.autoreset = autoreset
@@ -82,7 +90,8 @@ class CarlaBEVVectorEnv:
             reward_mode=E.REWARD_CARL if env.reward_mode == "carl" else E.REWARD_SHAPING, reward_params=params,
             autoreset=E.AUTORESET_NEXT_STEP if autoreset == "next_step" else E.AUTORESET_DISABLED,
             anchor=(env.ego_anchor_x_frac, env.ego_anchor_y_frac), max_actors=max_actors,
-            seed=cfg.seed if seed is None else seed, device=device, size=env.size, obs_size=env.obs_size)
+            seed=(cfg.seed if seed is None else seed) + (int(shard[0]) if shard is not None else 0),  # auto-reset draws
+            device=device, size=env.size, obs_size=env.obs_size)
         self.device = self.engine.device
         self.cls_map = load_town01_map()
         self.engine.upload_map(self.cls_map)
@@ -116,7 +125,7 @@ class CarlaBEVVectorEnv:
         self.current_hero = None
         self._generated, self._shipped_lists = {}, {}
         self.recorder, self._rec_pending_reset = None, False
-        if getattr(cfg, "capture_video", False):     # env 0 only, like make_carlabev_env (envs/__init__.py:93-100)
+        if getattr(cfg, "capture_video", False) and self.env_offset == 0:  # global env 0 only (envs/__init__.py:93-100)
             from .recorder import FrameRecorder
 
             self.recorder = FrameRecorder(cfg, eval=eval)
@@ -165,7 +174,7 @@ class CarlaBEVVectorEnv:
                 raise RuntimeError("no scene pool: pass scenes=... / call set_scene_pool(), or reset with "
                                    "options={'scene': 'lead_brake' | 'jaywalk', ...}")
             base = int(options.get("scene_seed", options.get("_vector_seed", self.env_cfg.seed)))
-            return (base + np.arange(n)) % len(self._scenes)
+            return (base + self.env_offset + np.arange(n)) % len(self._scenes)
         if authored is not None and not isinstance(authored, dict) and not os.path.exists(str(authored)):
             # the reference's own 7 scene files (assets/scenes/*.json) ship with the package, addressed by file name
             bundled = S.bundled_authored_files()
@@ -180,7 +189,7 @@ class CarlaBEVVectorEnv:
             if "scene_seed" in options:
                 seeds = np.full(n, int(options["scene_seed"]), dtype=np.int64)
             elif "_vector_seed" in options:
-                seeds = int(options["_vector_seed"]) + np.arange(n, dtype=np.int64)
+                seeds = int(options["_vector_seed"]) + self.env_offset + np.arange(n, dtype=np.int64)
             else:
                 seeds = np.full(n, int(self.env_cfg.seed), dtype=np.int64)
             base_opts = {k: v for k, v in options.items() if k not in ("scene_seed", "_vector_seed", "reset_mask")}
@@ -330,7 +339,9 @@ class CarlaBEVVectorEnv:
 
 
 def make_env(cfg=None, eval: bool = False, **engine_kwargs) -> CarlaBEVVectorEnv:  # noqa: A002
-    """envs/__init__.py:108-120."""
+    """envs/__init__.py:108-120.  Multi-GPU: one process per GPU, `make_env(cfg, shard=(rank, world_size),
+    device=local_rank)` gives each its contiguous slice of the `cfg.num_envs` environments; no collective is
+    involved in stepping (`distributed.allreduce_stats` sums the episode statistics when asked)."""
     if cfg is None:
         cfg = RunConfig()
     if not hasattr(cfg, "env") and not (isinstance(cfg, dict) and "env" in cfg):

@@ -698,3 +698,27 @@ def test_observation_size_errors():
     for bad in [(96, 130), (4, 4), (50, 51)]:
         with pytest.raises(E.CbevError):
             _engine(1, scenes, obs_size=bad)
+
+
+def test_sharded_vector_env_equals_the_slice_of_the_full_one():
+    """make_env(cfg, shard=(rank, world)): the shard's envs are envs [lo, hi) of the unsharded VectorEnv
+    (same per-env scene seeds, hence the same observations and rewards)."""
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+
+    cfg = RunConfig(env=EnvConfig(action_mode="continuous"), num_envs=6)
+    opts = {"scene": "lead_brake", "level": 2}
+    full = make_env(cfg, ring_budget_bytes=32 << 20)
+    obs_full, _ = full.reset(seed=100, options=dict(opts))
+    act = np.tile(np.array([[0.6, 0.1, 0.0]], np.float32), (6, 1))
+    _, rew_full, *_ = full.step(act)
+    for rank in range(3):
+        part = make_env(cfg, shard=(rank, 3), ring_budget_bytes=32 << 20)
+        assert part.num_envs == 2 and part.env_offset == 2 * rank
+        obs, _ = part.reset(seed=100, options=dict(opts))
+        assert bool((obs == obs_full[2 * rank: 2 * rank + 2]).all())
+        _, rew, *_ = part.step(act[:2])
+        assert bool((rew == rew_full[2 * rank: 2 * rank + 2]).all())
+        part.close()
+    full.close()
+    with pytest.raises(ValueError):
+        make_env(cfg, shard=(0, 4))
