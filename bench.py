@@ -240,7 +240,10 @@ def workload_pool(name, args):
     if name == "c2":
         return build_pool(args.pool)
     if w["pool"] == "rdm_rt_hard_v1":     # configs[2]: K = 4096 scenes, seeds 0..K-1
-        return _cached_pool("rdm_rt_hard_v1", [dict(scene="rdm", difficulty_id="rt_hard_v1", scene_seed=i)
+        from carlabev_env_b200.reset import RandomNavigationReset, build_reset_options
+
+        return _cached_pool("rdm_rt_hard_v1", [build_reset_options(RandomNavigationReset(difficulty_id="rt_hard_v1",
+                                                                                         scene_seed=i))
                                                for i in range(args.pool)])
     if w["pool"] == "mixed_edge":         # configs[3]: K = 2048, jaywalk levels 1-4 round-robin / red_light_runner
         k = min(args.pool, 2048)

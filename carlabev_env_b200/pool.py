@@ -165,17 +165,30 @@ def load_shipped_pool(name: str) -> list[dict]:
     return load_pool(os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "pools", f"{name}.npz"))
 
 
-def shipped_pool_for(options: dict) -> str | None:
-    """Name of the shipped pool generated with these reset options, if any."""
+_GENERATION_KEYS = ("ego_route_graph", "ego_target_speed", "route_profile", "route_profile_mix", "min_turns", "max_turns",
+                    "intersection_required", "max_route_attempts", "route_seed", "traffic_seed", "scenario_seed",
+                    "intersection_index", "anchor_x", "anchor_y", "ego_speed", "adv_speed", "max_reset_attempts")
+
+
+def shipped_pool_for(options: dict, max_vehicles: int = 50) -> str | None:
+    """Name of the shipped pool whose entries the reference generates for exactly these reset options (entry i <->
+    scene_seed i), if any.  The match is on the EFFECTIVE generation parameters (scene_generator.py:95-107:
+    `num_vehicles` defaults to EnvConfig.max_vehicles, `route_dist_range` to [30, 100]; a bare `difficulty_id` is
+    context metadata), and any option that changes the generated scene rules the snapshots out."""
     scene = options.get("scene", "rdm")
     if options.get("config_file") or str(scene).endswith(".json"):
         return "authored_scenes"
+    if any(options.get(k) is not None for k in _GENERATION_KEYS):
+        if not (options.get("ego_route_graph") in (None, "full_vehicle")
+                and all(options.get(k) is None for k in _GENERATION_KEYS if k != "ego_route_graph")):
+            return None
     if scene == "red_light_runner":
         return "red_light_runner"
-    if scene == "rdm":
-        diff = options.get("difficulty_id")
-        if diff in ("rt_hard_v1", "rt_medium_v1"):
-            return f"rdm_{diff}"
-        if options.get("num_vehicles") == 50:
-            return "rdm_dense_50"
+    if scene == "rdm" and options.get("traffic_enabled", True):
+        nv = int(options.get("num_vehicles", max_vehicles))
+        rng = tuple(int(v) for v in options.get("route_dist_range", (30, 100)))
+        for name in ("rdm_rt_hard_v1", "rdm_rt_medium_v1", "rdm_dense_50"):
+            ref = SHIPPED_POOLS[name]
+            if nv == ref["num_vehicles"] and rng == tuple(ref["route_dist_range"]):
+                return name
     return None

@@ -455,18 +455,14 @@ def build_rdm_scene(scene_seed: int, difficulty_id: str | None = None, num_vehic
     """CarlaBEV.reset(options={"scene": "rdm", ...}) -> pool entry (random navigation with background traffic).
 
     Option meaning and defaults follow build_scene (scene_generator.py:95-168): `num_vehicles` defaults to
-    EnvConfig.max_vehicles, `route_dist_range` to [30, 100], `ego_target_speed` to 12 m/s; `difficulty_id`
-    expands like build_random_navigation_options (config/reset.py:104-116).  Vehicles draw lanes / nodes from
+    EnvConfig.max_vehicles, `route_dist_range` to [30, 100], `ego_target_speed` to 12 m/s.  Vehicles draw lanes / nodes from
     traffic_rng and start jitter from traffic_np_rng, the ego route from route_rng, the hero jitter from
     route_np_rng (src/randomness.py)."""
     prof = {k: unsupported.get(k) for k in ("route_profile", "route_profile_mix", "min_turns", "max_turns",
                                              "intersection_required")}
-    if difficulty_id is not None:
-        from .config import get_difficulty_spec
-
-        spec = get_difficulty_spec(difficulty_id)   # KeyError lists the presets (config/difficulty.py:50-58)
-        traffic_enabled, num_vehicles, route_dist_range = (spec["traffic_enabled"], spec["num_vehicles"],
-                                                           spec["route_dist_range"])
+    # `difficulty_id` in raw reset options is context metadata only (scene_generator.py:144-150): the preset is
+    # expanded into num_vehicles / route_dist_range / traffic_enabled by the typed request
+    # (reset.build_random_navigation_options, config/reset.py:104-116), not here.
     num_vehicles = max_vehicles if num_vehicles is None else num_vehicles
     route_dist_range = [30, 100] if route_dist_range is None else route_dist_range
     bundle = RNGBundle(scene_seed, unsupported.get("route_seed"), unsupported.get("traffic_seed"),

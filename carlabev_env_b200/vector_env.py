@@ -199,7 +199,7 @@ class CarlaBEVVectorEnv:
             new = [int(sd) for sd in np.unique(seeds[sel]) if int(sd) not in cache]
             if new:
                 # snapshots exported from the reference with exactly these options (entry i <-> scene_seed i)
-                shipped = None if authored is not None else shipped_pool_for(options)
+                shipped = None if authored is not None else shipped_pool_for(options, self.env_cfg.max_vehicles)
                 ready = {}
                 if shipped is not None:
                     pool = self._shipped_scenes(shipped)

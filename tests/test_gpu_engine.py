@@ -202,7 +202,9 @@ def test_vector_env_surface_and_infos():
     assert len(set(envs._scene_of_env.tolist())) == 1            # options["scene_seed"]: the same scene for every env
     obs, _ = envs.reset(seed=40, options={"scene": "lead_brake", "level": 1})
     assert len(set(envs._scene_of_env.tolist())) == 6            # reset(seed=s): env i is seeded s + i
-    obs, _ = envs.reset(seed=3, options={"scene": "rdm", "difficulty_id": "rt_medium_v1"})
+    from carlabev_env_b200 import reset as R
+
+    obs, _ = envs.reset(seed=3, options=R.build_reset_options(R.RandomNavigationReset(difficulty_id="rt_medium_v1")))
     assert len(set(envs._scene_of_env.tolist())) == 6
     # seeds outside the shipped snapshots are generated on the host (lane graphs + shortest paths, scenes.py)
     obs, _ = envs.reset(seed=1000, options={"scene": "rdm", "num_vehicles": 3, "route_dist_range": [30, 60]})
@@ -215,8 +217,6 @@ def test_vector_env_surface_and_infos():
     obs, _ = envs.reset(seed=20, options={"scene": "rdm", "num_vehicles": 2, "route_profile": "single_left",
                                           "route_dist_range": [30, 130]})
     # authored scene file (bundled, addressed by name) and a typed preset request (config/reset.py mirror)
-    from carlabev_env_b200 import reset as R
-
     obs, _ = envs.reset(options=R.build_reset_options(R.AuthoredSceneReset("redlightrunner-01.01.json", True, 2)))
     assert len(envs._scenes[envs._scene_of_env[0]]["tl_color"]) >= 2
     envs.step(np.zeros((6, 3), np.float32))

@@ -111,6 +111,12 @@ def test_shipped_pools_load_and_validate():
             assert np.all(np.diff(kinds.astype(int)) >= 0)            # vehicles precede pedestrians
             assert s["act_route_off"][-1] == len(s["act_cx"])
     assert shipped_pool_for({"scene": "rdm", "num_vehicles": 3}) is None
+    # a bare difficulty_id does not change what the reference generates (50 vehicles, 30-100 m): no snapshot applies
+    assert shipped_pool_for({"scene": "rdm", "difficulty_id": "rt_hard_v1"}) is None
+    assert shipped_pool_for({"scene": "rdm", "num_vehicles": 25, "route_dist_range": [50, 130]}) == "rdm_rt_hard_v1"
+    assert shipped_pool_for({"scene": "rdm", "num_vehicles": 25, "route_dist_range": [50, 130],
+                             "ego_route_graph": "left_lane"}) is None
+    assert shipped_pool_for({"scene": "red_light_runner", "intersection_index": 11}) is None
 
 
 def test_pool_pack_roundtrip():
@@ -277,15 +283,18 @@ def test_red_light_generation_matches_reference_snapshots():
 def test_build_pool_workers_and_option_errors():
     from carlabev_env_b200 import scenes as S
 
-    reqs = [{"scene": "rdm", "difficulty_id": "rt_easy_v1", "scene_seed": i} for i in range(3)]
+    from carlabev_env_b200.reset import RandomNavigationReset, build_reset_options
+
+    reqs = [build_reset_options(RandomNavigationReset(difficulty_id="rt_easy_v1", scene_seed=i)) for i in range(3)]
     reqs += [{"scene": "lead_brake", "level": 2, "scene_seed": 5}, {"scene": "jaywalk", "scene_seed": 6}]
     serial = S.build_pool(reqs, workers=1)
     assert [int(s["kind"]) for s in serial] == [0, 0, 0, 1, 2]
     assert all(int(s["num_vehicles"]) <= 8 for s in serial[:3])
     again = S.build_pool(reqs, workers=1)
     assert all(_same_scene(a, b) == [] for a, b in zip(serial, again))
-    with pytest.raises(KeyError):
-        S.build_scene({"scene": "rdm", "difficulty_id": "nope"})
+    # a bare difficulty_id in raw options is context metadata, exactly as in the reference: defaults apply
+    raw = S.build_scene({"scene": "rdm", "difficulty_id": "rt_easy_v1", "scene_seed": 3, "num_vehicles": 2})
+    assert len(raw["act_kind"]) <= 2
     with pytest.raises(RuntimeError):   # a profile no route can have: the search gives up like the reference's
         S.build_scene({"scene": "rdm", "route_profile": "left_turn", "max_route_attempts": 1})
     with pytest.raises(ValueError):
@@ -298,7 +307,7 @@ def test_build_pool_workers_and_option_errors():
         S.build_scene({"scene": "rdm", "ego_route_graph": "sidewalk"})
     with pytest.raises(KeyError):
         S.build_scene({"scene": "no_such_scene"})
-    no_traffic = S.build_scene({"scene": "rdm", "difficulty_id": "rt_no_traffic_v1", "scene_seed": 3})
+    no_traffic = S.build_scene(build_reset_options(RandomNavigationReset(difficulty_id="rt_no_traffic_v1", scene_seed=3)))
     assert len(no_traffic["act_kind"]) == 0 and 30.0 <= float(no_traffic["len_ego_route"]) <= 80.0
 
 
@@ -306,7 +315,7 @@ def test_build_pool_parallel_equals_serial():
     from carlabev_env_b200 import scenes as S
 
     reqs = [{"scene": "lead_brake", "level": 1 + i % 3, "scene_seed": i} for i in range(60)]
-    reqs += [{"scene": "rdm", "difficulty_id": "rt_easy_v1", "scene_seed": i} for i in range(4)]
+    reqs += [{"scene": "rdm", "num_vehicles": 8, "route_dist_range": [30, 80], "scene_seed": i} for i in range(4)]
     serial = S.build_pool(reqs, workers=1)
     parallel = S.build_pool(reqs, workers=2)
     assert all(_same_scene(a, b) == [] for a, b in zip(serial, parallel))
@@ -394,7 +403,8 @@ def test_typed_reset_requests():
         R.build_reset_options(R.RandomNavigationReset(difficulty_id="nope"))
     # the dicts feed the host generator unchanged
     s1 = S.build_scene({k: v for k, v in o.items() if k != "reset_mask"}, cls_map=load_map())
-    s2 = S.build_scene({"scene": "rdm", "difficulty_id": "rt_hard_v1", "scene_seed": 5}, cls_map=load_map())
+    s2 = S.build_scene({"scene": "rdm", "num_vehicles": 25, "route_dist_range": [50, 130], "scene_seed": 5},
+                       cls_map=load_map())
     assert _same_scene(s1, s2) == []
     s3 = S.build_scene({**c, "scene_seed": 2})
     assert float(s3["ego_state0"][3]) == pytest.approx(9.0 / (40.0 / 128.0))
