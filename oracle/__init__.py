@@ -12,7 +12,9 @@ Parity status
   episode statistics and the mask / frame-stack wrappers are PINNED: the
   restatement is checked bit-for-bit (float64 equality on this CPU) against golden
   trajectories produced by the UNMODIFIED reference modules stepped in the build
-  container (oracle/gen_golden.py; fixtures in tests/golden/).
+  container (oracle/gen_golden.py; fixtures in tests/golden/), and fuzzed in lock-step
+  with the reference under random configurations, reset options and actions
+  (oracle/fuzz_steps.py, oracle/fuzz_scenes.py; results in DESIGN.md section 2).
 * The reference renders with pygame 2.6.1 and wraps with gymnasium 1.2.2, neither
   installed here.  The golden run therefore sits on oracle/shims (a restatement of
   those third-party libraries).  Raster values (transform.rotate sampling, rect
