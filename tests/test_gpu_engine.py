@@ -722,3 +722,75 @@ def test_sharded_vector_env_equals_the_slice_of_the_full_one():
     full.close()
     with pytest.raises(ValueError):
         make_env(cfg, shard=(0, 4))
+
+
+@pytest.mark.parametrize("seed", [3, 6, 27, 30])
+def test_random_configurations_against_the_oracle(seed):
+    """Random env configuration (action profile, reward mode, mask channels, camera anchor, fov mask, gray /
+    semantic), host-generated scenes of every kind and random actions: engine == oracle on observations, rewards,
+    flags and poses.  The same generator drives oracle/fuzz_steps.py against the unmodified reference."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.config import ACTION_PROFILES
+    from carlabev_env_b200.fovmask import corner_mask
+    from carlabev_env_b200.pool import pack_pool
+    from oracle.env import OracleEnv
+
+    rng = np.random.default_rng(seed)
+    cls = load_map()
+    profile = str(rng.choice(["continuous_gsb_v1", "discrete9_v1", "discrete13_v1"]))
+    continuous = profile == "continuous_gsb_v1"
+    reward = "shaping" if rng.random() < 0.4 else "carl"
+    mask = str(rng.choice(["6-class", "7-class", "5-class", "4-class", "binary"]))
+    anchor = (0.5, 0.75) if rng.random() < 0.4 else (0.5, 0.5)
+    fov_masked = bool(rng.random() < 0.4)
+    gray = bool(rng.random() < 0.3)
+    pad = 230 if anchor[1] == 0.75 else 182
+    reqs = [dict(scene="rdm", num_vehicles=int(rng.integers(0, 9)), route_dist_range=[30, 90], scene_seed=int(rng.integers(0, 10**6)))
+            for _ in range(5)]
+    reqs += [dict(scene="lead_brake", level=int(rng.integers(1, 4)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
+    reqs += [dict(scene="jaywalk", level=int(rng.integers(1, 5)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
+    reqs += [dict(scene="red_light_runner", scene_seed=int(rng.integers(0, 10**6)))]
+    scenes = [S.build_scene(r, cls_map=cls, pad=pad) for r in reqs]
+    n = len(scenes)
+    eng = E.Engine(n, obs_mode=E.OBS_GRAY if gray else E.OBS_SEMANTIC, mask_mode=mask, frame_stack=4,
+                   action_mode=E.ACTION_CONTINUOUS if continuous else E.ACTION_DISCRETE,
+                   discrete_table=ACTION_PROFILES[profile].get("discrete_actions"),
+                   reward_mode=E.REWARD_SHAPING if reward == "shaping" else E.REWARD_CARL, anchor=anchor, max_actors=12,
+                   ring_budget_bytes=64 << 20)
+    eng.upload_map(cls)
+    eng.upload_pool(pack_pool(scenes))
+    if fov_masked:
+        eng.upload_fov_mask(corner_mask(128, 0.5))
+    oracles = [OracleEnv(cls, obs_mode="bev_gray" if gray else "bev_semantic", semantic_mask_ch=mask,
+                         action_mode="continuous" if continuous else "discrete", action_profile=profile,
+                         reward_mode=reward, anchor=anchor, fov_masked=fov_masked) for _ in range(n)]
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i])), (i, "reset")
+    alive = np.ones(n, bool)
+    n_act = len(ACTION_PROFILES[profile].get("discrete_actions") or [])
+    for t in range(40):
+        if continuous:
+            a = _rand_actions(rng, n)
+            a[:, 2] *= rng.random(n) < 0.2
+            dev_a = torch.from_numpy(a).cuda()
+        else:
+            a = rng.integers(0, n_act, n)
+            dev_a = torch.from_numpy(a).cuda()
+        eng.step(dev_a)
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, trunc = eng.terminated.cpu().numpy().astype(bool), eng.truncated.cpu().numpy().astype(bool)
+        hero = eng.hero.cpu().numpy()
+        for i in range(n):
+            if not alive[i]:
+                continue
+            o, r, te, tr, _ = oracles[i].step(a[i] if continuous else int(a[i]))
+            e = oracles[i].sim.ego
+            assert np.array_equal(obs[i], o), (t, i, reqs[i], "observation")
+            assert abs(r - rew[i]) < 1e-9 and te == term[i] and tr == trunc[i], (t, i, reqs[i], r, rew[i])
+            assert np.allclose(hero[i, :4], [e.x, e.y, e.yaw, e.v], rtol=1e-9, atol=1e-9), (t, i, "pose")
+            alive[i] = not (te or tr)
+    eng.close()
