@@ -892,22 +892,47 @@ def _build_chunk(args):
 
 def build_pool(requests: list[dict], pad: int = 182, max_vehicles: int = 50, workers: int | None = None) -> list[dict]:
     """Reset-option dicts -> pool entries, on `workers` host processes (default: one per core, serial for small
-    pools).  Scene generation is host work by design (the device steps scenes, it does not build them)."""
+    pools).  Scene generation is host work by design (the device steps scenes, it does not build them).
+
+    The workers are plain child interpreters running this module (`python -m carlabev_env_b200.scenes --worker`),
+    fed and read through files: nothing of the caller's `__main__` is re-imported, so this is safe to call from any
+    script (no `if __name__ == "__main__"` guard needed) and from a process that already holds a CUDA context."""
     import os
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
 
     n = len(requests)
     workers = min(os.cpu_count() or 1, 32) if workers is None else workers
-    if workers <= 1 or n < 64:
+    workers = min(workers, max(1, n // 16))
+    if workers <= 1:
         return _build_chunk((requests, pad, max_vehicles))
-    import multiprocessing as mp
-
     chunks = [list(range(w, n, workers)) for w in range(workers)]
-    with mp.get_context("spawn").Pool(workers) as pool:
-        parts = pool.map(_build_chunk, [([requests[i] for i in c], pad, max_vehicles) for c in chunks])
+    pkg_parent = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = pkg_parent + os.pathsep + env.get("PYTHONPATH", "")
+    env.setdefault("OMP_NUM_THREADS", "1")  # one core per worker: the routes are tiny, BLAS threads only collide
     out = [None] * n
-    for c, part in zip(chunks, parts):
-        for i, sc in zip(c, part):
-            out[i] = sc
+    with tempfile.TemporaryDirectory(prefix="cbev_pool_") as tmp:
+        procs = []
+        for w, c in enumerate(chunks):
+            req, res = os.path.join(tmp, f"req{w}.pkl"), os.path.join(tmp, f"res{w}.pkl")
+            with open(req, "wb") as f:
+                pickle.dump(([requests[i] for i in c], pad, max_vehicles), f)
+            procs.append((c, res, subprocess.Popen([sys.executable, "-m", "carlabev_env_b200.scenes", "--worker", req, res],
+                                                   env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)))
+        errors = []
+        for c, res, p in procs:
+            _, err = p.communicate()
+            if p.returncode != 0:
+                errors.append(err.decode(errors="replace")[-800:])
+                continue
+            with open(res, "rb") as f:
+                for i, sc in zip(c, pickle.load(f)):
+                    out[i] = sc
+        if errors:
+            raise RuntimeError("scene generation worker failed:\n" + errors[0])
     return out
 
 
@@ -937,10 +962,19 @@ def _main(argv=None):
     """python -m carlabev_env_b200.scenes --scene rdm --difficulty-id rt_hard_v1 --count 4096 --out pool.npz"""
     import argparse
     import json
+    import sys
     import time
 
     from .pool import save_pool
 
+    if argv is None and len(sys.argv) == 4 and sys.argv[1] == "--worker":  # child of build_pool: chunk in, scenes out
+        import pickle
+
+        with open(sys.argv[2], "rb") as f:
+            args = pickle.load(f)
+        with open(sys.argv[3], "wb") as f:
+            pickle.dump(_build_chunk(args), f)
+        return
     ap = argparse.ArgumentParser(description="Generate a scene pool on the host cores (entry i has scene_seed = seed0 + i).")
     ap.add_argument("--scene", default="rdm", help="rdm | lead_brake | jaywalk | red_light_runner | path to an authored / scenario-config JSON")
     ap.add_argument("--count", type=int, default=256)
