@@ -408,3 +408,48 @@ def test_typed_reset_requests():
     assert _same_scene(s1, s2) == []
     s3 = S.build_scene({**c, "scene_seed": 2})
     assert float(s3["ego_state0"][3]) == pytest.approx(9.0 / (40.0 / 128.0))
+
+
+def test_rdm_seed_contracts_like_the_reference_suite():
+    """The contracts of the reference's tests/test_seeded_scene_consistency.py:100-184 on the host generator:
+    same seed -> identical spawn state; the camera anchor does not move the world spawn; a seed sequence replays;
+    route_seed changes the ego route but not the traffic, traffic_seed the traffic but not the route."""
+    from carlabev_env_b200 import scenes as S
+
+    cls = load_map()
+
+    def spawn(seed, pad=182, **kw):
+        s = S.build_scene({"scene": "rdm", "num_vehicles": 6, "route_dist_range": [30, 100], "scene_seed": seed, **kw},
+                          cls_map=cls, pad=pad)
+        return dict(hero=s["ego_state0"].tolist(), route=(s["ego_cx"][:16].tolist(), s["ego_cy"][:16].tolist()),
+                    vehicles=s["act_state0"][:16].tolist(), n=int(s["num_vehicles"]))
+
+    assert spawn(11) == spawn(11)
+    centre, lookahead = spawn(11, pad=182), spawn(11, pad=230)
+    assert centre == lookahead
+    assert [spawn(sd) for sd in (101, 102, 103)] == [spawn(sd) for sd in (101, 102, 103)]
+    a, b = spawn(11, route_seed=1001, traffic_seed=2001), spawn(11, route_seed=1002, traffic_seed=2001)
+    assert a["route"] != b["route"] and a["vehicles"] == b["vehicles"]
+    a, b = spawn(11, route_seed=3001, traffic_seed=4001), spawn(11, route_seed=3001, traffic_seed=4002)
+    assert a["route"] == b["route"] and a["vehicles"] != b["vehicles"]
+
+
+def test_route_profile_contracts_like_the_reference_suite():
+    """tests/test_route_profile.py of the reference, on the host restatement."""
+    from carlabev_env_b200 import reset as R
+    from carlabev_env_b200 import scenes as S
+
+    o = R.build_random_navigation_options(R.RandomNavigationReset(
+        difficulty_id="rt_medium_v1", route_profile="single_left",
+        route_profile_mix={"mostly_straight": 0.5, "single_left": 0.5}, min_turns=1, max_turns=2,
+        intersection_required=True))
+    assert o["ego_route_graph"] == "full_vehicle" and o["route_profile"] == "single_left"
+    assert o["route_profile_mix"] == {"mostly_straight": 0.5, "single_left": 0.5}
+    assert o["min_turns"] == 1 and o["max_turns"] == 2 and o["intersection_required"] is True
+    m = S.route_profile_metrics([0, 10, 20, 30, 40, 50], [0, 0, 0, 0, 0, 0])
+    assert m["route_profile"] == "mostly_straight" and m["turn_count"] == 0 and m["straight_fraction"] > 0.99
+    assert S.matches_route_profile(m, route_profile="mostly_straight")
+    assert not S.matches_route_profile(m, route_profile="single_left")
+    m = S.route_profile_metrics([0, 10, 20, 20, 20, 30, 40], [0, 0, 0, 10, 20, 20, 20])
+    assert m["turn_count"] >= 1 and m["route_profile"] in {"single_left", "multi_turn", "mixed"}
+    assert S.matches_route_profile(m, min_turns=1)
