@@ -80,6 +80,44 @@ def get_difficulty_spec(difficulty_id: str) -> dict:
                        f"{', '.join(sorted(DIFFICULTY_PRESETS))}") from exc
 
 
+def list_action_profile_ids() -> list:
+    return sorted(ACTION_PROFILES)
+
+
+def list_reward_profile_ids() -> list:
+    return sorted(REWARD_PROFILES)
+
+
+def list_difficulty_ids() -> list:
+    return sorted(DIFFICULTY_PRESETS)
+
+
+def get_env_capabilities() -> dict:
+    """config/env.py:328-355: what this implementation of the environment accepts (one map scale: Town01 at
+    size 128; `vector` observations are reachable through `CarlaBEVVectorEnv.vector_observation()`, not make_env)."""
+    from .scenes import SCENARIO_PRESETS, _SPEC_DEFAULTS
+
+    masks = ["binary", "2-class", "4-class", "5-class", "6-class", "7-class"]
+    fusion = ["stack", "vehicle_temporal", "vehicle_weighted"]
+    return {
+        "maps": ["Town01"], "obs_modes": ["bev_rgb", "bev_semantic", "vector"],
+        "semantic_mask_channels": masks, "semantic_mask_ch": masks,
+        "temporal_fusion_modes": fusion, "temporal_fusion_mode": fusion,
+        "action_modes": ["discrete", "continuous"], "action_profile_ids": list_action_profile_ids(),
+        "reward_modes": ["shaping", "carl"], "reward_profile_ids": list_reward_profile_ids(),
+        "difficulty_ids": list_difficulty_ids(), "render_modes": ["rgb_array"],
+        "supports_vector_make_env": False, "scenario_ids": list(_SPEC_DEFAULTS),
+        "scenario_preset_ids": list(SCENARIO_PRESETS),
+    }
+
+
+def resolve_env_profiles(env_cfg) -> dict:
+    """config/env.py:318-325."""
+    cfg = validate_env_config(env_cfg)
+    return {"action": get_action_profile_spec(cfg.action_profile_id),
+            "reward": get_reward_profile_spec(cfg.reward_profile_id)}
+
+
 @dataclass
 class EnvConfig:
     """config/env.py:43-74 (same names and defaults)."""

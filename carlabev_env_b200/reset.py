@@ -107,6 +107,27 @@ def build_scenario_config_options(request: ScenarioConfigReset, *, reset_mask=No
     return _with_mask(options, reset_mask)
 
 
+def build_scenario_options_from_config(config: dict, *, overrides: dict | None = None, reset_mask=None) -> dict[str, Any]:
+    """config/reset.py:161-172 -> scenarios/specs.py:248-272: a loaded scenario config + overrides -> options
+    (only the keys the config carries; scenes.scenario_config_options is the file loader that also fills defaults)."""
+    overrides = dict(overrides or {})
+    if reset_mask is None and "reset_mask" in overrides:
+        reset_mask = overrides.pop("reset_mask")
+    options = dict(config.get("parameters", {}))
+    anchor = config.get("anchor", {}) or {}
+    if anchor.get("x") is not None:
+        options["anchor_x"] = anchor["x"]
+    if anchor.get("y") is not None:
+        options["anchor_y"] = anchor["y"]
+    options["level"] = int(config.get("level", 1))
+    options["scene"] = config["scenario_id"]
+    for key, value in overrides.items():
+        if key in ("config_file", "scene", "reset_mask") or value is None:
+            continue
+        options[key] = value
+    return _with_mask(options, reset_mask)
+
+
 def build_reset_options(request, *, reset_mask=None) -> dict[str, Any]:
     if isinstance(request, RandomNavigationReset):
         return build_random_navigation_options(request, reset_mask=reset_mask)

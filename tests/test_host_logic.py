@@ -453,3 +453,48 @@ def test_route_profile_contracts_like_the_reference_suite():
     m = S.route_profile_metrics([0, 10, 20, 20, 20, 30, 40], [0, 0, 0, 10, 20, 20, 20])
     assert m["turn_count"] >= 1 and m["route_profile"] in {"single_left", "multi_turn", "mixed"}
     assert S.matches_route_profile(m, min_turns=1)
+
+
+def test_public_config_contract_like_the_reference_suite():
+    """The reference's tests/test_public_config.py (capabilities, profile resolution, reset builders), importing the
+    same names from the package root."""
+    import carlabev_env_b200 as P
+
+    assert P.__version__ == "0.1.0"
+    cap = P.get_env_capabilities()
+    for key, member in (("maps", "Town01"), ("action_modes", "discrete"), ("action_profile_ids", "discrete9_v1"),
+                        ("difficulty_ids", "rt_no_traffic_v1"), ("obs_modes", "bev_semantic"), ("reward_modes", "carl"),
+                        ("reward_profile_ids", "carl_base_v1"), ("scenario_ids", "jaywalk"),
+                        ("scenario_preset_ids", "jaywalk_debug")):
+        assert member in cap[key], key
+    assert cap["supports_vector_make_env"] is False
+    res = P.resolve_env_profiles(P.EnvConfig(action_profile_id="discrete13_v1", action_mode="discrete",
+                                             reward_profile_id="carl_safety_v1", reward_mode="carl"))
+    assert res["action"]["action_profile_id"] == "discrete13_v1" and res["reward"]["reward_profile_id"] == "carl_safety_v1"
+    assert P.get_difficulty_spec("rt_medium_v1")["num_vehicles"] == 16
+    assert P.get_action_profile_spec("discrete9_v1")["action_mode"] == "discrete"
+    assert P.get_reward_profile_spec("carl_base_v1")["family"] == "carl"
+    o = P.build_random_navigation_options(P.RandomNavigationReset(num_vehicles=7, route_dist_range=(40, 80)),
+                                          reset_mask=[True, False, True])
+    assert o["scene"] == "rdm" and o["num_vehicles"] == 7 and o["route_dist_range"] == [40, 80]
+    assert o["reset_mask"].tolist() == [True, False, True]
+    o = P.build_random_navigation_options(P.RandomNavigationReset(difficulty_id="rt_no_traffic_v1"))
+    assert (o["difficulty_id"], o["num_vehicles"], o["traffic_enabled"], o["route_dist_range"]) == \
+        ("rt_no_traffic_v1", 0, False, [30, 80])
+    o = P.build_random_navigation_options(P.RandomNavigationReset(num_vehicles=7, route_dist_range=(40, 80), scene_seed=11,
+                                                                  route_seed=22, traffic_seed=33, scenario_seed=44))
+    assert (o["scene_seed"], o["route_seed"], o["traffic_seed"], o["scenario_seed"]) == (11, 22, 33, 44)
+    o = P.build_authored_scene_options(P.AuthoredSceneReset("assets/scenes/jaywalk-01.01.json", True, 123))
+    assert o["config_file"].endswith("jaywalk-01.01.json") and o["variation_enabled"] and o["variation_seed"] == 123
+    o = P.build_scenario_preset_options(P.ScenarioPresetReset("jaywalk_debug", {"anchor_x": 11, "anchor_y": 13}))
+    assert (o["scene"], o["anchor_x"], o["anchor_y"]) == ("jaywalk", 11, 13)
+    o = P.build_scenario_config_options(P.ScenarioConfigReset("lead_brake", level=2, parameters={"ego_speed": 5.0}),
+                                        reset_mask=[False, True])
+    assert (o["scene"], o["level"], o["ego_speed"]) == ("lead_brake", 2, 5.0) and o["reset_mask"].tolist() == [False, True]
+    o = P.build_scenario_options_from_config(
+        {"scenario_id": "jaywalk", "level": 2, "anchor": {"x": 10, "y": 12}, "parameters": {"ego_speed": 8.0}},
+        overrides={"cross_delay": 1.5, "anchor_x": 14, "reset_mask": [True]})
+    assert (o["scene"], o["level"], o["anchor_x"], o["anchor_y"], o["ego_speed"], o["cross_delay"]) == \
+        ("jaywalk", 2, 14, 12, 8.0, 1.5) and o["reset_mask"].tolist() == [True]
+    with pytest.raises(ValueError, match="obs_mode='vector'"):
+        P.validate_run_config({"env": {"map_name": "Town01", "obs_mode": "vector", "render_mode": "rgb_array"}})
