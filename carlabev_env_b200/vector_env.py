@@ -247,8 +247,35 @@ class CarlaBEVVectorEnv:
             self._scene_of_env[m] = ids[m]
         if self.recorder is not None and (m is None or m[0]):
             self.recorder.on_reset(self.engine.fov()[0].cpu().numpy())
-        infos = {}
+        infos = self._reset_infos(np.ones(self.num_envs, bool) if m is None else m) if self.host_infos else {}
         return self._out_obs(obs), infos
+
+    def _reset_infos(self, mask):
+        """CarlaBEV.reset's info (carlabev.py:145-148) batched the way gymnasium's vector envs do (`key` array +
+        `_key` mask, nested dicts recursively): the scenario context that is a property of the scene (kind, level,
+        seed, route length, traffic count) and the spawn validation, which every pool entry has passed."""
+        from .pool import SCENE_KINDS
+
+        n = self.num_envs
+        idx = np.flatnonzero(mask)
+        sc = [self._scenes[int(self._scene_of_env[i])] for i in idx]
+
+        def col(values, dtype):
+            a = np.full(n, None, dtype=object) if dtype is object else np.zeros(n, dtype=dtype)
+            a[idx] = values
+            return a
+
+        scenario = {
+            "scene": col([SCENE_KINDS[int(s["kind"])] if 0 <= int(s["kind"]) < len(SCENE_KINDS) else "rdm" for s in sc], object),
+            "level": col([int(s["level"]) for s in sc], np.int64),
+            "scene_seed": col([int(s["seed"]) for s in sc], np.int64),
+            "route_length_m": col([float(s["len_ego_route"]) for s in sc], np.float64),
+            "scenario_param_num_vehicles": col([int(s["num_vehicles"]) for s in sc], np.int64),
+        }
+        scenario.update({f"_{k}": mask.copy() for k in list(scenario)})
+        spawn = {"valid": col([True] * len(idx), np.bool_), "reason": col(["ok"] * len(idx), object)}
+        spawn.update({f"_{k}": mask.copy() for k in list(spawn)})
+        return {"scenario": scenario, "_scenario": mask.copy(), "spawn_validation": spawn, "_spawn_validation": mask.copy()}
 
     def step(self, actions):
         t = self.torch

@@ -171,7 +171,8 @@ def test_vector_env_surface_and_infos():
     assert envs.num_envs == 6 and envs.single_observation_space.shape == (24, 96, 96)
     assert envs.single_action_space.shape == (3,)
     obs, infos = envs.reset(options={"scene_ids": np.arange(6)})
-    assert obs.shape == (6, 24, 96, 96) and obs.dtype == torch.float32 and infos == {}
+    assert obs.shape == (6, 24, 96, 96) and obs.dtype == torch.float32
+    assert infos["scenario"]["scene"].tolist() == ["lead_brake"] * 6 and infos["_spawn_validation"].all()
     with pytest.raises(AssertionError):
         envs.reset(options={"reset_mask": np.zeros(6, bool)})
     finished = None
@@ -197,8 +198,11 @@ def test_vector_env_surface_and_infos():
     obs, _ = envs.reset(options={"scene_ids": np.arange(6), "reset_mask": finished})
     envs.step(np.zeros((6, 3), np.float32))
     # scripted scene built on the host at reset time, like the reference's reset(options={"scene": ...})
-    obs, _ = envs.reset(options={"scene": "jaywalk", "level": 3, "scene_seed": 11})
+    obs, rinfo = envs.reset(options={"scene": "jaywalk", "level": 3, "scene_seed": 11})
     assert obs.shape == (6, 24, 96, 96)
+    assert rinfo["scenario"]["scene"].tolist() == ["jaywalk"] * 6 and rinfo["scenario"]["level"].tolist() == [3] * 6
+    assert rinfo["scenario"]["scene_seed"].tolist() == [11] * 6 and rinfo["_scenario"].all()
+    assert rinfo["spawn_validation"]["valid"].all() and rinfo["spawn_validation"]["reason"][0] == "ok"
     assert len(set(envs._scene_of_env.tolist())) == 1            # options["scene_seed"]: the same scene for every env
     obs, _ = envs.reset(seed=40, options={"scene": "lead_brake", "level": 1})
     assert len(set(envs._scene_of_env.tolist())) == 6            # reset(seed=s): env i is seeded s + i
