@@ -42,6 +42,12 @@ def random_env(rng):
         kw["fov_masked"] = True
     if rng.random() < 0.2:
         kw["obs_mode"] = "bev_rgb"
+    elif rng.random() < 0.3 and kw["semantic_mask_ch"] != "binary":
+        kw["temporal_fusion_mode"] = str(rng.choice(["vehicle_temporal", "vehicle_weighted"]))
+    if rng.random() < 0.3:
+        kw["frame_stack"] = int(rng.choice([3, 5, 6]))
+    if rng.random() < 0.3:
+        kw["obs_size"] = tuple(int(v) for v in rng.choice([(84, 84), (64, 64), (128, 128), (112, 100), (48, 64)]))
     return kw
 
 
@@ -70,7 +76,8 @@ def main():
                         action_profile=kw.get("action_profile_id") or ("continuous_gsb_v1" if am == "continuous" else "discrete9_v1"),
                         reward_mode=kw.get("reward_mode", "carl"),
                         anchor=(kw.get("ego_anchor_x_frac", 0.5), kw.get("ego_anchor_y_frac", 0.5)),
-                        fov_masked=kw.get("fov_masked", False))
+                        fov_masked=kw.get("fov_masked", False), frame_stack=kw.get("frame_stack", 4),
+                        obs_size=kw.get("obs_size", (96, 96)), temporal_fusion_mode=kw.get("temporal_fusion_mode", "stack"))
         o0 = ora.reset(scene)
         what = None
         if not np.array_equal(np.asarray(obs[0]), o0):
