@@ -991,8 +991,11 @@ def _main(argv=None):
         base["config_file"] = a.scene
     else:
         base["scene"] = a.scene
-    if a.difficulty_id is not None:
-        base["difficulty_id"] = a.difficulty_id
+    if a.difficulty_id is not None:  # expanded like the typed request does (a bare difficulty_id is metadata only)
+        from .reset import RandomNavigationReset, build_random_navigation_options
+
+        preset = build_random_navigation_options(RandomNavigationReset(difficulty_id=a.difficulty_id))
+        base = {**preset, **base}
     if a.level is not None:
         base["level"] = a.level
     t0 = time.time()
