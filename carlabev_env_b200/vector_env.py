@@ -24,6 +24,7 @@ Differences that follow from the design:
 from __future__ import annotations
 
 import os
+import time
 
 import numpy as np
 
@@ -124,6 +125,7 @@ class CarlaBEVVectorEnv:
         self._scene_of_env = np.zeros(self.num_envs, dtype=np.int64)
         self.current_hero = None
         self._generated, self._shipped_lists = {}, {}
+        self._episode_t0 = np.full(self.num_envs, time.perf_counter())
         self.recorder, self._rec_pending_reset = None, False
         if getattr(cfg, "capture_video", False) and self.env_offset == 0:  # global env 0 only (envs/__init__.py:93-100)
             from .recorder import FrameRecorder
@@ -242,9 +244,11 @@ class CarlaBEVVectorEnv:
         if m is None:
             self._needs_reset[:] = False
             self._scene_of_env[:] = ids
+            self._episode_t0[:] = time.perf_counter()
         else:
             self._needs_reset[m] = False
             self._scene_of_env[m] = ids[m]
+            self._episode_t0[m] = time.perf_counter()
         if self.recorder is not None and (m is None or m[0]):
             self.recorder.on_reset(self.engine.fov()[0].cpu().numpy())
         infos = self._reset_infos(np.ones(self.num_envs, bool) if m is None else m) if self.host_infos else {}
@@ -331,10 +335,14 @@ class CarlaBEVVectorEnv:
             episode_info[f"_{name}"] = mask
         r = np.zeros(n)
         ln = np.zeros(n, dtype=np.int64)
+        tm = np.zeros(n)
         r[idx] = ep[:, E.EPISODE_FIELDS.index("return")]
         ln[idx] = ep[:, E.EPISODE_FIELDS.index("length")]
+        now = time.perf_counter()  # RecordEpisodeStatistics' `t`: wall-clock seconds since the episode began
+        tm[idx] = np.round(now - self._episode_t0[idx], 6)
+        self._episode_t0[idx] = now   # device auto-reset: the next episode of these envs starts now
         return {"episode_info": episode_info, "_episode_info": mask,
-                "episode": {"r": r, "_r": mask, "l": ln, "_l": mask}, "_episode": mask}
+                "episode": {"r": r, "_r": mask, "l": ln, "_l": mask, "t": tm, "_t": mask}, "_episode": mask}
 
     def _record_step(self, done0):
         rec = self.recorder
