@@ -498,3 +498,82 @@ def test_public_config_contract_like_the_reference_suite():
         ("jaywalk", 2, 14, 12, 8.0, 1.5) and o["reset_mask"].tolist() == [True]
     with pytest.raises(ValueError, match="obs_mode='vector'"):
         P.validate_run_config({"env": {"map_name": "Town01", "obs_mode": "vector", "render_mode": "rgb_array"}})
+
+
+def test_vector_env_host_logic_with_a_stub_engine(monkeypatch):
+    """The Python side of CarlaBEVVectorEnv (option resolution, per-env seeds, masked resets, the disabled-autoreset
+    contract, reset / terminal infos) driven end to end on the CPU with the CUDA engine replaced by a stub -- the
+    kernels themselves are covered by the `-m gpu` tests."""
+    import types
+
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200 import vector_env as V
+    from carlabev_env_b200.config import EnvConfig, RunConfig
+
+    class StubEngine:
+        def __init__(self, n, **kw):
+            self.N, self.device, self.head = n, torch.device("cpu"), -1
+            self.cfg = types.SimpleNamespace(max_actors=kw.get("max_actors", 52))
+            self.reward = torch.zeros(n, dtype=torch.float64)
+            self.terminated = torch.zeros(n, dtype=torch.uint8)
+            self.truncated = torch.zeros(n, dtype=torch.uint8)
+            self.cause = torch.zeros(n, dtype=torch.uint8)
+            self.hero = torch.zeros(n, 32, dtype=torch.float64)
+            self.episode = torch.zeros(n, len(E.EPISODE_FIELDS), dtype=torch.float64)
+            self.t, self.pools, self.resets = 0, [], []
+
+        def upload_map(self, m): pass
+        def upload_pool(self, p): self.pools.append(int(p["n_scenes"]))
+        def close(self): pass
+        def obs(self): return torch.zeros(self.N, 24, 96, 96)
+
+        def reset(self, ids, mask=None):
+            self.head = 3
+            self.resets.append((np.asarray(ids).copy(), None if mask is None else np.asarray(mask).copy()))
+            return self.obs()
+
+        def step(self, a):
+            self.t += 1
+            self.terminated[:] = 0
+            if self.t == 3:
+                self.terminated[1] = 1
+                self.episode[1, E.EPISODE_FIELDS.index("length")] = 3
+                self.episode[1, E.EPISODE_FIELDS.index("return")] = 1.25
+                self.episode[1, E.EPISODE_FIELDS.index("cause")] = 2
+
+    monkeypatch.setattr(E, "Engine", StubEngine)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(synchronize=lambda: None))
+    envs = V.make_env(RunConfig(env=EnvConfig(action_mode="continuous"), num_envs=4))
+    with pytest.raises(RuntimeError):   # nothing to reset from yet
+        envs.reset()
+    obs, info = envs.reset(seed=7, options={"scene": "lead_brake", "level": 2})
+    assert obs.shape == (4, 24, 96, 96)
+    assert info["scenario"]["scene_seed"].tolist() == [7, 8, 9, 10] and info["_scenario"].all()   # env i seeded s + i
+    assert info["scenario"]["scene"].tolist() == ["lead_brake"] * 4 and info["spawn_validation"]["valid"].all()
+    assert envs.engine.pools[-1] == 4
+    for _ in range(3):
+        _, rew, term, trunc, inf = envs.step(np.zeros((4, 3), np.float32))
+    assert term.tolist() == [False, True, False, False] and inf["_episode"].tolist() == [False, True, False, False]
+    assert inf["episode"]["l"].tolist() == [0, 3, 0, 0] and inf["episode"]["r"][1] == 1.25 and inf["episode"]["t"][1] > 0
+    assert inf["episode_info"]["termination"][1] == "collision"
+    with pytest.raises(AssertionError):   # AutoresetMode.DISABLED: a finished env must be reset before the next step
+        envs.step(np.zeros((4, 3), np.float32))
+    mask = np.array([False, True, False, False])
+    obs, info = envs.reset(options={"scene": "rdm", "num_vehicles": 2, "scene_seed": 5, "reset_mask": mask})
+    ids, m = envs.engine.resets[-1]
+    assert m.tolist() == mask.tolist() and info["scenario"]["scene"].tolist() == [None, "rdm", None, None]
+    assert envs.engine.pools[-1] == 5 and not envs._needs_reset.any()
+    envs.step(np.zeros((4, 3), np.float32))
+    # the same options again hit the cache: no new upload
+    n_up = len(envs.engine.pools)
+    envs.reset(seed=7, options={"scene": "lead_brake", "level": 2})
+    assert len(envs.engine.pools) == n_up
+    envs.close()
+    # sharded construction: the shard's envs carry the seeds of envs [lo, hi) of the full VectorEnv
+    part = V.make_env(RunConfig(env=EnvConfig(action_mode="continuous"), num_envs=4), shard=(1, 2))
+    _, info = part.reset(seed=7, options={"scene": "lead_brake", "level": 2})
+    assert part.num_envs == 2 and info["scenario"]["scene_seed"].tolist() == [9, 10]
+    part.close()
