@@ -577,3 +577,21 @@ def test_vector_env_host_logic_with_a_stub_engine(monkeypatch):
     _, info = part.reset(seed=7, options={"scene": "lead_brake", "level": 2})
     assert part.num_envs == 2 and info["scenario"]["scene_seed"].tolist() == [9, 10]
     part.close()
+
+
+def test_bench_pool_is_generated_once_per_box(tmp_path):
+    """bench.py under torchrun: rank 0 generates the scene pool and publishes the file atomically, the other ranks
+    only wait for it (no collective is pending meanwhile, nobody generates twice)."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r); import bench; "
+            "s = bench.build_pool(96); print(len(s), int(s[95]['seed']))" % ROOT)
+    env = {**os.environ, "TMPDIR": str(tmp_path), "WORLD_SIZE": "2"}
+    procs = [subprocess.Popen([sys.executable, "-c", code], env={**env, "RANK": str(r)}, stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in (1, 0)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert [p.returncode for p in procs] == [0, 0], outs
+    assert [o[0].strip() for o in outs] == ["96 95", "96 95"]
+    assert "scenes generated" in outs[1][1] and "scenes generated" not in outs[0][1]   # only rank 0 built it
+    assert os.listdir(os.path.join(tmp_path, "cbev_bench_pools")) == ["pool_lead_brake_96.npz"]
