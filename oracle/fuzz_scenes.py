@@ -23,7 +23,21 @@ from carlabev_env_b200 import scenes as S  # noqa: E402
 from carlabev_env_b200.vector_env import load_town01_map  # noqa: E402
 
 
-def random_options(rng):
+AUTHORED = ("jaywalk-01.01.json", "jaywalk-01.02.json", "jaywalk-01.03.json", "leadbrake-01.01.json",
+            "leadbrake-01.02.json", "leadbrake-01.03.json", "redlightrunner-01.01.json")
+
+
+def random_options(rng, authored=False):
+    if authored and rng.random() < 0.35:   # authored scene file of the reference, with / without seeded variation
+        from oracle.ref_loader import REFERENCE_ROOT
+
+        o = {"config_file": os.path.join(REFERENCE_ROOT, "CarlaBEV", "assets", "scenes", str(rng.choice(AUTHORED))),
+             "scene_seed": int(rng.integers(0, 1000))}
+        if rng.random() < 0.7:
+            o["variation_enabled"] = True
+            if rng.random() < 0.8:
+                o["variation_seed"] = int(rng.integers(0, 10000))
+        return o
     kind = rng.choice(["rdm", "rdm", "rdm", "lead_brake", "jaywalk", "red_light_runner"])
     o = {"scene": str(kind), "scene_seed": int(rng.integers(0, 1_000_000))}
     if kind == "rdm":
@@ -68,7 +82,7 @@ def main():
     cls = load_town01_map()
     bad = errors = 0
     for case in range(n):
-        o = random_options(rng)
+        o = random_options(rng, authored=True)
         ref_err = got_err = None
         try:
             envs.reset(options={**o, "reset_mask": np.array([True])})
@@ -87,7 +101,7 @@ def main():
             continue
         diff = [k for k in ref if k not in ("kind", "level")
                 and (np.asarray(ref[k]).shape != np.asarray(got[k]).shape or not np.array_equal(ref[k], got[k]))]
-        if o["scene"] == "red_light_runner" and diff == ["act_state0"]:
+        if (o.get("scene") == "red_light_runner" or "config_file" in o) and diff == ["act_state0"]:
             d = np.abs(ref["act_state0"] - got["act_state0"])
             if d[:, :2].max() <= 2.0 and d[:, 3].max() == 0.0:
                 diff = []
