@@ -51,12 +51,16 @@ def random_env(rng):
     return kw
 
 
+PURSUIT = len(sys.argv) > 4 and sys.argv[4] == "pursuit"
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     max_steps = int(sys.argv[3]) if len(sys.argv) > 3 else 160
     cls = load_town01_map()
     bad = steps = 0
+    causes = {}
     for ep in range(n):
         kw = random_env(rng)
         o = random_options(rng)
@@ -84,10 +88,23 @@ def main():
             what = "reset observation"
         n_act = envs.single_action_space.n if am == "discrete" else 0
         style = rng.random()
+        pursuit = PURSUIT and rng.random() < 0.7   # steer towards the route so that episodes get long / succeed
+        table = np.asarray(ora.table, dtype=np.float64) if am == "discrete" else None
         for t in range(max_steps):
             if what:
                 break
-            if am == "continuous":
+            if pursuit:
+                h = base.map.hero
+                k = min(int(h.target_idx) + 2, len(h.cx) - 1)
+                err = np.arctan2(h.cy[k] - h.y, h.cx[k] - h.x) - h.yaw
+                err = (err + np.pi) % (2 * np.pi) - np.pi
+                want = np.array([0.7 if h.v < 25.0 else 0.0, np.clip(2.0 * err, -1, 1) + rng.normal(0, 0.05),
+                                 1.0 if h.v > 32.0 else 0.0])
+                if am == "continuous":
+                    a = np.clip(want, [0, -1, 0], [1, 1, 1]).astype(np.float32)
+                else:
+                    a = int(np.argmin(((table - want) ** 2).sum(1)))
+            elif am == "continuous":
                 a = np.array([rng.uniform(0.2 if style < 0.6 else 0, 1), rng.uniform(-1, 1) * (0.3 if style < 0.6 else 1.0),
                               rng.uniform(0, 1) * (rng.random() < 0.2)], dtype=np.float32)
             else:
@@ -111,11 +128,14 @@ def main():
             elif ref_a.shape != got_a.shape or not np.array_equal(ref_a, got_a):
                 what = f"actor states at step {t}"
             if term[0] or trunc[0]:
+                c = base.current_info["reward"]["cause"]
+                causes[c] = causes.get(c, 0) + 1
                 break
         if what:
             bad += 1
             print("MISMATCH", what, kw, o)
         envs.close()
+    print(f"endings: {causes}")
     print(f"{n} episodes, {steps} steps compared, {bad} mismatching episodes")
     return 1 if bad else 0
 
