@@ -1,0 +1,109 @@
+"""Engine vs oracle under random configurations with route-pursuit driving (long episodes, success / checkpoint
+endings).  Run on the B200 box:  python tools/gpu_fuzz.py [n_rounds] [seed] [steps]
+Same comparison as tests/test_gpu_engine.py::test_random_configurations_against_the_oracle, more of it."""
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+
+
+def main():
+    import torch
+
+    from golden_util import load_map
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.config import ACTION_PROFILES
+    from carlabev_env_b200.fovmask import corner_mask
+    from carlabev_env_b200.pool import pack_pool
+    from oracle.env import OracleEnv
+
+    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 300
+    cls = load_map()
+    bad = compared = 0
+    endings = {}
+    for rd in range(rounds):
+        profile = str(rng.choice(["continuous_gsb_v1", "discrete9_v1", "discrete13_v1"]))
+        continuous = profile == "continuous_gsb_v1"
+        reward = "shaping" if rng.random() < 0.4 else "carl"
+        mask = str(rng.choice(["6-class", "7-class", "5-class", "4-class", "binary"]))
+        anchor = (0.5, 0.75) if rng.random() < 0.4 else (0.5, 0.5)
+        fov_masked, gray = bool(rng.random() < 0.3), bool(rng.random() < 0.25)
+        frame_stack = int(rng.choice([3, 4, 4, 5]))
+        pad = 230 if anchor[1] == 0.75 else 182
+        reqs = [dict(scene="rdm", num_vehicles=int(rng.integers(0, 12)), route_dist_range=[30, 90],
+                     scene_seed=int(rng.integers(0, 10**6))) for _ in range(8)]
+        reqs += [dict(scene="lead_brake", level=int(rng.integers(1, 4)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
+        reqs += [dict(scene="jaywalk", level=int(rng.integers(1, 5)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
+        reqs += [dict(scene="red_light_runner", scene_seed=int(rng.integers(0, 10**6))) for _ in range(2)]
+        scenes = [S.build_scene(r, cls_map=cls, pad=pad) for r in reqs]
+        n = len(scenes)
+        table = ACTION_PROFILES[profile].get("discrete_actions")
+        eng = E.Engine(n, obs_mode=E.OBS_GRAY if gray else E.OBS_SEMANTIC, mask_mode=mask, frame_stack=frame_stack,
+                       action_mode=E.ACTION_CONTINUOUS if continuous else E.ACTION_DISCRETE, discrete_table=table,
+                       reward_mode=E.REWARD_SHAPING if reward == "shaping" else E.REWARD_CARL, anchor=anchor,
+                       max_actors=16, ring_budget_bytes=64 << 20)
+        eng.upload_map(cls)
+        eng.upload_pool(pack_pool(scenes))
+        if fov_masked:
+            eng.upload_fov_mask(corner_mask(128, 0.5))
+        oracles = [OracleEnv(cls, obs_mode="bev_gray" if gray else "bev_semantic", semantic_mask_ch=mask,
+                             action_mode="continuous" if continuous else "discrete", action_profile=profile,
+                             reward_mode=reward, anchor=anchor, fov_masked=fov_masked, frame_stack=frame_stack)
+                   for _ in range(n)]
+        obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+        what = None
+        for i in range(n):
+            if not np.array_equal(obs[i], oracles[i].reset(scenes[i])):
+                what = f"reset observation of env {i}"
+        alive = np.ones(n, bool)
+        tab = None if continuous else np.asarray(table, dtype=np.float64)
+        for t in range(steps):
+            if what or not alive.any():
+                break
+            acts = []
+            for i in range(n):
+                e = oracles[i].sim.ego
+                k = min(int(e.tidx) + 2, len(e.cx) - 1)
+                err = np.arctan2(e.cy[k] - e.y, e.cx[k] - e.x) - e.yaw
+                err = (err + np.pi) % (2 * np.pi) - np.pi
+                want = np.array([0.7 if e.v < 25.0 else 0.0, np.clip(2.0 * err, -1, 1) + rng.normal(0, 0.05),
+                                 1.0 if e.v > 32.0 else 0.0])
+                acts.append(np.clip(want, [0, -1, 0], [1, 1, 1]) if continuous else int(np.argmin(((tab - want) ** 2).sum(1))))
+            a = np.asarray(acts, dtype=np.float32 if continuous else np.int64)
+            eng.step(torch.from_numpy(a).cuda())
+            obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+            term, trunc = eng.terminated.cpu().numpy().astype(bool), eng.truncated.cpu().numpy().astype(bool)
+            hero = eng.hero.cpu().numpy()
+            for i in range(n):
+                if not alive[i]:
+                    continue
+                o, r, te, tr, _ = oracles[i].step(a[i] if continuous else int(a[i]))
+                e = oracles[i].sim.ego
+                compared += 1
+                if not np.array_equal(obs[i], o):
+                    what = f"observation env {i} step {t}"
+                elif abs(r - rew[i]) > 1e-9 or te != term[i] or tr != trunc[i]:
+                    what = f"reward / flags env {i} step {t}: {r} {rew[i]} {te} {term[i]}"
+                elif not np.allclose(hero[i, :4], [e.x, e.y, e.yaw, e.v], rtol=1e-9, atol=1e-9):
+                    what = f"pose env {i} step {t}"
+                if te or tr:
+                    alive[i] = False
+                    c = int(eng.cause.cpu()[i])
+                    endings[c] = endings.get(c, 0) + 1
+        eng.close()
+        if what:
+            bad += 1
+            print("MISMATCH", what, dict(profile=profile, reward=reward, mask=mask, anchor=anchor, fov_masked=fov_masked,
+                                         gray=gray, frame_stack=frame_stack), reqs)
+    print(f"endings (cause id -> count): {endings}")
+    print(f"{rounds} rounds, {compared} env-steps compared, {bad} mismatching rounds")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
