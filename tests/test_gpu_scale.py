@@ -1,0 +1,183 @@
+"""Parity with the oracle AT THE BENCHMARK SIZES (BASELINE.json configs[1..3] per-GPU shapes): the engine runs
+4096 / 8192 environments with device auto-reset exactly as `bench.py` drives it, and a seeded random sample of
+64 environments is compared step for step with `OracleEnv` -- stacked observation, reward, flags, ego pose,
+actor poses, and the scene every auto-reset draws (replayed through the same counter hash).  Size-independent
+properties cover the whole batch: episode counter == number of terminal flags raised, step counter == steps x N.
+
+The step order compared is the reference's (envs/carlabev.py:223-231): scene step -> collision -> reward /
+termination -> observation."""
+import numpy as np
+import pytest
+
+from golden_util import load_map
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+M64 = (1 << 64) - 1
+
+
+def _splitmix64(z):
+    z = (z + 0x9E3779B97F4A7C15) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+def autoreset_scene(seed, env, episode, n_scenes):
+    """sim.cu: device auto-reset draw of env `env` after its `episode`-th finished episode."""
+    return _splitmix64((seed + env * 0x9E3779B97F4A7C15 + episode * 0xD1B54A32D192ED03) & M64) % n_scenes
+
+
+def run_scale_parity(scenes, n_envs, *, steps, make_actions, engine_kw, oracle_kw, sample=64, seed=17,
+                     min_autoresets=1, check_actors=True):
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import pack_pool
+    from oracle_pool import OraclePool
+
+    cls = load_map()
+    K = len(scenes)
+    amax = int(max(len(s["act_kind"]) for s in scenes))
+    kw = dict(obs_mode=E.OBS_SEMANTIC, mask_mode="6-class", frame_stack=4, autoreset=E.AUTORESET_NEXT_STEP,
+              max_actors=max(amax, 1), seed=seed, ring_budget_bytes=24 << 30)
+    kw.update(engine_kw)
+    eng = E.Engine(n_envs, **kw)
+    eng.upload_map(cls)
+    eng.upload_pool(pack_pool(scenes))
+    eng.reset(torch.arange(n_envs, dtype=torch.int32) % K)
+    rng = np.random.default_rng(seed)
+    # the sample always holds the first / last env of the batch and of a CTA-sized block, the rest is random
+    fixed = [0, 1, 15, 16, n_envs - 1]
+    rest = rng.choice(np.setdiff1d(np.arange(n_envs), fixed), size=sample - len(fixed), replace=False)
+    idx = np.sort(np.concatenate([fixed, rest])).astype(np.int64)
+    idx_t = torch.from_numpy(idx).cuda()
+    pool = OraclePool(len(idx), scenes, oracle_kw)
+    try:
+        ref = pool.run([("reset", int(i) % K) for i in idx])
+        obs0 = eng.obs()[idx_t].cpu().numpy()
+        for j, i in enumerate(idx):
+            assert np.array_equal(obs0[j], ref[j]["obs"]), (i, "reset observation")
+        done = np.zeros(len(idx), bool)
+        episodes = np.zeros(len(idx), dtype=np.int64)
+        n_auto = n_term = 0
+        term_total = torch.zeros((), dtype=torch.int64, device="cuda")
+        H = {k: c for c, k in enumerate(E.HERO_FIELDS)}
+        for t in range(steps):
+            a = make_actions(rng, n_envs, t)
+            eng.step(torch.from_numpy(a).cuda())
+            # the oracle sample steps on the host cores while the device works
+            drawn = [autoreset_scene(seed, int(i), int(episodes[j]), K) if done[j] else -1 for j, i in enumerate(idx)]
+            cmds = [("reset", drawn[j]) if done[j] else ("step", a[int(i)]) for j, i in enumerate(idx)]
+            ref = pool.run(cmds)
+            term_total += eng.terminated.sum()
+            obs = eng.obs()[idx_t].cpu().numpy()
+            rew = eng.reward[idx_t].cpu().numpy()
+            term = eng.terminated[idx_t].cpu().numpy().astype(bool)
+            trunc = eng.truncated[idx_t].cpu().numpy().astype(bool)
+            hero = eng.hero[idx_t].cpu().numpy()
+            act = eng.get_state(amax)[1][idx] if check_actors and amax else None
+            for j, i in enumerate(idx):
+                i, r = int(i), ref[j]
+                if done[j]:  # gymnasium NEXT_STEP: this step resets, ignores the action, reward 0, not terminated
+                    assert int(hero[j][H["scene"]]) == drawn[j], (t, i, "auto-reset scene draw")
+                    assert rew[j] == 0.0 and not term[j] and not trunc[j], (t, i)
+                    assert np.array_equal(obs[j], r["obs"]), (t, i, "auto-reset observation")
+                    done[j] = False
+                    n_auto += 1
+                    continue
+                assert np.allclose(hero[j][:4], r["ego"], rtol=1e-9, atol=1e-9), (t, i, "ego pose")
+                assert abs(r["reward"] - rew[j]) < 1e-9, (t, i, "reward", r["reward"], rew[j])
+                assert r["term"] == term[j] and r["trunc"] == trunc[j], (t, i, "flags")
+                assert np.array_equal(obs[j], r["obs"]), (t, i, "observation", int((obs[j] != r["obs"]).sum()))
+                if act is not None and len(r["actors"]):
+                    na = len(r["actors"])
+                    assert np.allclose(act[j, :na, :4], r["actors"], rtol=1e-9, atol=1e-9), (t, i, "actor poses")
+                if r["term"] or r["trunc"]:
+                    done[j] = True
+                    episodes[j] += 1
+                    n_term += 1
+    finally:
+        pool.close()
+    stats = eng.read_stats().cpu().numpy()
+    assert stats[0] == int(term_total), "episode counter != number of terminal flags raised over the whole batch"
+    assert stats[-1] == steps * n_envs
+    assert n_auto >= min_autoresets, (n_auto, n_term)
+    eng.close()
+    return n_auto, n_term
+
+
+def _uniform_continuous(rng, n, t):
+    return np.stack([rng.uniform(0, 1, n), rng.uniform(-1, 1, n), rng.uniform(0, 1, n)], axis=1).astype(np.float32)
+
+
+def test_c2_4096_lead_brake_autoreset_tables():
+    """configs[1]: 4096 envs, lead_brake levels 1-3, continuous actions, trajectory tables on, auto-reset."""
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.scenes import build_scripted_scene
+
+    cls = load_map()
+    scenes = [build_scripted_scene("lead_brake", i, level=1 + i % 3, cls_map=cls) for i in range(256)]
+    n_auto, n_term = run_scale_parity(scenes, 4096, steps=120, make_actions=_uniform_continuous,
+                                      engine_kw=dict(action_mode=E.ACTION_CONTINUOUS),
+                                      oracle_kw=dict(action_mode="continuous"), min_autoresets=64)
+    assert n_term >= 64
+
+
+@pytest.mark.parametrize("tables", [True, False])
+def test_c3_8192_rdm_25_vehicles(tables):
+    """configs[2] per-GPU shape: 8192 envs, rdm rt_hard_v1 (25 vehicles) from the shipped reference snapshots,
+    discrete9 actions; with the open-loop trajectory tables and with live actor stepping (wide actor loops)."""
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.config import ACTION_PROFILES
+    from carlabev_env_b200.pool import load_shipped_pool
+
+    scenes = load_shipped_pool("rdm_rt_hard_v1")
+
+    def actions(rng, n, t):
+        return rng.choice(np.array([1, 1, 1, 3, 4, 0, 5, 6], dtype=np.int64), size=n)
+
+    run_scale_parity(scenes, 8192, steps=120 if tables else 60, make_actions=actions,
+                     engine_kw=dict(action_mode=E.ACTION_DISCRETE,
+                                    discrete_table=ACTION_PROFILES["discrete9_v1"]["discrete_actions"],
+                                    trajectory_steps=1024 if tables else 0),
+                     oracle_kw=dict(action_mode="discrete"), min_autoresets=1)
+
+
+def test_c4_8192_jaywalk_red_light_mix_autoreset():
+    """configs[3] per-GPU shape: 8192 envs, 50/50 jaywalk (levels 1-4) / red_light_runner with traffic lights,
+    continuous actions, auto-reset with mixed scene kinds; table -> live hand-over is crossed by using short tables."""
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import load_shipped_pool
+    from carlabev_env_b200.scenes import build_scripted_scene
+
+    cls = load_map()
+    rl = load_shipped_pool("red_light_runner")
+    scenes = []
+    for i in range(64):
+        scenes.append(build_scripted_scene("jaywalk", 7000 + i, level=1 + i % 4, cls_map=cls) if i % 2 == 0
+                      else rl[(i // 2) % len(rl)])
+
+    def actions(rng, n, t):
+        a = _uniform_continuous(rng, n, t)
+        a[::2, 0] *= 0.25  # half of the envs crawl: the pedestrians' FSMs (incl. the StopReturn retreat) play out
+        return a
+
+    run_scale_parity(scenes, 8192, steps=120, make_actions=actions,
+                     engine_kw=dict(action_mode=E.ACTION_CONTINUOUS, trajectory_steps=48),
+                     oracle_kw=dict(action_mode="continuous"), min_autoresets=16)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_engine_fuzz_with_pursuit_driving(seed):
+    """tools/gpu_fuzz.py under pytest: random configurations, route-pursuit driving (long episodes, checkpoint and
+    success endings), engine vs oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz.py"), "2", str(seed), "220"], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 mismatching rounds" in r.stdout
