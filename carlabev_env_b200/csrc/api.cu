@@ -118,20 +118,28 @@ int build_tensor_map(cbev_engine* e) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)e->map_w, (cuuint64_t)e->map_h};
   cuuint64_t strides[1] = {(cuuint64_t)e->map_w};
-  cuuint32_t box[2] = {(cuuint32_t)e->box_w, (cuuint32_t)e->crop};
+  cuuint32_t box[2] = {(cuuint32_t)CBEV_TILE_W, (cuuint32_t)CBEV_TILE_H};  // the fetch window (sim.cu:compute_view)
   cuuint32_t estr[2] = {1, 1};
   CUresult r = ((EncodeTiledFn)fn)(reinterpret_cast<CUtensorMap*>(e->tmap), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, e->map,
                                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     cbev_set_error("cuTensorMapEncodeTiled failed with CUresult %d (map %dx%d, box %dx%d)", (int)r, e->map_w, e->map_h,
-                   e->box_w, e->crop);
+                   CBEV_TILE_W, CBEV_TILE_H);
     return CBEV_ERR_CUDA;
   }
   return CBEV_OK;
 }
 
 }  // namespace
+
+// Every entry point runs on the engine's device, whatever the caller's current device is (one engine = one GPU).
+static int use_device(cbev_handle e) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != e->device) CU_TRY(cudaSetDevice(e->device));
+  return CBEV_OK;
+}
 
 extern "C" {
 
@@ -232,10 +240,8 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   int mx = ax > m - ax ? ax : m - ax, my = ay > m - ay ? ay : m - ay;
   int crop = (int)ceil(2.0 * hypot((double)mx, (double)my));
   if (crop < cfg->fov_size) crop = cfg->fov_size;
-  if (crop > 241) { delete e; cbev_set_error("crop size %d exceeds the 256-texel TMA box (crop + 15 alignment slack)", crop); return CBEV_ERR_ARG; }
-  e->crop = crop;
+  e->crop = crop;  // any size: the raster kernel only ever fetches the CBEV_TILE_H x CBEV_TILE_W window a frame can sample
   e->pad = crop;
-  e->box_w = ((crop + 15 + 15) / 16) * 16;  // aligned superset of any 16-byte-unaligned crop origin
   e->channels = cfg->obs_mode == CBEV_OBS_SEMANTIC ? channels_of(cfg->mask_mode) : 1;
   if (cfg->obs_mode == CBEV_OBS_SEMANTIC) e->frame_bytes = (int64_t)e->channels * cfg->obs_h * cfg->obs_w * 4;
   else if (cfg->obs_mode == CBEV_OBS_GRAY) e->frame_bytes = (int64_t)cfg->obs_h * cfg->obs_w;
@@ -248,7 +254,7 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   rc |= dev_alloc(&e->st.done, N);
   rc |= dev_alloc(&e->st.ego, N * 24);
   rc |= dev_alloc(&e->st.egoi, N * 8);
-  rc |= dev_alloc(&e->st.tgt_vis, N);
+  rc |= dev_alloc(&e->st.tgt_vis, N * CBEV_TGT_WORDS);
   rc |= dev_alloc(&e->st.stats, N * 12);
   rc |= dev_alloc(&e->st.ax, N * A);
   rc |= dev_alloc(&e->st.ay, N * A);
@@ -276,6 +282,7 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
 
 int cbev_destroy(cbev_handle e) {
   if (!e) return CBEV_OK;
+  use_device(e);
   free_pool(e->pool);
   free_state(e->st);
   dev_free(e->fov_mask); dev_free(e->rs_tab); dev_free(e->trace);
@@ -285,8 +292,9 @@ int cbev_destroy(cbev_handle e) {
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->ev_sim) cudaEventDestroy(e->ev_sim);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+  if (e->ev_judge) cudaEventDestroy(e->ev_judge);
   if (e->prof_ev) {
-    for (int i = 0; i < 3 * CBEV_PROF_MAX; ++i) cudaEventDestroy(e->prof_ev[i]);
+    for (int i = 0; i < CBEV_PROF_EVENTS * CBEV_PROF_MAX; ++i) cudaEventDestroy(e->prof_ev[i]);
     delete[] e->prof_ev;
   }
   delete e;
@@ -295,6 +303,7 @@ int cbev_destroy(cbev_handle e) {
 
 int cbev_upload_map(cbev_handle e, const uint8_t* cls_host, int32_t w, int32_t h_px) {
   if (!e || !cls_host) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   if (w < 16 || h_px < 16 || (w % 16) != 0) { cbev_set_error("map width must be a multiple of 16 (TMA row pitch), got %dx%d", w, h_px); return CBEV_ERR_ARG; }
   for (size_t i = 0; i < (size_t)w * h_px; ++i)
     if (cls_host[i] > 2) { cbev_set_error("map classes must be 0 (non-drivable), 1 (drivable) or 2 (sidewalk)"); return CBEV_ERR_ARG; }
@@ -311,6 +320,7 @@ int cbev_upload_map(cbev_handle e, const uint8_t* cls_host, int32_t w, int32_t h
 
 int cbev_upload_scene_pool(cbev_handle e, const cbev_pool_desc* p) {
   if (!e || !p) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   if (p->n_scenes < 1) { cbev_set_error("scene pool is empty"); return CBEV_ERR_ARG; }
   const int n = p->n_scenes;
   // ---- validate (the reference raises on malformed scenes at reset; here at upload) ----
@@ -346,8 +356,18 @@ int cbev_upload_scene_pool(cbev_handle e, const cbev_pool_desc* p) {
   }
   if (max_actors > e->cfg.max_actors) { cbev_set_error("pool has scenes with %d actors but the engine was created with max_actors=%d", max_actors, e->cfg.max_actors); return CBEV_ERR_ARG; }
 
-  free_pool(e->pool);
-  PoolDev& d = e->pool;
+  // Environments may be mid-episode (SyncVectorEnv resets a subset with a new scene while the others keep running):
+  // a pool uploaded then must EXTEND the previous one (scene i keeps its index), and everything a running env
+  // depends on stays as it is -- the length of the trajectory tables (the hand-over step), the per-env retreat
+  // routes and their row stride.  The new pool is built on the side and swapped in only when complete, so a failed
+  // upload leaves the previous pool in place.
+  const bool live = e->was_reset && e->has_pool;
+  if (live) {
+    if (n < e->pool.n_scenes) { cbev_set_error("a pool uploaded while environments are running must extend the previous one (%d scenes < %d)", n, e->pool.n_scenes); return CBEV_ERR_ARG; }
+    CU_TRY(cudaDeviceSynchronize());
+    if (max_retreat < e->pool.max_retreat) max_retreat = e->pool.max_retreat;
+  }
+  PoolDev d;
   d.n_scenes = n;
   d.n_actors_total = p->n_actors_total;
   d.max_actors = max_actors;
@@ -391,21 +411,40 @@ int cbev_upload_scene_pool(cbev_handle e, const cbev_pool_desc* p) {
   rc |= dev_upload(&d.tl_rect, p->tl_rect, ntl * 4);
   rc |= dev_upload(&d.tl_color, p->tl_color, ntl);
   if (p->sg_mat) rc |= dev_upload(&d.sg_mat, p->sg_mat, (size_t)(CBEV_SG_MAX + 1) * CBEV_SG_MAX * CBEV_SG_MAX);
-  if (rc) return rc;
-  // per-env buffers that depend on the pool
-  dev_free(e->rects);
-  dev_free(e->st.retreat);
-  dev_free(e->st.retreat_n);
-  e->max_rects = e->cfg.max_actors + CBEV_MAX_TARGETS + max_tl + 1;
-  rc |= dev_alloc(&e->rects, (size_t)e->N * e->max_rects);
-  rc |= dev_alloc(&e->st.retreat, (size_t)e->N * (max_retreat ? max_retreat : 1) * 3 * CBEV_SG_MAX);
-  rc |= dev_alloc(&e->st.retreat_n, (size_t)e->N * (max_retreat ? max_retreat : 1));
-  if (rc) return rc;
+  if (rc) { free_pool(d); return rc; }
+  // ---- per-env buffers that depend on the pool ----
+  const size_t Rn = (size_t)(max_retreat ? max_retreat : 1), Ro = (size_t)(e->pool.max_retreat ? e->pool.max_retreat : 1);
+  const int32_t new_max_rects = e->cfg.max_actors + CBEV_MAX_TARGETS + max_tl + 1;
+  uint32_t* rects = nullptr;
+  double* retreat = nullptr;
+  int32_t* retreat_n = nullptr;
+  const bool grow_rects = !e->rects || new_max_rects > e->max_rects;
+  const bool grow_retreat = !e->st.retreat || !live || Rn != Ro;
+  if (grow_rects) rc |= dev_alloc(&rects, (size_t)e->N * CBEV_RECT_WORDS * new_max_rects);
+  if (grow_retreat) {
+    rc |= dev_alloc(&retreat, (size_t)e->N * Rn * 3 * CBEV_SG_MAX);
+    rc |= dev_alloc(&retreat_n, (size_t)e->N * Rn);
+    if (!rc && live && e->st.retreat) {  // running envs keep the retreat routes they are following (new row stride)
+      const size_t row_o = Ro * 3 * CBEV_SG_MAX * sizeof(double), row_n = Rn * 3 * CBEV_SG_MAX * sizeof(double);
+      if (cudaMemcpy2D(retreat, row_n, e->st.retreat, row_o, row_o, (size_t)e->N, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+          cudaMemcpy2D(retreat_n, Rn * sizeof(int32_t), e->st.retreat_n, Ro * sizeof(int32_t), Ro * sizeof(int32_t),
+                       (size_t)e->N, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+        cbev_set_error("copying the retreat routes failed");
+        rc = CBEV_ERR_CUDA;
+      }
+    }
+  }
   // ---- open-loop actor trajectories: roll every scene out once on the device (k_rollout) ----
-  int T = e->cfg.trajectory_steps;
-  if (T > 0 && na > 0) {
+  int T = live ? e->pool.traj_steps : e->cfg.trajectory_steps;  // the hand-over step never moves under running envs
+  if (!rc && T > 0 && na > 0) {
     const size_t budget = (size_t)4 << 30;  // cap the tables at 4 GiB
-    while (T > 16 && (size_t)T * na * sizeof(double4) > budget) T /= 2;
+    if (!live) {
+      while (T > 16 && (size_t)T * na * sizeof(double4) > budget) T /= 2;
+    } else if ((size_t)T * na * sizeof(double4) > 2 * budget) {
+      cbev_set_error("the extended pool needs %zu bytes of trajectory tables at the %d steps fixed by the first upload",
+                     (size_t)T * na * sizeof(double4), T);
+      rc = CBEV_ERR_NOMEM;
+    }
     std::vector<long long> off((size_t)n);
     long long acc = 0;
     for (int s2 = 0; s2 < n; ++s2) {
@@ -414,20 +453,38 @@ int cbev_upload_scene_pool(cbev_handle e, const cbev_pool_desc* p) {
     }
     const size_t S = (size_t)n, A = (size_t)(e->cfg.max_actors > 0 ? e->cfg.max_actors : 1);
     EnvState& r = d.roll;
-    rc |= dev_upload(&d.traj_off, off.data(), S);
-    rc |= dev_alloc(&d.traj, (size_t)acc);
-    rc |= dev_alloc(&r.ax, S * A); rc |= dev_alloc(&r.ay, S * A); rc |= dev_alloc(&r.ayaw, S * A);
-    rc |= dev_alloc(&r.av, S * A); rc |= dev_alloc(&r.atarget_mps, S * A); rc |= dev_alloc(&r.aelapsed, S * A);
-    rc |= dev_alloc(&r.astate_elapsed, S * A); rc |= dev_alloc(&r.atidx, S * A); rc |= dev_alloc(&r.arxlen, S * A);
-    rc |= dev_alloc(&r.aflags, S * A);
-    rc |= dev_alloc(&r.retreat, S * (max_retreat ? max_retreat : 1) * 3 * CBEV_SG_MAX);
-    rc |= dev_alloc(&r.retreat_n, S * (max_retreat ? max_retreat : 1));
-    if (rc) return rc;
-    d.traj_steps = T;
-    cbev_launch_rollout(e, 0);
-    CU_TRY(cudaDeviceSynchronize());
+    if (!rc) {
+      rc |= dev_upload(&d.traj_off, off.data(), S);
+      rc |= dev_alloc(&d.traj, (size_t)acc);
+      rc |= dev_alloc(&r.ax, S * A); rc |= dev_alloc(&r.ay, S * A); rc |= dev_alloc(&r.ayaw, S * A);
+      rc |= dev_alloc(&r.av, S * A); rc |= dev_alloc(&r.atarget_mps, S * A); rc |= dev_alloc(&r.aelapsed, S * A);
+      rc |= dev_alloc(&r.astate_elapsed, S * A); rc |= dev_alloc(&r.atidx, S * A); rc |= dev_alloc(&r.arxlen, S * A);
+      rc |= dev_alloc(&r.aflags, S * A);
+      rc |= dev_alloc(&r.retreat, S * Rn * 3 * CBEV_SG_MAX);
+      rc |= dev_alloc(&r.retreat_n, S * Rn);
+    }
+    if (!rc) d.traj_steps = T;
   }
+  if (rc) {
+    free_pool(d);
+    dev_free(rects); dev_free(retreat); dev_free(retreat_n);
+    return rc;
+  }
+  // ---- swap in ----
+  free_pool(e->pool);
+  e->pool = d;
+  if (grow_rects) { dev_free(e->rects); e->rects = rects; e->max_rects = new_max_rects; }
+  if (grow_retreat) { dev_free(e->st.retreat); dev_free(e->st.retreat_n); e->st.retreat = retreat; e->st.retreat_n = retreat_n; }
   e->has_pool = true;
+  if (e->pool.traj_steps > 0) {
+    cbev_launch_rollout(e, 0);
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) {
+      cbev_set_error("trajectory roll-out failed: %s", cudaGetErrorString(ce));
+      e->has_pool = false;
+      return CBEV_ERR_CUDA;
+    }
+  }
   return CBEV_OK;
 }
 
@@ -435,6 +492,7 @@ int64_t cbev_frame_bytes(cbev_handle e) { return e ? e->frame_bytes : -1; }
 
 int cbev_bind_obs_ring(cbev_handle e, void* ring_dev, int64_t bytes) {
   if (!e || !ring_dev) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   int64_t need = (int64_t)e->N * e->cfg.ring_slots * e->frame_bytes;
   if (bytes < need) { cbev_set_error("observation ring needs %lld bytes, got %lld", (long long)need, (long long)bytes); return CBEV_ERR_ARG; }
   if (((uintptr_t)ring_dev & 15) != 0) { cbev_set_error("observation ring must be 16-byte aligned"); return CBEV_ERR_ARG; }
@@ -445,6 +503,7 @@ int cbev_bind_obs_ring(cbev_handle e, void* ring_dev, int64_t bytes) {
 
 static int check_ready(cbev_handle e, bool need_reset) {
   if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   if (!e->has_map) { cbev_set_error("no map uploaded (cbev_upload_map)"); return CBEV_ERR_STATE; }
   if (!e->has_pool) { cbev_set_error("no scene pool uploaded (cbev_upload_scene_pool)"); return CBEV_ERR_STATE; }
   if (!e->ring) { cbev_set_error("no observation ring bound (cbev_bind_obs_ring)"); return CBEV_ERR_STATE; }
@@ -469,78 +528,133 @@ int cbev_reset(cbev_handle e, const uint8_t* mask_dev, const int32_t* scene_ids_
   return CBEV_OK;
 }
 
+static int ensure_side_stream(cbev_engine* e) {
+  if (e->side_stream) return CBEV_OK;
+  int lo = 0, hi = 0;  // numerically lowest = highest priority: k_judge's few CTAs must not queue behind the raster grid
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU_TRY(cudaStreamCreateWithPriority(&e->side_stream, cudaStreamNonBlocking, hi));
+  CU_TRY(cudaEventCreateWithFlags(&e->ev_sim, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&e->ev_judge, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming));
+  return CBEV_OK;
+}
+
+int cbev_step_ex(cbev_handle e, const void* actions_dev, const cbev_step_out* out, const cbev_host_out* host, void* stream);
+
 int cbev_step(cbev_handle e, const void* actions_dev, const cbev_step_out* out, void* stream) {
+  return cbev_step_ex(e, actions_dev, out, nullptr, stream);
+}
+
+int cbev_step_ex(cbev_handle e, const void* actions_dev, const cbev_step_out* out, const cbev_host_out* host,
+                 void* stream) {
   int rc = check_ready(e, true);
   if (rc) return rc;
   if (!actions_dev || !out || !out->reward || !out->terminated || !out->truncated) { cbev_set_error("actions, reward, terminated and truncated are required"); return CBEV_ERR_ARG; }
+  if (host && (!host->reward || !host->terminated || !host->truncated)) { cbev_set_error("null host buffer"); return CBEV_ERR_ARG; }
+  if ((rc = ensure_side_stream(e))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const int F = e->cfg.frame_stack, L = e->cfg.ring_slots;
   int head = e->head + 1;
   if (head >= L) head = F - 1;
   const int mirror = F > 1 ? L - F + 1 : 0;
-  // One (sim, raster) kernel pair per step.  Splitting the batch into chunks on side streams so that the sim
-  // of chunk c+1 overlaps the raster of chunk c was measured on B200 (2/4/8 chunks: 240/253/265 us per step
-  // vs 239 us unsplit at 4096 envs) and does not pay: the raster CTAs already fill every SM.
+  // Per step: k_move on `stream`; then k_judge on the (high-priority) side stream CONCURRENTLY with k_render on
+  // `stream` -- the raster kernel reads only the descriptor / draw list k_move wrote, the judging chain (reward,
+  // termination, statistics) touches neither.  `stream` joins the side stream at the end of the step, so whatever
+  // the caller enqueues next (its reads of reward / flags, the next step) is ordered after both.
   const bool prof = e->profiling && e->prof_n < CBEV_PROF_MAX;
-  if (prof) cudaEventRecord(e->prof_ev[3 * e->prof_n + 0], s);
-  cbev_launch_sim(e, actions_dev, out, 0, e->N, s);
-  if (e->debug_flags & 2) cbev_launch_sim(e, actions_dev, out, 0, e->N, s);  // timing probe: second, instruction-warm launch
-  if (prof) cudaEventRecord(e->prof_ev[3 * e->prof_n + 1], s);
-  if ((rc = debug_sync("k_sim", s))) return rc;
-  if (e->host_out) {  // reward / flags are final after the sim kernel: copy them out while the raster kernel runs
+  cudaEvent_t* pe = prof ? e->prof_ev + CBEV_PROF_EVENTS * e->prof_n : nullptr;
+  if (prof) cudaEventRecord(pe[0], s);
+  cbev_launch_move(e, actions_dev, out, 0, e->N, s);
+  if (prof) cudaEventRecord(pe[1], s);
+  if ((rc = debug_sync("k_move", s))) return rc;
+  CU_TRY(cudaEventRecord(e->ev_sim, s));
+  CU_TRY(cudaStreamWaitEvent(e->side_stream, e->ev_sim, 0));
+  if (prof) cudaEventRecord(pe[3], e->side_stream);
+  cbev_launch_judge(e, out, 0, e->N, e->side_stream);
+  if (prof) cudaEventRecord(pe[4], e->side_stream);
+  if ((rc = debug_sync("k_judge", e->side_stream))) return rc;
+  if (host) {  // reward / flags are final after k_judge: copy them out while the raster kernel runs
     const size_t N = (size_t)e->N;
-    CU_TRY(cudaEventRecord(e->ev_sim, s));
-    CU_TRY(cudaStreamWaitEvent(e->side_stream, e->ev_sim, 0));
-    if (e->host_term == (uint8_t*)e->host_out + N * 8 && e->host_trunc == e->host_term + N) {
-      // the caller laid the three outputs out back to back: one D2H copy instead of three
-      CU_TRY(cudaMemcpyAsync(e->host_out, e->h_reward_dev, N * 10, cudaMemcpyDeviceToHost, e->side_stream));
+    const cbev_host_out* ho = host;
+    const bool packed_dev = out->terminated == (uint8_t*)out->reward + N * 8 && out->truncated == out->terminated + N;
+    const bool packed_host = ho->terminated == (uint8_t*)ho->reward + N * 8 && ho->truncated == ho->terminated + N;
+    if (packed_dev && packed_host) {
+      // both sides laid the three outputs out back to back: one D2H copy instead of three
+      CU_TRY(cudaMemcpyAsync(ho->reward, out->reward, N * 10, cudaMemcpyDeviceToHost, e->side_stream));
     } else {
-      CU_TRY(cudaMemcpyAsync(e->host_out, e->h_reward_dev, N * 8, cudaMemcpyDeviceToHost, e->side_stream));
-      CU_TRY(cudaMemcpyAsync(e->host_term, e->h_term_dev, N, cudaMemcpyDeviceToHost, e->side_stream));
-      CU_TRY(cudaMemcpyAsync(e->host_trunc, e->h_trunc_dev, N, cudaMemcpyDeviceToHost, e->side_stream));
+      CU_TRY(cudaMemcpyAsync(ho->reward, out->reward, N * 8, cudaMemcpyDeviceToHost, e->side_stream));
+      CU_TRY(cudaMemcpyAsync(ho->terminated, out->terminated, N, cudaMemcpyDeviceToHost, e->side_stream));
+      CU_TRY(cudaMemcpyAsync(ho->truncated, out->truncated, N, cudaMemcpyDeviceToHost, e->side_stream));
     }
+    if (ho->cause && out->cause) CU_TRY(cudaMemcpyAsync(ho->cause, out->cause, N, cudaMemcpyDeviceToHost, e->side_stream));
+    if (ho->episode && out->episode)
+      CU_TRY(cudaMemcpyAsync(ho->episode, out->episode, N * CBEV_EPISODE_FIELDS * sizeof(double), cudaMemcpyDeviceToHost,
+                             e->side_stream));
     CU_TRY(cudaEventRecord(e->ev_copy, e->side_stream));
+    e->host_copy_pending = true;
   }
+  CU_TRY(cudaEventRecord(e->ev_judge, e->side_stream));
   if (cbev_launch_render(e, head, mirror, 0, e->N, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
-  if (prof) { cudaEventRecord(e->prof_ev[3 * e->prof_n + 2], s); e->prof_n += 1; }
+  if (prof) { cudaEventRecord(pe[2], s); e->prof_n += 1; }
   if ((rc = debug_sync("k_render", s))) return rc;
+  CU_TRY(cudaStreamWaitEvent(s, e->ev_judge, 0));  // join (covers the host copies too)
   CU_TRY(cudaGetLastError());
   e->head = head;
   e->steps += 1;
   return CBEV_OK;
 }
 
-int cbev_step_host(cbev_handle e, const void* actions_host, double* reward_host, uint8_t* terminated_host,
-                   uint8_t* truncated_host, void* stream) {
+int cbev_step_host_ex(cbev_handle e, const void* actions_host, const cbev_step_out* dev_out, const cbev_host_out* host,
+                      void* stream) {
   int rc = check_ready(e, true);
   if (rc) return rc;
-  if (!actions_host || !reward_host || !terminated_host || !truncated_host) { cbev_set_error("null host buffer"); return CBEV_ERR_ARG; }
+  if (!actions_host || !host || !host->reward || !host->terminated || !host->truncated) { cbev_set_error("null host buffer"); return CBEV_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = (size_t)e->N;
   const size_t abytes = e->cfg.action_mode == CBEV_ACTION_DISCRETE ? N * 8 : N * 12;
   CU_TRY(cudaMemcpyAsync(e->h_actions_dev, actions_host, abytes, cudaMemcpyHostToDevice, s));
   cbev_step_out out;
-  memset(&out, 0, sizeof(out));
-  out.reward = e->h_reward_dev;
-  out.terminated = e->h_term_dev;
-  out.truncated = e->h_trunc_dev;
-  if (!e->side_stream) {
-    CU_TRY(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
-    CU_TRY(cudaEventCreateWithFlags(&e->ev_sim, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming));
+  if (dev_out) {
+    out = *dev_out;
+  } else {
+    memset(&out, 0, sizeof(out));
+    out.reward = e->h_reward_dev;
+    out.terminated = e->h_term_dev;
+    out.truncated = e->h_trunc_dev;
   }
-  e->host_out = reward_host;
-  e->host_term = terminated_host;
-  e->host_trunc = truncated_host;
-  rc = cbev_step(e, e->h_actions_dev, &out, stream);
-  e->host_out = nullptr;
-  if (rc) return rc;
-  CU_TRY(cudaStreamWaitEvent(s, e->ev_copy, 0));  // a synchronize on `stream` also covers the copy
+  return cbev_step_ex(e, e->h_actions_dev, &out, host, stream);  // `stream` joins the side stream: a synchronize covers the copies
+}
+
+int cbev_step_host(cbev_handle e, const void* actions_host, double* reward_host, uint8_t* terminated_host,
+                   uint8_t* truncated_host, void* stream) {
+  cbev_host_out host;
+  memset(&host, 0, sizeof(host));
+  host.reward = reward_host;
+  host.terminated = terminated_host;
+  host.truncated = truncated_host;
+  return cbev_step_host_ex(e, actions_host, nullptr, &host, stream);
+}
+
+int cbev_invalidate(cbev_handle e) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
+  CU_TRY(cudaDeviceSynchronize());
+  e->was_reset = false;
+  return CBEV_OK;
+}
+
+int cbev_wait_host_outputs(cbev_handle e) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
+  if (!e->host_copy_pending) return CBEV_OK;
+  CU_TRY(cudaEventSynchronize(e->ev_copy));
+  e->host_copy_pending = false;
   return CBEV_OK;
 }
 
 int cbev_upload_fov_mask(cbev_handle e, const uint8_t* mask_host) {
   if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   CU_TRY(cudaDeviceSynchronize());
   dev_free(e->fov_mask);
   if (!mask_host) return CBEV_OK;
@@ -595,15 +709,16 @@ int cbev_obs_head(cbev_handle e, int32_t* head) {
 
 int cbev_get_state(cbev_handle e, double* ego_host, double* actors_host) {
   if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   CU_TRY(cudaDeviceSynchronize());
   const size_t N = (size_t)e->N, A = (size_t)(e->cfg.max_actors > 0 ? e->cfg.max_actors : 1);
   if (ego_host) {
     std::vector<double> eg(N * 24);
     std::vector<int32_t> ei(N * 8);
-    std::vector<unsigned long long> tv(N);
+    std::vector<unsigned long long> tv(N * CBEV_TGT_WORDS);
     CU_TRY(cudaMemcpy(eg.data(), e->st.ego, N * 24 * 8, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(ei.data(), e->st.egoi, N * 8 * 4, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(tv.data(), e->st.tgt_vis, N * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(tv.data(), e->st.tgt_vis, N * CBEV_TGT_WORDS * 8, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < N; ++i) {
       double* o = ego_host + i * 16;
       for (int k = 0; k < 9; ++k) o[k] = eg[i * 24 + k];  // x,y,yaw,v,x1,y1,yaw1,v1,acc
@@ -612,8 +727,8 @@ int cbev_get_state(cbev_handle e, double* ego_host, double* actors_host) {
       o[11] = eg[i * 24 + 10];                             // dist2goal
       o[12] = eg[i * 24 + 11];                             // dist2goal_1
       o[13] = eg[i * 24 + 12];                             // s_prev
-      o[14] = (double)(uint32_t)(tv[i] & 0xffffffffull);
-      o[15] = (double)(uint32_t)(tv[i] >> 32);
+      o[14] = (double)(uint32_t)(tv[i * CBEV_TGT_WORDS] & 0xffffffffull);  // first 64 targets
+      o[15] = (double)(uint32_t)(tv[i * CBEV_TGT_WORDS] >> 32);
     }
   }
   if (actors_host) {
@@ -638,6 +753,7 @@ int cbev_get_state(cbev_handle e, double* ego_host, double* actors_host) {
 
 int cbev_set_ego_state(cbev_handle e, const double* ego_host) {
   if (!e || !ego_host) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   CU_TRY(cudaDeviceSynchronize());
   const size_t N = (size_t)e->N;
   std::vector<double> eg(N * 24);
@@ -654,6 +770,37 @@ int cbev_set_ego_state(cbev_handle e, const double* ego_host) {
   return CBEV_OK;
 }
 
+int cbev_set_state(cbev_handle e, const double* ego_host, const double* actors_host) {
+  if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
+  if (ego_host) {
+    int rc = cbev_set_ego_state(e, ego_host);
+    if (rc) return rc;
+  }
+  if (actors_host) {
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t N = (size_t)e->N, A = (size_t)(e->cfg.max_actors > 0 ? e->cfg.max_actors : 1);
+    std::vector<double> x(N * A), y(N * A), yaw(N * A), v(N * A), tm(N * A);
+    std::vector<int32_t> ti(N * A);
+    std::vector<uint8_t> fl(N * A);
+    for (size_t i = 0; i < N * A; ++i) {
+      const double* o = actors_host + i * 8;
+      x[i] = o[0]; y[i] = o[1]; yaw[i] = o[2]; v[i] = o[3];
+      ti[i] = (int32_t)o[4];
+      tm[i] = o[6];
+      fl[i] = (uint8_t)(((int)o[7] & ~15) | ((int)o[5] & 15));  // flags byte with the FSM state of column 5
+    }
+    CU_TRY(cudaMemcpy(e->st.ax, x.data(), N * A * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(e->st.ay, y.data(), N * A * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(e->st.ayaw, yaw.data(), N * A * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(e->st.av, v.data(), N * A * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(e->st.atarget_mps, tm.data(), N * A * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(e->st.atidx, ti.data(), N * A * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(e->st.aflags, fl.data(), N * A, cudaMemcpyHostToDevice));
+  }
+  return CBEV_OK;
+}
+
 int cbev_set_debug_flags(cbev_handle e, int32_t flags) {
   if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
   e->debug_flags = flags;
@@ -663,6 +810,7 @@ int cbev_set_debug_flags(cbev_handle e, int32_t flags) {
 
 int cbev_debug_read_trace(cbev_handle e, uint64_t* host_out) {
   if (!e || !host_out) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   if (!e->trace) { cbev_set_error("tracing is off (set debug flag 4 first)"); return CBEV_ERR_STATE; }
   CU_TRY(cudaDeviceSynchronize());
   CU_TRY(cudaMemcpy(host_out, e->trace, (size_t)e->N * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -677,6 +825,7 @@ int cbev_keep_fov(cbev_handle e, int32_t on) {
 
 int cbev_copy_fov(cbev_handle e, uint8_t* fov_dev, void* stream) {
   if (!e || !fov_dev) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   if (!e->keep_fov) { cbev_set_error("palette frames are not kept: call cbev_keep_fov(h, 1) before stepping"); return CBEV_ERR_STATE; }
   size_t bytes = (size_t)e->N * e->cfg.fov_size * e->cfg.fov_size;
   CU_TRY(cudaMemcpyAsync(fov_dev, e->fov, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -685,6 +834,7 @@ int cbev_copy_fov(cbev_handle e, uint8_t* fov_dev, void* stream) {
 
 int cbev_read_stats(cbev_handle e, double* stats_dev, int32_t reset_after, void* stream) {
   if (!e || !stats_dev) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   cudaStream_t s = (cudaStream_t)stream;
   CU_TRY(cudaMemcpyAsync(stats_dev, e->gstats, CBEV_STATS_FIELDS * sizeof(double), cudaMemcpyDeviceToDevice, s));
   double steps = (double)e->steps * (double)e->N;
@@ -701,32 +851,43 @@ int64_t cbev_launch_count(cbev_handle e) { return e ? e->launches : -1; }
 
 int cbev_profile_enable(cbev_handle e, int32_t on) {
   if (!e) { cbev_set_error("null handle"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
   if (on && !e->prof_ev) {
-    e->prof_ev = new (std::nothrow) cudaEvent_t[3 * CBEV_PROF_MAX];
+    e->prof_ev = new (std::nothrow) cudaEvent_t[CBEV_PROF_EVENTS * CBEV_PROF_MAX];
     if (!e->prof_ev) return CBEV_ERR_NOMEM;
-    for (int i = 0; i < 3 * CBEV_PROF_MAX; ++i) CU_TRY(cudaEventCreate(&e->prof_ev[i]));
+    for (int i = 0; i < CBEV_PROF_EVENTS * CBEV_PROF_MAX; ++i) CU_TRY(cudaEventCreate(&e->prof_ev[i]));
   }
   e->profiling = on != 0;
   e->prof_n = 0;
   return CBEV_OK;
 }
 
-int cbev_profile_read(cbev_handle e, double* sim_ms, double* render_ms, int64_t* steps) {
-  if (!e || !sim_ms || !render_ms || !steps) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
-  double a = 0.0, b = 0.0;
+int cbev_profile_read_ex(cbev_handle e, double* move_ms, double* render_ms, double* judge_ms, int64_t* steps) {
+  if (!e || !move_ms || !render_ms || !judge_ms || !steps) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
+  double a = 0.0, b = 0.0, c = 0.0;
   if (e->prof_n > 0) CU_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < e->prof_n; ++i) {
-    float t0 = 0.f, t1 = 0.f;
-    CU_TRY(cudaEventElapsedTime(&t0, e->prof_ev[3 * i + 0], e->prof_ev[3 * i + 1]));
-    CU_TRY(cudaEventElapsedTime(&t1, e->prof_ev[3 * i + 1], e->prof_ev[3 * i + 2]));
+    const cudaEvent_t* pe = e->prof_ev + CBEV_PROF_EVENTS * i;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    CU_TRY(cudaEventElapsedTime(&t0, pe[0], pe[1]));
+    CU_TRY(cudaEventElapsedTime(&t1, pe[1], pe[2]));
+    CU_TRY(cudaEventElapsedTime(&t2, pe[3], pe[4]));
     a += t0;
     b += t1;
+    c += t2;
   }
-  *sim_ms = a;
+  *move_ms = a;
   *render_ms = b;
-  *steps = e->prof_n;  // kernel pairs timed (one per chunk per step)
+  *judge_ms = c;
+  *steps = e->prof_n;
   e->prof_n = 0;
   return CBEV_OK;
+}
+
+int cbev_profile_read(cbev_handle e, double* sim_ms, double* render_ms, int64_t* steps) {
+  double judge = 0.0;
+  return cbev_profile_read_ex(e, sim_ms, render_ms, &judge, steps);
 }
 
 int cbev_abi_sizes(int32_t* config_bytes, int32_t* pool_desc_bytes, int32_t* step_out_bytes) {

@@ -11,21 +11,28 @@
 
 #include "../../include/cbev.h"
 
-#define CBEV_MAX_TARGETS 64   // ego route points (targets) per scene, one visibility bit each
-#define CBEV_DESC_WORDS 16    // ints per render-descriptor header
+#define CBEV_TGT_WORDS 2      // 64-bit words of target-visibility bits per env
+#define CBEV_MAX_TARGETS (64 * CBEV_TGT_WORDS)  // ego route points (targets) per scene, one visibility bit each
+#define CBEV_RECT_WORDS 2     // draw-list entry: x0 | y0 << 16, (w - 1) | (h - 1) << 12 | palette << 24
+#define CBEV_DESC_WORDS 20    // ints per render-descriptor header
+#define CBEV_TILE_H 184       // rows of the class-map tile one frame can sample (fetch window, sim.cu:compute_view)
+#define CBEV_TILE_W 208       // tile pitch in bytes: window (<= 184) + 15 bytes of TMA alignment slack, rounded up to
+                              // an ODD number of 16-byte chunks (rows then rotate through the shared-memory banks)
 #define CBEV_WARPS_PER_BLOCK 4
 #define CBEV_PROF_MAX 2048
+#define CBEV_PROF_EVENTS 5     // per profiled step: before k_move, after k_move, after k_render, before / after k_judge
 
 // render descriptor header words
 enum {
-  RD_OX = 0,   // crop origin in MAP coordinates (xmin - pad), may be negative (TMA zero-fills = NON_DRIVABLE)
+  RD_OX = 0,   // fetch-window origin in MAP coordinates, may be negative (TMA zero-fills = NON_DRIVABLE)
   RD_OY,
   RD_MODE,     // 0: exact 90-degree turns, 1: 16.16 fixed-point walk
   RD_TURNS,
   RD_NX, RD_NY, RD_ISIN, RD_ICOS, RD_AX, RD_AY, RD_XD, RD_YD, RD_CY,
   RD_NRECTS,
-  RD_FLAGS,    // bit0: reset frame (fill every window slot)
-  RD_PAD
+  RD_FLAGS,    // bit0: reset frame (fill every window slot), bit1: skip this env (masked-out env of a partial reset)
+  RD_FX, RD_FY,  // fetch-window origin in CROP coordinates (rebases the rotate walk onto the tile)
+  RD_BG        // palette index of crop pixel (0, 0) after drawing = transform.rotate's background colour
 };
 
 struct EnvState {
@@ -33,9 +40,10 @@ struct EnvState {
   int32_t* episode = nullptr;      // [N] episodes finished by this env
   uint8_t* done = nullptr;         // [N] last step was terminal (needs reset)
   double* ego = nullptr;           // [N][24]: x,y,yaw,v,x1,y1,yaw1,v1,acc,t,dist2goal,dist2goal_1,s_prev,last_dyaw,
-                                   //          previous comfort (accel_long, accel_lat, yaw_rate), target speed (sim.cu E_*)
+                                   //          previous comfort (accel_long, accel_lat, yaw_rate), target speed,
+                                   //          decoded action + applied steering angle of the step (sim.cu E_*)
   int32_t* egoi = nullptr;         // [N][8]: tidx, flags(bit0 comfort valid, bit1 s_prev valid), k, consecutive_offroad, step
-  unsigned long long* tgt_vis = nullptr;  // [N]
+  unsigned long long* tgt_vis = nullptr;  // [N][CBEV_TGT_WORDS]
   double* stats = nullptr;         // [N][12]: return, length, sum speed, sum |comfort| x6, viol, harsh, cause
   // actors [N][max_actors]
   double *ax = nullptr, *ay = nullptr, *ayaw = nullptr, *av = nullptr, *atarget_mps = nullptr;
@@ -89,7 +97,7 @@ struct SimParams {
 struct cbev_engine {
   cbev_config cfg;
   int device = 0;
-  int32_t N = 0, crop = 0, pad = 0, anchor_x = 0, anchor_y = 0, box_w = 0;
+  int32_t N = 0, crop = 0, pad = 0, anchor_x = 0, anchor_y = 0;
   int32_t map_w = 0, map_h = 0;
   uint8_t* map = nullptr;
   alignas(64) unsigned char tmap[128];  // CUtensorMap of the class map
@@ -99,7 +107,7 @@ struct cbev_engine {
   int32_t max_rects = 0;
   int32_t debug_flags = 0;         // cbev_set_debug_flags
   int32_t* desc = nullptr;         // [N][CBEV_DESC_WORDS]
-  uint32_t* rects = nullptr;       // [N][max_rects]
+  uint32_t* rects = nullptr;       // [N][max_rects][CBEV_RECT_WORDS]
   uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)
   unsigned long long* trace = nullptr;  // [N][8] phase timestamps (debug flag 4)
   int32_t rs_mode = 0, rs_words = 0;  // CBEV_RS_*: how ResizeObservation is computed for this obs_size
@@ -114,23 +122,23 @@ struct cbev_engine {
   void* h_actions_dev = nullptr;
   double* h_reward_dev = nullptr;
   uint8_t *h_term_dev = nullptr, *h_trunc_dev = nullptr;
-  // cbev_step_host: the D2H copy of reward / flags runs on a side stream right after the sim kernel,
-  // overlapped with the raster kernel
+  // k_judge (reward / termination / statistics) and the D2H copies of cbev_step_host run on a high-priority side
+  // stream, overlapped with the raster kernel
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_sim = nullptr, ev_copy = nullptr;
-  void* host_out = nullptr;       // pending host destination(s) for the current step, or null
-  uint8_t *host_term = nullptr, *host_trunc = nullptr;
+  cudaEvent_t ev_sim = nullptr, ev_copy = nullptr, ev_judge = nullptr;
+  bool host_copy_pending = false;           // cbev_wait_host_outputs has something to wait for
   int64_t launches = 0;
   int64_t steps = 0;
   // per-kernel profiling (cbev_profile_enable)
   bool profiling = false;
-  cudaEvent_t* prof_ev = nullptr;  // [CBEV_PROF_MAX][3]
+  cudaEvent_t* prof_ev = nullptr;  // [CBEV_PROF_MAX][CBEV_PROF_EVENTS]
   int32_t prof_n = 0;
 };
 
 // kernels (sim.cu / render.cu)
 void cbev_launch_reset(cbev_engine* e, const uint8_t* mask, const int32_t* scene_ids, cudaStream_t s);
-void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, int lo, int hi, cudaStream_t s);
+void cbev_launch_move(cbev_engine* e, const void* actions, const cbev_step_out* out, int lo, int hi, cudaStream_t s);
+void cbev_launch_judge(cbev_engine* e, const cbev_step_out* out, int lo, int hi, cudaStream_t s);
 int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int hi, cudaStream_t s);
 void cbev_set_error(const char* fmt, ...);
 int cbev_launch_fuse(cbev_engine* e, int32_t mode, float* out, cudaStream_t s);

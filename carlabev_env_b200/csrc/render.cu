@@ -83,10 +83,10 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct RenderParams {
-  int32_t N, env_lo, fov, crop, box_w, anchor_x, anchor_y;
+  int32_t N, env_lo, fov, crop, anchor_x, anchor_y;
   int32_t frame_stack, ring_slots, head, mirror;  // mirror = slot offset (L - F + 1)
   int64_t frame_bytes;
-  int32_t tile_bytes, pad0;
+  int32_t pad0, pad1;
   const int32_t* desc;
   const uint32_t* rects;
   int32_t max_rects;
@@ -167,17 +167,23 @@ __device__ __forceinline__ uint32_t classify_key(uint32_t key, const uint32_t* s
   return (uint32_t)(int)g & 255u;
 }
 
+// The 128 x 128 palette-index frame lives in shared memory with its 16-byte chunks XOR-swizzled by the row
+// (chunk' = chunk ^ (row & 7)): the rotate writes 8-row x 16-px patches per warp, and with this layout those word
+// stores -- like every row-wise 16-byte read of the later phases -- hit 32 different banks.
+__device__ __forceinline__ int fov_word(int row, int cw) { return row * 32 + ((((cw >> 2) ^ row) & 7) << 2) + (cw & 3); }
+__device__ __forceinline__ int fov_byte(int row, int x) { return row * 128 + ((((x >> 4) ^ row) & 7) << 4) + (x & 15); }
+
 // GEN = false: the 128 -> 96 x 96 specialisation (4x4-block two-pass resize).  GEN = true: any obs_size <= 128 through
 // OpenCV's area tables (float32 accumulate in OpenCV's order), the 2x2 integer average for 64 x 64, or a copy for 128.
 template <int OBS_MODE, int CHANNELS, bool GEN>
 __global__ void __launch_bounds__(RT, 4)
 k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [tile: crop rows x box_w | re-used as: 96x96 output bytes + mixed-block worklist / RGB staging]
-  //         [fov 128x128] [tables] [mbar]
+  // layout: [tile: CBEV_TILE_H rows x CBEV_TILE_W | re-used as: 96x96 output bytes + mixed-block worklist / RGB staging
+  //          (which runs on into the fov region)] [fov 128x128, swizzled] [tables] [mbar] [draw list]
   constexpr int S = 128;
-  const int crop = P.crop, pitch = P.box_w;
-  const int tile_bytes = P.tile_bytes;
+  constexpr int pitch = CBEV_TILE_W;
+  constexpr int tile_bytes = CBEV_TILE_W * CBEV_TILE_H;
   uint8_t* s_tile = smem;
   uint8_t* const s_region = smem;  // start of the tile region (16-byte aligned), re-used after the rotate
   uint8_t* s_fov = smem + tile_bytes;
@@ -189,10 +195,11 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   uint8_t* s_cm = (uint8_t*)(s_bar + 2);     // channel bits per palette index for this mask mode
   float4* s_lut = (float4*)(s_cm + 16);      // 16 x float4: 4 mask bits -> four 0.0f / 1.0f values
   int* s_count = (int*)(s_lut + 16);
-  uint32_t* s_rects = (uint32_t*)(s_count + 4);  // draw list (max_rects words); the resize tables follow (GEN)
+  uint32_t* s_rects = (uint32_t*)(s_count + 4);  // draw list (max_rects x 2 words); the resize tables follow (GEN)
 
   const int env = P.env_lo + blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
   const int flags = d[RD_FLAGS];
   if (flags & 2) return;  // masked-out env of a partial reset
@@ -201,9 +208,9 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(s_bar, (uint32_t)(crop * pitch));
+    mbar_expect_tx(s_bar, (uint32_t)tile_bytes);
     // the TMA unit needs a 16-byte aligned inner coordinate (measured on B200: an unaligned x raises
-    // "illegal instruction"), so fetch the aligned superset [ox & ~15, +box_w) and index it with +shift
+    // "illegal instruction"), so fetch the aligned superset [ox & ~15, +CBEV_TILE_W) and index it with +shift
     tma_load_2d(s_tile, &tmap, d[RD_OX] & ~15, d[RD_OY], s_bar);
     *s_count = 0;
   }
@@ -222,57 +229,62 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   const int nrects = d[RD_NRECTS];
   {
     // speculative: every slot of the list is fetched without waiting for the count (no dependent load)
-    const uint32_t* rl = P.rects + (size_t)env * P.max_rects;
-    for (int r = tid; r < P.max_rects; r += RT) s_rects[r] = rl[r];
+    const uint32_t* rl = P.rects + (size_t)env * P.max_rects * CBEV_RECT_WORDS;
+    for (int r = tid; r < P.max_rects * CBEV_RECT_WORDS; r += RT) s_rects[r] = rl[r];
   }
   __syncthreads();
   mbar_wait(s_bar, 0);
-  s_tile += s_desc[RD_OX] & 15;  // crop pixel (x, y) lives at s_tile[y * pitch + x]
+  s_tile += s_desc[RD_OX] & 15;  // fetch-window pixel (x, y) lives at s_tile[y * pitch + x]
   trace_mark(P, env, 1);
 
   // ---- 2. draw list, in order (later rects overwrite earlier ones) ----
-  // Runs of consecutive rects with the same colour (the route targets are one long run) are painted in parallel,
-  // one rect per lane: overlapping rects of one run write the same value, so their order does not matter; runs
-  // follow each other in list order, which is all "later overwrites earlier" needs.
+  // Runs of consecutive rects with the same colour (all vehicles, all pedestrians, the route targets) are painted in
+  // parallel, one rect per thread: overlapping rects of one run write the same value, so their order does not matter;
+  // runs follow each other in list order, which is all "later overwrites earlier" needs.
   if (nrects > 0) {
-    if (tid < 32) {
-      int r = 0;
-      while (r < nrects) {
-        const uint32_t pal = s_rects[r] >> 28;
-        int e = r;
-        for (;;) {  // end of the run that starts at r
-          const int idx = e + tid;
-          const unsigned same = __ballot_sync(0xffffffffu, idx < nrects && (s_rects[idx] >> 28) == pal);
-          if (same == 0xffffffffu) { e += 32; continue; }
-          e += __ffs(~same) - 1;
-          break;
-        }
-        for (int q = r + tid; q < e; q += 32) {
-          const uint32_t pk = s_rects[q];
-          const int x0 = pk & 255, y0 = (pk >> 8) & 255, w = ((pk >> 16) & 63) + 1, h = ((pk >> 22) & 63) + 1;
-          uint8_t* row = s_tile + y0 * pitch + x0;
-          for (int yy = 0; yy < h; ++yy, row += pitch)
-            for (int xx = 0; xx < w; ++xx) row[xx] = (uint8_t)pal;
-        }
-        __syncwarp();
-        r = e;
+    int r = 0;
+    while (r < nrects) {  // r, e are uniform over the CTA: every warp scans the run boundaries itself
+      const uint32_t pal = s_rects[2 * r + 1] >> 24;
+      int e = r;
+      for (;;) {  // end of the run that starts at r
+        const int idx = e + lane;
+        const unsigned same = __ballot_sync(0xffffffffu, idx < nrects && (s_rects[2 * idx + 1] >> 24) == pal);
+        if (same == 0xffffffffu) { e += 32; continue; }
+        e += __ffs(~same) - 1;
+        break;
       }
+      for (int q = r + tid; q < e; q += RT) {
+        const uint32_t w0 = s_rects[2 * q], w1 = s_rects[2 * q + 1];
+        const int x0 = w0 & 0xffff, y0 = w0 >> 16, w = (w1 & 0xfff) + 1, h = ((w1 >> 12) & 0xfff) + 1;
+        uint8_t* row = s_tile + y0 * pitch + x0;
+        for (int yy = 0; yy < h; ++yy, row += pitch)
+          for (int xx = 0; xx < w; ++xx) row[xx] = (uint8_t)pal;
+      }
+      r = e;
+      __syncthreads();
     }
     trace_mark(P, env, 7);
-    __syncthreads();
   }
 
   trace_mark(P, env, 2);
   // ---- 3. rotate + compose + ego square -> 128x128 palette-index FOV ----
+  // Thread mapping: a warp covers 16-px x 8-row patches (lane = 4 px of one row: lx = lane & 3, ly = lane >> 2).  With
+  // the tile pitch an odd number of 16-byte chunks, the 32 byte-gathers of one instruction spread over the banks for
+  // every heading (<= 2-way, against up to 28-way for a warp walking one 128-px row: cars mostly drive along the axes,
+  // which is exactly the worst case of a row walk).
   {
     const int mode = s_desc[RD_MODE], turns = s_desc[RD_TURNS];
     const int nx = s_desc[RD_NX], ny = s_desc[RD_NY];
     const int isin = s_desc[RD_ISIN], icos = s_desc[RD_ICOS];
     const int rax = s_desc[RD_AX] + s_desc[RD_XD], ray = s_desc[RD_AY] + s_desc[RD_YD], rcy = s_desc[RD_CY];
     const int left = P.anchor_x - (nx >> 1), top = P.anchor_y - (ny >> 1);  // get_rect(center=anchor)
+    const int crop = P.crop;
     const int lim = (crop << 16) - 1;
-    const uint8_t bg = s_tile[0];  // transform.rotate background = source's first pixel
+    const uint32_t bg = (uint32_t)s_desc[RD_BG];  // transform.rotate background = source's first pixel
     const int ex0 = P.anchor_x - 2, ey0 = P.anchor_y - 2;
+    // crop pixel (sx, sy) = tile0[sy * pitch + sx]
+    const uint8_t* tile0 = s_tile - s_desc[RD_FY] * pitch - s_desc[RD_FX];
+    const int lx = lane & 3, ly = lane >> 2;
     // The crop is sized so that the 128x128 window normally lies inside the rotated surface and inside the
     // source range of the fixed-point walk.  Both facts are linear in (x, y): checking the four window corners
     // proves them for every pixel, which removes all per-pixel range tests (the generic loop remains for the rest).
@@ -285,29 +297,34 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
         fast = fast && dx >= 0 && dy >= 0 && dx <= lim && dy <= lim;
       }
     }
+    uint32_t* fov32 = (uint32_t*)s_fov;
     if (fast && mode == 1) {
-      // 16 samples (4 words of 4 pixels) per iteration: all loads are issued before the first store, so the
-      // shared-memory latency is paid once per 16 pixels instead of once per 4 (tile and fov may alias for the compiler)
-      for (int u0 = tid; u0 < S * S / 4; u0 += 4 * RT) {
+      // 16 samples (4 patches) per iteration: all loads are issued before the first store, so the shared-memory
+      // latency is paid once per 16 pixels instead of once per 4 (tile and fov may alias for the compiler)
+#pragma unroll 1
+      for (int i0 = 0; i0 < 16; i0 += 4) {
         uint32_t packed[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int u = u0 + g * RT;
-          const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+          const int p = warp * 16 + i0 + g;
+          const int oy = (p >> 3) * 8 + ly, ox0 = (p & 7) * 16 + lx * 4;
           const int ryp = oy - top, rxp = ox0 - left;
           int dx = rax + isin * (rcy - ryp) + rxp * icos;
           int dy = ray - icos * (rcy - ryp) + rxp * isin;
           uint32_t pk = 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            pk |= (uint32_t)s_tile[(dy >> 16) * pitch + (dx >> 16)] << (8 * k);
+            pk |= (uint32_t)tile0[(dy >> 16) * pitch + (dx >> 16)] << (8 * k);
             dx += icos;
             dy += isin;
           }
           packed[g] = pk;
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ((uint32_t*)s_fov)[u0 + g * RT] = packed[g];
+        for (int g = 0; g < 4; ++g) {
+          const int p = warp * 16 + i0 + g;
+          fov32[fov_word((p >> 3) * 8 + ly, (p & 7) * 4 + lx)] = packed[g];
+        }
       }
     } else if (fast) {
       // exact 90-degree turns (rotate90): src = base + x * step_x + y * step_y
@@ -317,15 +334,18 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       else if (turns == 2) { base = (crop - 1) * pitch + crop - 1; stepx = -1; stepy = -pitch; }
       else { base = (crop - 1) * pitch; stepx = -pitch; stepy = 1; }
       base += -left * stepx - top * stepy;
-      for (int u = tid; u < S * S / 4; u += RT) {
-        const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int p = warp * 16 + i;
+        const int oy = (p >> 3) * 8 + ly, ox0 = (p & 7) * 16 + lx * 4;
         const int a = base + ox0 * stepx + oy * stepy;
-        ((uint32_t*)s_fov)[u] = (uint32_t)s_tile[a] | ((uint32_t)s_tile[a + stepx] << 8) |
-                                ((uint32_t)s_tile[a + 2 * stepx] << 16) | ((uint32_t)s_tile[a + 3 * stepx] << 24);
+        fov32[fov_word(oy, ox0 >> 2)] = (uint32_t)tile0[a] | ((uint32_t)tile0[a + stepx] << 8) |
+                                         ((uint32_t)tile0[a + 2 * stepx] << 16) | ((uint32_t)tile0[a + 3 * stepx] << 24);
       }
     } else {
-      for (int u = tid; u < S * S / 4; u += RT) {
-        const int oy = u / (S / 4), ox0 = (u % (S / 4)) * 4;
+      for (int i = 0; i < 16; ++i) {
+        const int p = warp * 16 + i;
+        const int oy = (p >> 3) * 8 + ly, ox0 = (p & 7) * 16 + lx * 4;
         const int ryp = oy - top;
         const bool row_in = ryp >= 0 && ryp < ny;
         const int bx = rax + isin * (rcy - ryp);
@@ -342,16 +362,16 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
               else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
               else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
               else { sx = ryp; sy = crop - 1 - rxp; }
-              v = s_tile[sy * pitch + sx];
+              v = tile0[sy * pitch + sx];
             } else {
               int dx = bx + rxp * icos, dy = by + rxp * isin;
               if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
-              else v = s_tile[(dy >> 16) * pitch + (dx >> 16)];
+              else v = tile0[(dy >> 16) * pitch + (dx >> 16)];
             }
           }
           packed |= v << (8 * k);
         }
-        ((uint32_t*)s_fov)[u] = packed;
+        fov32[fov_word(oy, ox0 >> 2)] = packed;
       }
     }
     __syncthreads();
@@ -359,7 +379,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     if (P.fov_mask != nullptr) {
       for (int u = tid; u < S * S / 4; u += RT) {
         const uint32_t mk = ((const uint32_t*)P.fov_mask)[u];
-        uint32_t* px = (uint32_t*)s_fov + u;
+        uint32_t* px = fov32 + fov_word(u >> 5, u & 31);
         *px = (*px & ~mk) | ((CBEV_PAL_BLACK * 0x01010101u) & mk);
       }
       __syncthreads();
@@ -367,14 +387,14 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     // Hero.draw: 4x4 black square centred on the anchor (hero.py:26-32), clipped to the surface
     if (tid < 16) {
       const int x = ex0 + (tid & 3), y = ey0 + (tid >> 2);
-      if (x >= 0 && x < S && y >= 0 && y < S) s_fov[y * S + x] = CBEV_PAL_BLACK;
+      if (x >= 0 && x < S && y >= 0 && y < S) s_fov[fov_byte(y, x)] = CBEV_PAL_BLACK;
     }
   }
   __syncthreads();
   trace_mark(P, env, 3);
   if (P.fov_out != nullptr) {
     uint4* dst = (uint4*)(P.fov_out + (size_t)env * S * S);
-    for (int u = tid; u < S * S / 16; u += RT) dst[u] = ((const uint4*)s_fov)[u];
+    for (int u = tid; u < S * S / 16; u += RT) dst[u] = *(const uint4*)(s_fov + fov_byte(u >> 3, (u & 7) << 4));
   }
 
   // which ring slots receive this frame: the head slot, or every window slot for a reset frame,
@@ -383,10 +403,20 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   const int first = (flags & 1) ? P.head - F + 1 : P.head;
 
   if (OBS_MODE == CBEV_OBS_RGB) {
-    // raw render(): (S, S, 3) uint8, staged through shared memory for 16-byte coalesced stores
+    // raw render(): (S, S, 3) uint8, staged through shared memory for 16-byte coalesced stores.  The staging area
+    // (48 KB) starts at the dead tile and runs on into the frame itself, so the frame is pulled into registers first.
+    uint32_t f[S * S / 4 / RT];
+#pragma unroll
+    for (int i = 0; i < S * S / 4 / RT; ++i) {
+      const int u = tid + i * RT;
+      f[i] = ((const uint32_t*)s_fov)[fov_word(u >> 5, u & 31)];
+    }
+    __syncthreads();
     uint8_t* s_rgb = s_region;
-    for (int u = tid; u < S * S / 4; u += RT) {  // 4 pixels -> 12 bytes = 3 words
-      const uint32_t p4 = ((const uint32_t*)s_fov)[u];
+#pragma unroll
+    for (int i = 0; i < S * S / 4 / RT; ++i) {  // 4 pixels -> 12 bytes = 3 words
+      const int u = tid + i * RT;
+      const uint32_t p4 = f[i];
       const uint32_t k0 = s_key[p4 & 255u], k1 = s_key[(p4 >> 8) & 255u], k2 = s_key[(p4 >> 16) & 255u],
                      k3 = s_key[p4 >> 24];
       uint32_t* o = (uint32_t*)s_rgb + 3 * u;
@@ -404,7 +434,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   uint8_t* s_out = s_region;                        // OH x OW bytes: channel bitmask (semantic) or gray level
   if (GEN) {
     // ---- 4g. cv2.resize(INTER_AREA) for any obs_size <= 128 (ResizeObservation, envs/__init__.py:62) ----
-    int32_t* s_tab = (int32_t*)(s_rects + ((P.max_rects + 3) & ~3));
+    int32_t* s_tab = (int32_t*)(s_rects + ((P.max_rects * CBEV_RECT_WORDS + 3) & ~3));
     for (int u = tid; u < P.rs_words; u += RT) s_tab[u] = P.rs_tab[u];
     __syncthreads();
     const int nx = s_tab[0], ny = s_tab[1];
@@ -418,11 +448,12 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       const int dy = o / OW, dx = o - dy * OW;
       uint32_t key;
       if (P.rs_mode == CBEV_RS_COPY) {
-        key = s_key[s_fov[dy * S + dx]];
+        key = s_key[s_fov[fov_byte(dy, dx)]];
       } else if (P.rs_mode == CBEV_RS_HALF) {
         // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
-        const uint8_t* q = s_fov + 2 * dy * S + 2 * dx;
-        const uint32_t c0 = q[0], c1 = q[1], c2 = q[S], c3 = q[S + 1];
+        const uint8_t* q0 = s_fov + fov_byte(2 * dy, 2 * dx);
+        const uint8_t* q1 = s_fov + fov_byte(2 * dy + 1, 2 * dx);
+        const uint32_t c0 = q0[0], c1 = q0[1], c2 = q1[0], c3 = q1[1];
         const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
         const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
         key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
@@ -431,10 +462,10 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
         float sr = 0.f, sg = 0.f, sb = 0.f;
         const int y0 = yoff[dy], y1 = yoff[dy + 1], x0 = xoff[dx], x1 = xoff[dx + 1];
         for (int j = y0; j < y1; ++j) {
-          const uint8_t* row = s_fov + ysi[j] * S;
+          const int srow = ysi[j];
           float br = 0.f, bg = 0.f, bb = 0.f;
           for (int k = x0; k < x1; ++k) {
-            const uint32_t kk = s_key[row[xsi[k]]];
+            const uint32_t kk = s_key[s_fov[fov_byte(srow, xsi[k])]];
             const float a = xal[k];
             br = __fadd_rn(br, __fmul_rn((float)(kk & 255u), a));
             bg = __fadd_rn(bg, __fmul_rn((float)((kk >> 8) & 255u), a));
@@ -463,7 +494,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     const int br = tid >> 3, j = tid & 7;  // 32 block rows x 8 strips of 4 blocks (RT == 256)
     uint4 R[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) R[i] = *(const uint4*)(s_fov + (4 * br + i) * S + 16 * j);
+    for (int i = 0; i < 4; ++i) R[i] = *(const uint4*)(s_fov + fov_byte(4 * br + i, 16 * j));
     uint32_t m[4];
     uint32_t mixed = 0;
 #pragma unroll
@@ -503,8 +534,9 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       const int blk = s_list[idx / 9], px = idx % 9;
       const int i = px / 3, jj = px % 3;
       const int bry = blk >> 5, bcx = blk & 31;
-      const uint8_t* src = s_fov + (4 * bry + i) * S + 4 * bcx + jj;
-      const uint32_t res = resolve_px<OBS_MODE>(src[0], src[1], src[S], src[S + 1], 3 - jj, 1 + jj, 3 - i, 1 + i, s_rg,
+      const uint8_t* src0 = s_fov + fov_byte(4 * bry + i, 4 * bcx + jj);      // the 2x2 taps stay inside one 4-px block
+      const uint8_t* src1 = s_fov + fov_byte(4 * bry + i + 1, 4 * bcx + jj);
+      const uint32_t res = resolve_px<OBS_MODE>(src0[0], src0[1], src1[0], src1[1], 3 - jj, 1 + jj, 3 - i, 1 + i, s_rg,
                                                 s_b, s_key, s_cm);
       s_out[(3 * bry + i) * O + 3 * bcx + jj] = (uint8_t)res;
     }
@@ -614,7 +646,9 @@ k_fuse(const float* __restrict__ ring, float* __restrict__ out, int N, int L, in
   }
 }
 
-bool g_tables_ready = false;
+// per-device state: the constant tables and the dynamic shared-memory opt-in belong to a device / context
+constexpr int MAX_DEVICES = 64;
+bool g_tables_ready[MAX_DEVICES] = {};
 
 void upload_tables() {
   static const uint8_t pal[CBEV_PAL_COUNT][3] = {{150, 150, 150}, {255, 255, 255}, {220, 220, 220}, {0, 7, 175},
@@ -648,10 +682,11 @@ void upload_tables() {
 template <int MODE, int CH, bool GEN>
 int launch2(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
   auto kern = k_render<MODE, CH, GEN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[MAX_DEVICES] = {};
+  const int dev = e->device >= 0 && e->device < MAX_DEVICES ? e->device : 0;
+  if (!attr_done[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return 1;
-    attr_done = true;
+    attr_done[dev] = true;
   }
   kern<<<P.N, RT, smem, s>>>(P, *reinterpret_cast<const CUtensorMap*>(e->tmap), e->cfg.mask_mode);
   return 0;
@@ -666,16 +701,18 @@ int launch(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
 }  // namespace
 
 int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int hi, cudaStream_t s) {
-  if (!g_tables_ready) {
-    upload_tables();
-    g_tables_ready = true;
+  {
+    const int dev = e->device >= 0 && e->device < MAX_DEVICES ? e->device : 0;
+    if (!g_tables_ready[dev]) {
+      upload_tables();
+      g_tables_ready[dev] = true;
+    }
   }
   RenderParams P;
   P.N = hi - lo;
   P.env_lo = lo;
   P.fov = e->cfg.fov_size;
   P.crop = e->crop;
-  P.box_w = e->box_w;
   P.anchor_x = e->anchor_x;
   P.anchor_y = e->anchor_y;
   P.frame_stack = e->cfg.frame_stack;
@@ -690,12 +727,8 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.fov_mask = e->fov_mask;
   P.ring = e->ring;
   const int S = P.fov;
-  size_t tile = (size_t)P.crop * P.box_w;
-  if (e->cfg.obs_mode == CBEV_OBS_RGB && tile < (size_t)S * S * 3) tile = (size_t)S * S * 3;  // RGB staging
-  if (tile < 96 * 96 + 2 * 12288) tile = 96 * 96 + 2 * 12288;  // output bytes + worklist / 2 x 12 KB store staging
-  if (tile < (size_t)e->cfg.obs_h * e->cfg.obs_w) tile = (size_t)e->cfg.obs_h * e->cfg.obs_w;
-  tile = ((tile + 127) / 128) * 128;
-  P.tile_bytes = (int32_t)tile;
+  const size_t tile = (size_t)CBEV_TILE_W * CBEV_TILE_H;  // >= 96*96 + 2*12288 (staging), >= any obs_h * obs_w <= 128^2
+  P.pad1 = 0;
   P.pad0 = e->debug_flags;  // bit0: force the generic (range-tested) rotate path
   P.obs_h = e->cfg.obs_h;
   P.obs_w = e->cfg.obs_w;
@@ -704,7 +737,8 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.rs_tab = e->rs_tab;
   P.trace = (e->debug_flags & 4) ? e->trace : nullptr;
   size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16 +
-                (size_t)((e->max_rects + 3) & ~3) * 4 + (e->rs_mode == CBEV_RS_FAST96 ? 0 : (size_t)e->rs_words * 4);
+                (size_t)((e->max_rects * CBEV_RECT_WORDS + 3) & ~3) * 4 +
+                (e->rs_mode == CBEV_RS_FAST96 ? 0 : (size_t)e->rs_words * 4);
   int rc = 1;
   if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, s);
   else if (e->cfg.obs_mode == CBEV_OBS_GRAY) rc = launch<CBEV_OBS_GRAY, 1>(e, P, smem, s);

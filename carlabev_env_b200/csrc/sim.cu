@@ -14,6 +14,7 @@
 // double (NumPy / CPython scalars), so no contraction is allowed here.  Lanes of a warp run the
 // scalar ego / reward arithmetic redundantly (uniform), and split route points, actors and
 // targets between them; collisions and termination are resolved with warp ballots.
+#include <limits.h>
 #include <math.h>
 
 #include "engine.h"
@@ -39,7 +40,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // ego double slots
 enum { E_X = 0, E_Y, E_YAW, E_V, E_X1, E_Y1, E_YAW1, E_V1, E_ACC, E_T, E_D2G, E_D2G1, E_SPREV, E_LAST_DYAW,
-       E_PC_AL, E_PC_AT, E_PC_YR, E_TARGET, E_SLOTS = 24 };
+       E_PC_AL, E_PC_AT, E_PC_YR, E_TARGET, E_GAS, E_STEER, E_BRAKE, E_DELTA, E_SLOTS = 24 };
 enum { I_TIDX = 0, I_FLAGS, I_K, I_OFFROAD, I_STEP, I_SLOTS = 8 };
 enum { S_RET = 0, S_LEN, S_SPEED, S_C0, S_VIOL = 9, S_HARSH, S_CAUSE, S_SLOTS = 12 };
 enum { FL_COMFORT = 1, FL_SPREV = 2 };
@@ -130,18 +131,26 @@ __device__ __forceinline__ void body_update(Body& b, double acc, double delta, d
 }
 
 // ---- render descriptor -------------------------------------------------------------------------
-__device__ void write_desc_header(const SimParams& P, int32_t* __restrict__ d, double x, double y, double theta,
-                                  int nrects, int flags) {
+// Camera + pygame.transform.rotate parameters of one frame, and the FETCH WINDOW: the bounding box (in crop
+// coordinates) of the source texels the 128 x 128 view can sample.  The view is an affine image of a 128-px square,
+// so whatever the crop size (182 px for the centred camera, 230 px for lookahead_75, up to 360 px for a corner
+// anchor) the box is at most ceil(128 * sqrt(2)) + 2 = 183 px on a side: the raster kernel fetches a constant
+// CBEV_TILE_H x CBEV_TILE_W tile for every configuration.
+struct View {
+  int xmin, ymin;  // crop origin on the padded scene surface
+  int mode, turns, nx, ny, isin, icos, ax, ay, xd, yd, cy;
+  int fx, fy, bw, bh;  // fetch window inside the crop
+};
+
+__device__ void compute_view(const SimParams& P, double x, double y, double theta, View& v) {
   // Follow.scroll + compute_crop_rect: camera.py:39-42, world.py:105-111, fov.py:70-79
   const int crop = P.crop, pad = P.pad;
   int offx = (int)(((double)pad + x * 1.0) + (-(double)crop / 2.0));
   int offy = (int)(((double)pad + y * 1.0) + (-(double)crop / 2.0));
   int cx = (int)rint((double)offx + (double)crop / 2.0);
   int cy = (int)rint((double)offy + (double)crop / 2.0);
-  int xmin = max(0, min(max(0, P.map_w + 2 * pad - crop), cx - crop / 2));
-  int ymin = max(0, min(max(0, P.map_h + 2 * pad - crop), cy - crop / 2));
-  d[RD_OX] = xmin - pad;
-  d[RD_OY] = ymin - pad;
+  v.xmin = max(0, min(max(0, P.map_w + 2 * pad - crop), cx - crop / 2));
+  v.ymin = max(0, min(max(0, P.map_h + 2 * pad - crop), cy - crop / 2));
   // pygame.transform.rotate(crop, degrees(yaw) + 90): fov.py:84-88, SURVEY.md A.6
   float anglef = (float)(theta * RAD2DEG + 90.0);
   double angle = (double)anglef;
@@ -149,11 +158,10 @@ __device__ void write_desc_header(const SimParams& P, int32_t* __restrict__ d, d
     int a = (int)angle;
     int turns = (a / 90) % 4;
     if (turns < 0) turns += 4;
-    d[RD_MODE] = 0;
-    d[RD_TURNS] = turns;
-    d[RD_NX] = crop;
-    d[RD_NY] = crop;
-    d[RD_ISIN] = d[RD_ICOS] = d[RD_AX] = d[RD_AY] = d[RD_XD] = d[RD_YD] = d[RD_CY] = 0;
+    v.mode = 0;
+    v.turns = turns;
+    v.nx = v.ny = crop;
+    v.isin = v.icos = v.ax = v.ay = v.xd = v.yd = v.cy = 0;
   } else {
     double rad = angle * 0.01745329251994329;
     double s = sin(rad), c = cos(rad);
@@ -161,31 +169,89 @@ __device__ void write_desc_header(const SimParams& P, int32_t* __restrict__ d, d
     double cxx = c * w, cyy = c * h, sx = s * w, sy = s * h;
     int nx = (int)fmax(fmax(fmax(fabs(cxx + sy), fabs(cxx - sy)), fabs(-cxx + sy)), fabs(-cxx - sy));
     int ny = (int)fmax(fmax(fmax(fabs(sx + cyy), fabs(sx - cyy)), fabs(-sx + cyy)), fabs(-sx - cyy));
-    d[RD_MODE] = 1;
-    d[RD_TURNS] = 0;
-    d[RD_NX] = nx;
-    d[RD_NY] = ny;
-    d[RD_ISIN] = (int)(s * 65536.0);
-    d[RD_ICOS] = (int)(c * 65536.0);
-    d[RD_AX] = (nx << 15) - (int)(c * (double)((nx - 1) << 15));
-    d[RD_AY] = (ny << 15) - (int)(s * (double)((nx - 1) << 15));
-    d[RD_XD] = (crop - nx) * 32768;
-    d[RD_YD] = (crop - ny) * 32768;
-    d[RD_CY] = ny / 2;
+    v.mode = 1;
+    v.turns = 0;
+    v.nx = nx;
+    v.ny = ny;
+    v.isin = (int)(s * 65536.0);
+    v.icos = (int)(c * 65536.0);
+    v.ax = (nx << 15) - (int)(c * (double)((nx - 1) << 15));
+    v.ay = (ny << 15) - (int)(s * (double)((nx - 1) << 15));
+    v.xd = (crop - nx) * 32768;
+    v.yd = (crop - ny) * 32768;
+    v.cy = ny / 2;
   }
-  d[RD_NRECTS] = nrects;
-  d[RD_FLAGS] = flags;
-  d[RD_PAD] = 0;
+  // fetch window: source texel of the four corners of the view (the map view -> source is affine, floor is monotone)
+  const int S = P.fov;
+  const int left = P.anchor_x - (v.nx >> 1), top = P.anchor_y - (v.ny >> 1);  // get_rect(center=anchor), fov.py:88-94
+  int x_lo = INT_MAX, x_hi = INT_MIN, y_lo = INT_MAX, y_hi = INT_MIN;
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const int rxp = ((c4 & 1) ? S - 1 : 0) - left, ryp = ((c4 & 2) ? S - 1 : 0) - top;
+    int sx, sy;
+    if (v.mode == 0) {
+      if (v.turns == 0) { sx = rxp; sy = ryp; }
+      else if (v.turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
+      else if (v.turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
+      else { sx = ryp; sy = crop - 1 - rxp; }
+    } else {
+      sx = ((v.ax + v.xd) + v.isin * (v.cy - ryp) + rxp * v.icos) >> 16;
+      sy = ((v.ay + v.yd) - v.icos * (v.cy - ryp) + rxp * v.isin) >> 16;
+    }
+    x_lo = min(x_lo, sx); x_hi = max(x_hi, sx);
+    y_lo = min(y_lo, sy); y_hi = max(y_hi, sy);
+  }
+  x_lo = max(x_lo, 0); y_lo = max(y_lo, 0);
+  x_hi = min(x_hi, crop - 1); y_hi = min(y_hi, crop - 1);
+  if (x_hi < x_lo || y_hi < y_lo) { x_lo = y_lo = 0; x_hi = y_hi = 0; }  // the view misses the crop: nothing is sampled
+  v.fx = x_lo;
+  v.fy = y_lo;
+  v.bw = min(x_hi - x_lo + 1, CBEV_TILE_H);  // <= 183 by the bound above
+  v.bh = min(y_hi - y_lo + 1, CBEV_TILE_H);
 }
 
-// clip a scene-surface rect to the crop window and pack it; returns false if empty
-__device__ __forceinline__ bool pack_rect(int rx, int ry, int rw, int rh, int pal, int xmin, int ymin, int crop,
-                                          uint32_t& out) {
-  int x0 = max(rx - xmin, 0), y0 = max(ry - ymin, 0);
-  int x1 = min(rx + rw - xmin, crop), y1 = min(ry + rh - ymin, crop);
+__device__ void write_desc_header(const SimParams& P, int32_t* __restrict__ d, const View& v, int nrects, int flags,
+                                  int bg) {
+  d[RD_OX] = v.xmin + v.fx - P.pad;  // fetch-window origin in MAP coordinates (may be negative: TMA zero-fills)
+  d[RD_OY] = v.ymin + v.fy - P.pad;
+  d[RD_MODE] = v.mode;
+  d[RD_TURNS] = v.turns;
+  d[RD_NX] = v.nx;
+  d[RD_NY] = v.ny;
+  d[RD_ISIN] = v.isin;
+  d[RD_ICOS] = v.icos;
+  d[RD_AX] = v.ax;
+  d[RD_AY] = v.ay;
+  d[RD_XD] = v.xd;
+  d[RD_YD] = v.yd;
+  d[RD_CY] = v.cy;
+  d[RD_NRECTS] = nrects;
+  d[RD_FLAGS] = flags;
+  d[RD_FX] = v.fx;
+  d[RD_FY] = v.fy;
+  d[RD_BG] = bg;
+}
+
+// palette index of crop pixel (0, 0) of the bare map: transform.rotate's background colour is the source surface's
+// first pixel; rectangles drawn over it are accounted for by the caller
+__device__ __forceinline__ int crop_corner_class(const SimParams& P, const View& v) {
+  const int mx = v.xmin - P.pad, my = v.ymin - P.pad;
+  if (mx < 0 || my < 0 || mx >= P.map_w || my >= P.map_h) return CBEV_PAL_NON_DRIVABLE;  // padding colour
+  return P.map[(size_t)my * P.map_w + mx];
+}
+
+// clip a scene-surface rect to the fetch window and pack it (CBEV_RECT_WORDS = 2 words:
+// x0 | y0 << 16, (w - 1) | (h - 1) << 12 | palette << 24, window coordinates); returns false if nothing is left.
+// `covers00` reports whether the rect covers crop pixel (0, 0), the rotate background sample.
+__device__ __forceinline__ bool pack_rect(int rx, int ry, int rw, int rh, int pal, const View& v, uint32_t& w0,
+                                          uint32_t& w1, bool& covers00) {
+  covers00 = rx <= v.xmin && v.xmin < rx + rw && ry <= v.ymin && v.ymin < ry + rh;
+  const int wx = v.xmin + v.fx, wy = v.ymin + v.fy;
+  int x0 = max(rx - wx, 0), y0 = max(ry - wy, 0);
+  int x1 = min(rx + rw - wx, v.bw), y1 = min(ry + rh - wy, v.bh);
   if (x1 <= x0 || y1 <= y0) return false;
-  int w = min(x1 - x0, 64), h = min(y1 - y0, 64);
-  out = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)(w - 1) << 16) | ((uint32_t)(h - 1) << 22) | ((uint32_t)pal << 28);
+  w0 = (uint32_t)x0 | ((uint32_t)y0 << 16);
+  w1 = (uint32_t)(x1 - x0 - 1) | ((uint32_t)(y1 - y0 - 1) << 12) | ((uint32_t)pal << 24);
   return true;
 }
 
@@ -242,7 +308,10 @@ __device__ void reset_env(const SimParams& P, const PoolDev& pool, const EnvStat
     ei[I_STEP] = 0;
     st.scene[env] = scene;
     st.done[env] = 0;
-    st.tgt_vis[env] = nt >= 64 ? ~0ull : ((1ull << nt) - 1ull);
+    for (int w = 0; w < CBEV_TGT_WORDS; ++w) {
+      const int n = nt - 64 * w;
+      st.tgt_vis[(size_t)env * CBEV_TGT_WORDS + w] = n >= 64 ? ~0ull : (n > 0 ? ((1ull << n) - 1ull) : 0ull);
+    }
     double* sa = st.stats + (size_t)env * S_SLOTS;
     for (int k = 0; k < S_SLOTS; ++k) sa[k] = 0.0;
   }
@@ -265,7 +334,9 @@ k_reset(SimParams P, PoolDev pool, EnvState st, const uint8_t* __restrict__ mask
   if (lane == 0) {
     const double* s0 = pool.ego_state0 + (size_t)scene * 4;
     // BaseMap.reset draws the bare map with _theta = 0.0 and no actors (world.py:92-100)
-    write_desc_header(P, desc + (size_t)env * CBEV_DESC_WORDS, s0[0], s0[1], 0.0, 0, 1);
+    View v;
+    compute_view(P, s0[0], s0[1], 0.0, v);
+    write_desc_header(P, desc + (size_t)env * CBEV_DESC_WORDS, v, 0, 1, crop_corner_class(P, v));
   }
 }
 
@@ -497,26 +568,45 @@ __device__ __forceinline__ void actor_chunk_step(const SimParams& P, const PoolD
     }
 }
 
-// ---- the step kernel ----------------------------------------------------------------------------
-// G lanes cooperate on one environment (32 / G environments per warp).  The ego / reward arithmetic is scalar and
-// runs uniformly on the G lanes of a group, so a smaller G wastes less of the fp64 pipe; G = 32 is used when scenes
-// carry many actors (lanes = actors), G = 8 for the scripted scenarios (<= 8 actors).
+// ---- the step kernels ---------------------------------------------------------------------------
+// The step is split where the reference's data flow allows it (envs/carlabev.py:223-231, scenes/scene.py:90-140):
+//   k_move  -- everything that MOVES: action decode, ego bicycle physics, scripted actors (trajectory tables or live
+//              behaviour FSM + Stanley), and what the rasteriser needs from it: the crop / rotate descriptor and the
+//              clipped draw list.  Short dependent chain; the raster kernel waits only for this.
+//   k_judge -- everything that JUDGES the new state: nearest waypoint, comfort signals, rect collisions / proximity /
+//              TTC, target consumption, tile lookup, CaRL / shaping reward, termination, episode statistics, info
+//              block.  The long fp64 chain; runs on a side stream CONCURRENTLY with the raster kernel, which reads
+//              only the descriptor and the draw list.
+// G lanes cooperate on one environment (32 / G environments per warp).  The scalar arithmetic runs uniformly on the
+// G lanes of a group, so a smaller G wastes less of the fp64 pipe; G = 32 is used when scenes carry many actors that
+// are stepped live (lanes = actors), G = 8 otherwise.
+template <int G>
+struct Group {
+  int warp, lane, gb, grp;
+  unsigned GM;
+  int env;
+  __device__ __forceinline__ Group(const SimParams& P) {
+    constexpr int EPW = 32 / G;
+    warp = threadIdx.x >> 5;
+    const int wl = threadIdx.x & 31;
+    lane = wl & (G - 1);   // lane within the environment's group
+    gb = wl & ~(G - 1);    // first warp lane of the group
+    grp = wl / G;
+    GM = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gb);
+    env = P.env_lo + (blockIdx.x * CBEV_WARPS_PER_BLOCK + warp) * EPW + grp;
+  }
+};
+
 template <int G>
 __global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, G == 32 ? CBEV_SIM_BLOCKS_PER_SM : 4)
-k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, cbev_step_out out,
-      int32_t* __restrict__ desc, uint32_t* __restrict__ rects, double* __restrict__ gstats) {
-  constexpr int EPW = 32 / G;  // environments per warp
-  __shared__ double s_hero[CBEV_WARPS_PER_BLOCK][EPW][CBEV_HERO_FIELDS];
-  const int warp = threadIdx.x >> 5;
-  const int wl = threadIdx.x & 31;
-  const int lane = wl & (G - 1);   // lane within the environment's group
-  const int gb = wl & ~(G - 1);    // first warp lane of the group
-  const int grp = wl / G;
-  const unsigned GM = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gb);
-  const int env = P.env_lo + (blockIdx.x * CBEV_WARPS_PER_BLOCK + warp) * EPW + grp;
+k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, cbev_step_out out,
+       int32_t* __restrict__ desc, uint32_t* __restrict__ rects) {
+  const Group<G> g(P);
+  const int lane = g.lane, gb = g.gb, env = g.env;
+  const unsigned GM = g.GM;
   if (env >= P.env_hi) return;
   int32_t* d = desc + (size_t)env * CBEV_DESC_WORDS;
-  uint32_t* rl = rects + (size_t)env * P.max_rects;
+  uint32_t* rl = rects + (size_t)env * P.max_rects * CBEV_RECT_WORDS;
 
   // ---- device auto-reset (gymnasium NEXT_STEP semantics) from the pool -------------------------
   if (P.autoreset == CBEV_AUTORESET_NEXT_STEP && st.done[env]) {
@@ -527,7 +617,9 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
     reset_env(P, pool, st, env, scene, lane, G);
     if (lane == 0) {
       const double* s0 = pool.ego_state0 + (size_t)scene * 4;
-      write_desc_header(P, d, s0[0], s0[1], 0.0, 0, 1);
+      View v;
+      compute_view(P, s0[0], s0[1], 0.0, v);
+      write_desc_header(P, d, v, 0, 1, crop_corner_class(P, v));  // bit0: reset frame; k_judge skips this env
       out.reward[env] = 0.0;
       out.terminated[env] = 0;
       out.truncated[env] = 0;
@@ -546,9 +638,8 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
   const int r0 = pool.ego_off[scene], nt = pool.ego_off[scene + 1] - r0;
   const double* __restrict__ ecx = pool.ego_cx + r0;
   const double* __restrict__ ecy = pool.ego_cy + r0;
-  const double* __restrict__ ecyaw = pool.ego_cyaw + r0;
   double* eg = st.ego + (size_t)env * E_SLOTS;
-  int32_t* ei = st.egoi + (size_t)env * I_SLOTS;
+  const int32_t* ei = st.egoi + (size_t)env * I_SLOTS;
 
   // ---- a1: decode action (spaces.py:43-47, hero.py:165-187) ----------------------------------------
   float gas, steer, brake;
@@ -570,15 +661,7 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
   e.x = eg[E_X]; e.y = eg[E_Y]; e.yaw = eg[E_YAW]; e.v = eg[E_V];
   double acc = eg[E_ACC];
   const double etarget = eg[E_TARGET];
-  double t_sim = eg[E_T] + DT;  // scene.py:91
-  int tidx = ei[I_TIDX];
-  int flags = ei[I_FLAGS];
-  {
-    double sn, cs;
-    sincos(e.yaw, &sn, &cs);
-    int idx = warp_nearest<G>(e.x + WB * cs, e.y + WB * sn, ecx, ecy, nt, lane, GM);
-    if (tidx < idx) tidx = idx;  // stanley_controller.py:76-77
-  }
+  const double t_sim = eg[E_T] + DT;  // scene.py:91 (k_judge stores it)
   double acc_val = gas > 0.0f ? (double)__fmul_rn(gas, 8.0f) : 0.0;
   double delta;
   if (fabs(e.v) < 0.1) {
@@ -596,52 +679,24 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
   e.v *= 0.9999;
   if (fabs(e.v) < 0.05) e.v = 0.0;
   e.v *= 0.985;
-  // compute_comfort_kinematics, comfort.py:17-61
-  double speed_mps = e.v * MPP, prev_speed_mps = e.v1 * MPP;
-  double dyaw_c = e.yaw - e.yaw1;
-  double yaw_rate_rad = atan2(sin(dyaw_c), cos(dyaw_c)) / DT;
-  double yaw_rate_deg = yaw_rate_rad * RAD2DEG;
-  double accel_long = (speed_mps - prev_speed_mps) / DT;
-  double accel_lat = speed_mps * yaw_rate_rad;
-  double jerk_long = 0.0, jerk_lat = 0.0, yaw_acc = 0.0;
-  if (flags & FL_COMFORT) {
-    jerk_long = (accel_long - eg[E_PC_AL]) / DT;
-    jerk_lat = (accel_lat - eg[E_PC_AT]) / DT;
-    yaw_acc = (yaw_rate_deg - eg[E_PC_YR]) / DT;
+  if (lane == 0) {
+    eg[E_X] = e.x; eg[E_Y] = e.y; eg[E_YAW] = e.yaw; eg[E_V] = e.v;
+    eg[E_X1] = e.x1; eg[E_Y1] = e.y1; eg[E_YAW1] = e.yaw1; eg[E_V1] = e.v1;
+    eg[E_ACC] = acc;
+    eg[E_GAS] = (double)gas; eg[E_STEER] = (double)steer; eg[E_BRAKE] = (double)brake; eg[E_DELTA] = applied_delta;
   }
-  flags |= FL_COMFORT;
 
-  // ego rect (hero.sync_rect, hero.py:34-35)
   const int pad = P.pad;
-  const int hx = rect_left(e.x, pad, 4), hy = rect_left(e.y, pad, 4);
-  const int hcx = hx + 2, hcy = hy + 2;
-
-  // crop window (needed to clip the draw list); same arithmetic as write_desc_header
-  const int crop = P.crop;
-  int xmin, ymin;
-  {
-    int offx = (int)(((double)pad + e.x * 1.0) + (-(double)crop / 2.0));
-    int offy = (int)(((double)pad + e.y * 1.0) + (-(double)crop / 2.0));
-    int ccx = (int)rint((double)offx + (double)crop / 2.0);
-    int ccy = (int)rint((double)offy + (double)crop / 2.0);
-    xmin = max(0, min(max(0, P.map_w + 2 * pad - crop), ccx - crop / 2));
-    ymin = max(0, min(max(0, P.map_h + 2 * pad - crop), ccy - crop / 2));
-  }
+  View view;
+  compute_view(P, e.x, e.y, e.yaw, view);
+  int bg = crop_corner_class(P, view);  // rotate background: crop pixel (0, 0) after every draw below
 
   // ---- a4/a5: scripted actors ---------------------------------------------------------------------
-  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
-  int hit = HIT_NONE, hit_id = -1, n_nearby = 0, nrects = 0;
-  double min_ttc = INFINITY;
-  double hvx_m, hvy_m, hvx, hvy;
-  {
-    double sn, cs;
-    sincos(e.yaw, &sn, &cs);
-    hvx = e.v * cs; hvy = e.v * sn;                 // compute_ttc (px units)
-    hvx_m = (e.v * MPP) * cs; hvy_m = (e.v * MPP) * sn;  // compute_ttc_raw (metres)
-  }
   // Scripted actors never read the ego: their trajectories are functions of (scene, step).
   // The first traj_steps steps of every scene were rolled out at pool upload by the same device code
   // (k_rollout); afterwards the env continues live from the roll-out's final state.
+  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
+  int nrects = 0;
   const int step_idx = ei[I_STEP];
   const bool use_table = step_idx < pool.traj_steps;
   if (!use_table && pool.traj_steps > 0 && step_idx == pool.traj_steps) {
@@ -670,18 +725,156 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
         const double4 q = pool.traj[pool.traj_off[scene] + (size_t)step_idx * A + a];
         b.x = q.x; b.y = q.y; b.yaw = q.z; b.v = q.w;
         kind = pool.act_kind[ga];
-        st.ax[o] = b.x; st.ay[o] = b.y; st.ayaw[o] = b.yaw; st.av[o] = b.v;  // kept for cbev_get_state
+        st.ax[o] = b.x; st.ay[o] = b.y; st.ayaw[o] = b.yaw; st.av[o] = b.v;  // read back by k_judge / cbev_get_state
       }
     } else {
       actor_chunk_step<G>(P, pool, st, (size_t)env, ga, o, has, t_sim, lane, gb, GM, b, kind);
     }
-    // ---- a9: collision / proximity (scene.py:110-140, actor.py:166-176) ----
+    // ---- a6: draw list (vehicles then pedestrians; pool stores them in that order) ----
     const int size = kind == 0 ? 4 : 2;  // vehicle.py:24, pedestrian.py:24
-    int rx = 0, ry = 0;
+    uint32_t pk0 = 0, pk1 = 0;
+    bool vis = false, c00 = false;
+    const int pal = kind == 0 ? CBEV_PAL_VEHICLE : CBEV_PAL_PEDESTRIAN;
+    if (has) {
+      const int rx = rect_left(b.x, pad, size), ry = rect_left(b.y, pad, size);
+      vis = pack_rect(rx, ry, size, size, pal, view, pk0, pk1, c00);
+    }
+    {
+      unsigned bm = __ballot_sync(GM, c00) >> gb;
+      if (bm) bg = __shfl_sync(GM, pal, gb + 31 - __clz(bm));  // the last rect drawn over the corner wins
+    }
+    unsigned vm = __ballot_sync(GM, vis) >> gb;
+    if (vis) {
+      uint32_t* w = rl + (size_t)(nrects + __popc(vm & ((1u << lane) - 1u))) * CBEV_RECT_WORDS;
+      w[0] = pk0; w[1] = pk1;
+    }
+    nrects += __popc(vm);
+  }
+
+  // ---- targets still visible at draw time (target.py:46-50); k_judge consumes them afterwards ----------
+  const unsigned long long* tv = st.tgt_vis + (size_t)env * CBEV_TGT_WORDS;
+  for (int base = 0; base < nt; base += G) {
+    int i = base + lane;
+    bool has = i < nt && ((tv[i >> 6] >> (i & 63)) & 1ull);
+    int size = (i == nt - 1) ? 4 : 2;  // scenes/utils.py:114-122
+    uint32_t pk0 = 0, pk1 = 0;
+    bool vis = false, c00 = false;
+    if (has) {
+      const int tx = rect_left(ecx[i], pad, size), ty = rect_left(ecy[i], pad, size);
+      vis = pack_rect(tx, ty, size, size, CBEV_PAL_ROUTE, view, pk0, pk1, c00);
+    }
+    if (__ballot_sync(GM, c00)) bg = CBEV_PAL_ROUTE;
+    unsigned vm = __ballot_sync(GM, vis) >> gb;
+    if (vis) {
+      uint32_t* w = rl + (size_t)(nrects + __popc(vm & ((1u << lane) - 1u))) * CBEV_RECT_WORDS;
+      w[0] = pk0; w[1] = pk1;
+    }
+    nrects += __popc(vm);
+  }
+  // ---- traffic lights: drawn without the padding offset (traffic_light.py:81-90, quirk C-4) ----------
+  {
+    const int t0 = pool.tl_off[scene], ntl = pool.tl_off[scene + 1] - t0;
+    for (int base = 0; base < ntl; base += G) {
+      int i = base + lane;
+      uint32_t pk0 = 0, pk1 = 0;
+      bool vis = false, c00 = false;
+      int pal = 0;
+      if (i < ntl) {
+        const int32_t* r = pool.tl_rect + (size_t)(t0 + i) * 4;
+        pal = pool.tl_color[t0 + i];
+        vis = pack_rect(r[0], r[1], r[2], r[3], pal, view, pk0, pk1, c00);
+      }
+      {
+        unsigned bm = __ballot_sync(GM, c00) >> gb;
+        if (bm) bg = __shfl_sync(GM, pal, gb + 31 - __clz(bm));
+      }
+      unsigned vm = __ballot_sync(GM, vis) >> gb;
+      if (vis) {
+        uint32_t* w = rl + (size_t)(nrects + __popc(vm & ((1u << lane) - 1u))) * CBEV_RECT_WORDS;
+        w[0] = pk0; w[1] = pk1;
+      }
+      nrects += __popc(vm);
+    }
+  }
+  if (lane == 0) write_desc_header(P, d, view, nrects, 0, bg);
+}
+
+template <int G>
+__global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, G == 32 ? CBEV_SIM_BLOCKS_PER_SM : 4)
+k_judge(SimParams P, PoolDev pool, EnvState st, cbev_step_out out, const int32_t* __restrict__ desc,
+        double* __restrict__ gstats) {
+  constexpr int EPW = 32 / G;  // environments per warp
+  __shared__ double s_hero[CBEV_WARPS_PER_BLOCK][EPW][CBEV_HERO_FIELDS];
+  const Group<G> g(P);
+  const int warp = g.warp, lane = g.lane, gb = g.gb, grp = g.grp, env = g.env;
+  const unsigned GM = g.GM;
+  if (env >= P.env_hi) return;
+  if (desc[(size_t)env * CBEV_DESC_WORDS + RD_FLAGS] & 1) return;  // auto-reset this step: k_move wrote the outputs
+
+  const int scene = st.scene[env];
+  const int r0 = pool.ego_off[scene], nt = pool.ego_off[scene + 1] - r0;
+  const double* __restrict__ ecx = pool.ego_cx + r0;
+  const double* __restrict__ ecy = pool.ego_cy + r0;
+  const double* __restrict__ ecyaw = pool.ego_cyaw + r0;
+  double* eg = st.ego + (size_t)env * E_SLOTS;
+  int32_t* ei = st.egoi + (size_t)env * I_SLOTS;
+
+  // the pose k_move produced, and the one before it
+  Body e;
+  e.x = eg[E_X]; e.y = eg[E_Y]; e.yaw = eg[E_YAW]; e.v = eg[E_V];
+  e.x1 = eg[E_X1]; e.y1 = eg[E_Y1]; e.yaw1 = eg[E_YAW1]; e.v1 = eg[E_V1];
+  const double acc = eg[E_ACC];
+  const double t_sim = eg[E_T] + DT;  // scene.py:91
+  int tidx = ei[I_TIDX];
+  int flags = ei[I_FLAGS];
+  {  // Controller.calc_target_index on the pre-step pose (hero.py:100-104, stanley_controller.py:76-77)
+    double sn, cs;
+    sincos(e.yaw1, &sn, &cs);
+    int idx = warp_nearest<G>(e.x1 + WB * cs, e.y1 + WB * sn, ecx, ecy, nt, lane, GM);
+    if (tidx < idx) tidx = idx;
+  }
+  // compute_comfort_kinematics, comfort.py:17-61
+  double speed_mps = e.v * MPP, prev_speed_mps = e.v1 * MPP;
+  double dyaw_c = e.yaw - e.yaw1;
+  double yaw_rate_rad = atan2(sin(dyaw_c), cos(dyaw_c)) / DT;
+  double yaw_rate_deg = yaw_rate_rad * RAD2DEG;
+  double accel_long = (speed_mps - prev_speed_mps) / DT;
+  double accel_lat = speed_mps * yaw_rate_rad;
+  double jerk_long = 0.0, jerk_lat = 0.0, yaw_acc = 0.0;
+  if (flags & FL_COMFORT) {
+    jerk_long = (accel_long - eg[E_PC_AL]) / DT;
+    jerk_lat = (accel_lat - eg[E_PC_AT]) / DT;
+    yaw_acc = (yaw_rate_deg - eg[E_PC_YR]) / DT;
+  }
+  flags |= FL_COMFORT;
+
+  // ego rect (hero.sync_rect, hero.py:34-35)
+  const int pad = P.pad;
+  const int hx = rect_left(e.x, pad, 4), hy = rect_left(e.y, pad, 4);
+  const int hcx = hx + 2, hcy = hy + 2;
+
+  // ---- a9: collision / proximity (scene.py:110-140, actor.py:166-176) on the actor poses of this step ----
+  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
+  int hit = HIT_NONE, hit_id = -1, n_nearby = 0;
+  double min_ttc = INFINITY;
+  double hvx_m, hvy_m, hvx, hvy;
+  {
+    double sn, cs;
+    sincos(e.yaw, &sn, &cs);
+    hvx = e.v * cs; hvy = e.v * sn;                 // compute_ttc (px units)
+    hvx_m = (e.v * MPP) * cs; hvy_m = (e.v * MPP) * sn;  // compute_ttc_raw (metres)
+  }
+  for (int base = 0; base < A; base += G) {
+    const int a = base + lane;
+    const bool has = a < A;
+    const size_t o = (size_t)env * P.max_actors + (has ? a : 0);
+    int kind = 0, rx = 0, ry = 0;
     bool near = false, coll = false;
     if (has) {
-      rx = rect_left(b.x, pad, size);
-      ry = rect_left(b.y, pad, size);
+      kind = pool.act_kind[A0 + a];
+      const int size = kind == 0 ? 4 : 2;  // vehicle.py:24, pedestrian.py:24
+      rx = rect_left(st.ax[o], pad, size);
+      ry = rect_left(st.ay[o], pad, size);
       int dcx = hcx - (rx + (size >> 1)), dcy = hcy - (ry + (size >> 1));
       near = dcx * dcx + dcy * dcy < 35 * 35;  // math.hypot(ints) < min_dist
       coll = overlap(hx, hy, 4, rx, ry, size);
@@ -691,74 +884,48 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
       int src = 31 - __clz(cm);  // last colliding actor in iteration order wins
       int k = __shfl_sync(GM, kind, gb + src);
       hit = k == 0 ? HIT_VEHICLE : HIT_PEDESTRIAN;
-      hit_id = k;
+      hit_id = k;  // Actor.id: Vehicle passes id=0, Pedestrian id=1 (vehicle.py:23, pedestrian.py:23)
     }
     n_nearby += __popc(__ballot_sync(GM, near));
     if (near) {
+      const double bx = st.ax[o], by = st.ay[o], byaw = st.ayaw[o], bv = st.av[o];
       double sn, cs;
-      sincos(b.yaw, &sn, &cs);
-      double avx = b.v * cs, avy = b.v * sn;
+      sincos(byaw, &sn, &cs);
+      double avx = bv * cs, avy = bv * sn;
       double rxx, ryy, rvx, rvy;
       if (P.reward_mode == CBEV_REWARD_CARL) {  // compute_ttc_raw, reward_signals.py:45-94
-        rxx = b.x * MPP - e.x * MPP; ryy = b.y * MPP - e.y * MPP;
+        rxx = bx * MPP - e.x * MPP; ryy = by * MPP - e.y * MPP;
         rvx = avx * MPP - hvx_m; rvy = avy * MPP - hvy_m;
       } else {                                  // compute_ttc, reward_signals.py:15-42
-        rxx = b.x - e.x; ryy = b.y - e.y;
+        rxx = bx - e.x; ryy = by - e.y;
         rvx = avx - hvx; rvy = avy - hvy;
       }
       double nrm = sqrt(rxx * rxx + ryy * ryy);
       double rel = (rvx * rxx + rvy * ryy) / (nrm + 1e-6);
       if (rel < 0.0) min_ttc = fmin(min_ttc, fabs(nrm / rel));
     }
-    // ---- a6: draw list (vehicles then pedestrians; pool stores them in that order) ----
-    uint32_t packed = 0;
-    bool vis = has && pack_rect(rx, ry, size, size, kind == 0 ? CBEV_PAL_VEHICLE : CBEV_PAL_PEDESTRIAN, xmin, ymin,
-                                crop, packed);
-    unsigned vm = __ballot_sync(GM, vis) >> gb;
-    if (vis) rl[nrects + __popc(vm & ((1u << lane) - 1u))] = packed;
-    nrects += __popc(vm);
   }
 #pragma unroll
   for (int o2 = G / 2; o2 > 0; o2 >>= 1) min_ttc = fmin(min_ttc, __shfl_xor_sync(GM, min_ttc, o2));
 
-  // ---- targets: draw (visible at draw time), then consume on overlap (target.py:37-50) ----------------
-  unsigned long long tvis = st.tgt_vis[env];
+  // ---- targets: consumed on overlap, last in order wins (target.py:37-44) ----------------
+  unsigned long long tvis[CBEV_TGT_WORDS];
+#pragma unroll
+  for (int w = 0; w < CBEV_TGT_WORDS; ++w) tvis[w] = st.tgt_vis[(size_t)env * CBEV_TGT_WORDS + w];
   for (int base = 0; base < nt; base += G) {
     int i = base + lane;
-    bool has = i < nt && ((tvis >> i) & 1ull);
+    bool has = i < nt && ((tvis[(i >> 6) & (CBEV_TGT_WORDS - 1)] >> (i & 63)) & 1ull);
     int size = (i == nt - 1) ? 4 : 2;  // scenes/utils.py:114-122
-    int tx = 0, ty = 0;
+    bool coll = false;
     if (has) {
-      tx = rect_left(ecx[i], pad, size);
-      ty = rect_left(ecy[i], pad, size);
+      const int tx = rect_left(ecx[i], pad, size), ty = rect_left(ecy[i], pad, size);
+      coll = overlap(hx, hy, 4, tx, ty, size);
     }
-    uint32_t packed = 0;
-    bool vis = has && pack_rect(tx, ty, size, size, CBEV_PAL_ROUTE, xmin, ymin, crop, packed);
-    unsigned vm = __ballot_sync(GM, vis) >> gb;
-    if (vis) rl[nrects + __popc(vm & ((1u << lane) - 1u))] = packed;
-    nrects += __popc(vm);
-    bool coll = has && overlap(hx, hy, 4, tx, ty, size);
     unsigned cm = __ballot_sync(GM, coll) >> gb;
     if (cm) {
-      tvis &= ~((unsigned long long)cm << base);
+      tvis[(base >> 6) & (CBEV_TGT_WORDS - 1)] &= ~((unsigned long long)cm << (base & 63));
       hit = HIT_TARGET;
       hit_id = base + 31 - __clz(cm);
-    }
-  }
-  // ---- traffic lights: drawn without the padding offset (traffic_light.py:81-90, quirk C-4) ----------
-  {
-    const int t0 = pool.tl_off[scene], ntl = pool.tl_off[scene + 1] - t0;
-    for (int base = 0; base < ntl; base += G) {
-      int i = base + lane;
-      uint32_t packed = 0;
-      bool vis = false;
-      if (i < ntl) {
-        const int32_t* r = pool.tl_rect + (size_t)(t0 + i) * 4;
-        vis = pack_rect(r[0], r[1], r[2], r[3], pool.tl_color[t0 + i], xmin, ymin, crop, packed);
-      }
-      unsigned vm = __ballot_sync(GM, vis) >> gb;
-      if (vis) rl[nrects + __popc(vm & ((1u << lane) - 1u))] = packed;
-      nrects += __popc(vm);
     }
   }
 
@@ -929,13 +1096,12 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
 
   // ---- write back (lane 0) ----
   if (lane == 0) {
-    eg[E_X] = e.x; eg[E_Y] = e.y; eg[E_YAW] = e.yaw; eg[E_V] = e.v;
-    eg[E_X1] = e.x1; eg[E_Y1] = e.y1; eg[E_YAW1] = e.yaw1; eg[E_V1] = e.v1;
-    eg[E_ACC] = acc; eg[E_T] = t_sim; eg[E_D2G] = d2g; eg[E_D2G1] = d2g_1;
+    eg[E_T] = t_sim; eg[E_D2G] = d2g; eg[E_D2G1] = d2g_1;  // the pose itself was stored by k_move
     eg[E_SPREV] = s_prev; eg[E_LAST_DYAW] = last_dyaw;
     eg[E_PC_AL] = accel_long; eg[E_PC_AT] = accel_lat; eg[E_PC_YR] = yaw_rate_deg;
-    ei[I_TIDX] = tidx; ei[I_FLAGS] = flags; ei[I_K] = kcount; ei[I_OFFROAD] = offroad; ei[I_STEP] = step_idx + 1;
-    st.tgt_vis[env] = tvis;
+    ei[I_TIDX] = tidx; ei[I_FLAGS] = flags; ei[I_K] = kcount; ei[I_OFFROAD] = offroad; ei[I_STEP] += 1;
+#pragma unroll
+    for (int w = 0; w < CBEV_TGT_WORDS; ++w) st.tgt_vis[(size_t)env * CBEV_TGT_WORDS + w] = tvis[w];
     out.reward[env] = reward;
     out.terminated[env] = terminated;
     out.truncated[env] = truncated;
@@ -967,15 +1133,14 @@ k_sim(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, 
       for (int k = 0; k < 6; ++k) sa[S_C0 + k] += cm6[k];
       sa[S_VIOL] = ep_viol; sa[S_HARSH] = ep_harsh; sa[S_CAUSE] = ep_cause;
     }
-    write_desc_header(P, d, e.x, e.y, e.yaw, nrects, 0);
     if (out.hero) {
       double* hb = s_hero[warp][grp];
       hb[CBEV_H_X] = e.x; hb[CBEV_H_Y] = e.y; hb[CBEV_H_YAW] = e.yaw; hb[CBEV_H_V] = e.v;
       hb[CBEV_H_X1] = e.x1; hb[CBEV_H_Y1] = e.y1; hb[CBEV_H_YAW1] = e.yaw1; hb[CBEV_H_V1] = e.v1;
       hb[CBEV_H_DIST2WP] = dist2wp; hb[CBEV_H_SP_X] = ecx[tidx]; hb[CBEV_H_SP_Y] = ecy[tidx];
       hb[CBEV_H_SP_YAW] = ecyaw[tidx];
-      hb[CBEV_H_CMD_GAS] = (double)gas; hb[CBEV_H_CMD_STEER] = (double)steer; hb[CBEV_H_CMD_BRAKE] = (double)brake;
-      hb[CBEV_H_DELTA] = applied_delta;
+      hb[CBEV_H_CMD_GAS] = eg[E_GAS]; hb[CBEV_H_CMD_STEER] = eg[E_STEER]; hb[CBEV_H_CMD_BRAKE] = eg[E_BRAKE];
+      hb[CBEV_H_DELTA] = eg[E_DELTA];
       hb[CBEV_H_SPEED_MPS] = speed_mps; hb[CBEV_H_ACCEL_LONG] = accel_long; hb[CBEV_H_ACCEL_LAT] = accel_lat;
       hb[CBEV_H_JERK_LONG] = jerk_long; hb[CBEV_H_JERK_LAT] = jerk_lat; hb[CBEV_H_YAW_RATE] = yaw_rate_deg;
       hb[CBEV_H_YAW_ACC] = yaw_acc;
@@ -1051,19 +1216,35 @@ void cbev_launch_reset(cbev_engine* e, const uint8_t* mask, const int32_t* scene
   e->launches += 1;
 }
 
-void cbev_launch_sim(cbev_engine* e, const void* actions, const cbev_step_out* out, int lo, int hi, cudaStream_t s) {
+static bool narrow_groups(const cbev_engine* e) {
+  return e->pool.max_actors <= 8 || e->pool.traj_steps > 0;  // table look-ups need no wide actor loops
+}
+
+void cbev_launch_move(cbev_engine* e, const void* actions, const cbev_step_out* out, int lo, int hi, cudaStream_t s) {
   SimParams P = make_params(e);
   P.env_lo = lo;
   P.env_hi = hi;
-  if (e->pool.max_actors <= 8 || e->pool.traj_steps > 0) {  // table look-ups need no wide actor loops
+  if (narrow_groups(e)) {
     constexpr int G = 8;
     int per_block = CBEV_WARPS_PER_BLOCK * (32 / G);
     int blocks = (hi - lo + per_block - 1) / per_block;
-    k_sim<G><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->gstats);
+    k_move<G><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects);
   } else {
     int blocks = (hi - lo + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
-    k_sim<32><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->gstats);
+    k_move<32><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects);
   }
+  e->launches += 1;
+}
+
+void cbev_launch_judge(cbev_engine* e, const cbev_step_out* out, int lo, int hi, cudaStream_t s) {
+  SimParams P = make_params(e);
+  P.env_lo = lo;
+  P.env_hi = hi;
+  // the judging loops over actors / route segments are cheap per element: 8 lanes per env unless routes are long
+  constexpr int G = 8;
+  int per_block = CBEV_WARPS_PER_BLOCK * (32 / G);
+  int blocks = (hi - lo + per_block - 1) / per_block;
+  k_judge<G><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, *out, e->desc, e->gstats);
   e->launches += 1;
 }
 

@@ -37,7 +37,10 @@ SG_MAX = 12
 EXPORTS = ("cbev_version", "cbev_last_error", "cbev_create", "cbev_destroy", "cbev_upload_map",
            "cbev_upload_scene_pool", "cbev_frame_bytes", "cbev_bind_obs_ring", "cbev_reset", "cbev_step",
            "cbev_step_host", "cbev_obs_head", "cbev_get_state", "cbev_set_ego_state", "cbev_copy_fov",
-           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes", "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse", "cbev_debug_rerender", "cbev_set_debug_flags", "cbev_debug_read_trace")
+           "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes",
+           "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse", "cbev_debug_rerender", "cbev_set_debug_flags",
+           "cbev_debug_read_trace", "cbev_step_host_ex", "cbev_wait_host_outputs", "cbev_set_state",
+           "cbev_profile_read_ex", "cbev_step_ex", "cbev_invalidate")
 
 
 class CbevConfig(C.Structure):
@@ -80,6 +83,10 @@ class CbevStepOut(C.Structure):
     _fields_ = [("reward", _P), ("terminated", _P), ("truncated", _P), ("cause", _P), ("hero", _P), ("episode", _P)]
 
 
+class CbevHostOut(C.Structure):
+    _fields_ = [("reward", _P), ("terminated", _P), ("truncated", _P), ("cause", _P), ("episode", _P)]
+
+
 class CbevError(RuntimeError):
     pass
 
@@ -92,9 +99,10 @@ def load_library(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or _build.needs_build():
+        # a library older than csrc/ or include/cbev.h would run stale kernels behind an unchanged ABI
         if not build_if_missing:
-            raise CbevError(f"{LIB_PATH} is missing; run `python -m carlabev_env_b200.build`")
+            raise CbevError(f"{LIB_PATH} is missing or older than its sources; run `python -m carlabev_env_b200.build`")
         _build.build()
     lib = C.CDLL(LIB_PATH)
     lib.cbev_last_error.restype = C.c_char_p
@@ -110,6 +118,13 @@ def load_library(build_if_missing: bool = True):
     lib.cbev_reset.argtypes = [_P, _P, _P, _P]
     lib.cbev_step.argtypes = [_P, _P, C.POINTER(CbevStepOut), _P]
     lib.cbev_step_host.argtypes = [_P, _P, _P, _P, _P, _P]
+    lib.cbev_step_host_ex.argtypes = [_P, _P, C.POINTER(CbevStepOut), C.POINTER(CbevHostOut), _P]
+    lib.cbev_step_ex.argtypes = [_P, _P, C.POINTER(CbevStepOut), C.POINTER(CbevHostOut), _P]
+    lib.cbev_invalidate.argtypes = [_P]
+    lib.cbev_wait_host_outputs.argtypes = [_P]
+    lib.cbev_set_state.argtypes = [_P, _P, _P]
+    lib.cbev_profile_read_ex.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int64)]
     lib.cbev_obs_head.argtypes = [_P, C.POINTER(C.c_int32)]
     lib.cbev_get_state.argtypes = [_P, _P, _P]
     lib.cbev_set_ego_state.argtypes = [_P, _P]
@@ -194,7 +209,10 @@ class Engine:
                 if ring_budget_bytes is None:
                     free, _ = torch.cuda.mem_get_info(self.device)
                     ring_budget_bytes = int(free * 0.35)
-                ring_slots = max(2 * self.F - 1, min(64, ring_budget_bytes // max(1, self.N * frame)))
+                # L >= 2F: the previous observation window stays intact for one more step (a caller holding both
+                # `obs` and `next_obs` -- replay buffers, GAE bootstrap -- reads two valid windows); with the minimum
+                # L = 2F - 1 the next head or mirror write lands inside the previous window
+                ring_slots = max(2 * self.F, min(64, ring_budget_bytes // max(1, self.N * frame)))
         self.L = int(ring_slots)
         cfg = CbevConfig()
         cfg.num_envs = self.N
@@ -219,7 +237,15 @@ class Engine:
         cfg.trajectory_steps = int(trajectory_steps)
         params = dict(CARL_DEFAULTS)
         params.update(SHAPING_DEFAULTS)
-        params.update({k: v for k, v in (reward_params or {}).items() if k in params})
+        fixed = {"zero_speed_reward_offroad": True, "zero_progress_reward_offroad": True}  # what the kernels implement
+        for k, v in (reward_params or {}).items():
+            if k in params:
+                params[k] = v
+            elif k in fixed:
+                if bool(v) != fixed[k]:
+                    raise CbevError(f"reward parameter {k}={v!r} is not implemented (the engine computes {k}={fixed[k]})")
+            else:
+                raise CbevError(f"unknown reward parameter {k!r}; known: {sorted(params) + sorted(fixed)}")
         for k, v in params.items():
             setattr(cfg, k, v)
         cfg.seed = int(seed) & (2**64 - 1)
@@ -233,9 +259,12 @@ class Engine:
         dev = self.device
         self.ring = torch.empty(self.N * self.L * frame, dtype=torch.uint8, device=dev)
         _check(self.lib, self.lib.cbev_bind_obs_ring(self.handle, self.ring.data_ptr(), self.ring.numel()))
-        self.reward = torch.zeros(self.N, dtype=torch.float64, device=dev)
-        self.terminated = torch.zeros(self.N, dtype=torch.uint8, device=dev)
-        self.truncated = torch.zeros(self.N, dtype=torch.uint8, device=dev)
+        # reward f64[N] | terminated u8[N] | truncated u8[N] back to back: one D2H copy brings all three to the host
+        self._rtt = torch.zeros(self.N * 10, dtype=torch.uint8, device=dev)
+        self.reward = self._rtt[: self.N * 8].view(torch.float64)
+        self.terminated = self._rtt[self.N * 8: self.N * 9]
+        self.truncated = self._rtt[self.N * 9:]
+        self._host = None  # pinned mirrors, allocated by the first step_host_full
         self.cause = torch.zeros(self.N, dtype=torch.uint8, device=dev)
         self.hero = torch.zeros(self.N, len(HERO_FIELDS), dtype=torch.float64, device=dev)
         self.episode = torch.zeros(self.N, len(EPISODE_FIELDS), dtype=torch.float64, device=dev)
@@ -316,6 +345,36 @@ class Engine:
         _check(self.lib, self.lib.cbev_step_host(self.handle, actions_host.data_ptr(), reward_host.data_ptr(),
                                                  term_host.data_ptr(), trunc_host.data_ptr(), self._stream()))
 
+    def step_host_full(self, actions, episode=True):
+        """Pinned host actions (or a CUDA tensor) in; reward / terminated / truncated (and the episode block) come back into pinned host
+        mirrors (`host_reward`, `host_terminated`, `host_truncated`, `host_episode`) through D2H copies that overlap
+        the raster kernel.  All device outputs (hero, cause, episode, ...) are written as in `step`.  Call
+        `wait_host_outputs()` before reading the mirrors."""
+        t = self.torch
+        if self._host is None:
+            blk = t.zeros(self.N * 10, dtype=t.uint8).pin_memory()
+            self.host_reward = blk[: self.N * 8].view(t.float64)
+            self.host_terminated = blk[self.N * 8: self.N * 9]
+            self.host_truncated = blk[self.N * 9:]
+            self.host_episode = t.zeros(self.N, len(EPISODE_FIELDS), dtype=t.float64).pin_memory()
+            self._host = CbevHostOut(self.host_reward.data_ptr(), self.host_terminated.data_ptr(),
+                                     self.host_truncated.data_ptr(), None, self.host_episode.data_ptr())
+            self._host_noep = CbevHostOut(self.host_reward.data_ptr(), self.host_terminated.data_ptr(),
+                                          self.host_truncated.data_ptr(), None, None)
+            self._host_blk = blk
+        fn = self.lib.cbev_step_ex if actions.is_cuda else self.lib.cbev_step_host_ex
+        _check(self.lib, fn(self.handle, actions.data_ptr(), C.byref(self._out),
+                            C.byref(self._host if episode else self._host_noep), self._stream()))
+
+    def invalidate(self):
+        """Every env must be reset before the next step (after the pool was replaced by an unrelated one)."""
+        _check(self.lib, self.lib.cbev_invalidate(self.handle))
+
+    def wait_host_outputs(self):
+        """Block until the host copies of the last step_host / step_host_full have landed (the raster kernel of that
+        step may still be running)."""
+        _check(self.lib, self.lib.cbev_wait_host_outputs(self.handle))
+
     @property
     def head(self) -> int:
         h = C.c_int32(-1)
@@ -373,15 +432,27 @@ class Engine:
         _check(self.lib, self.lib.cbev_copy_fov(self.handle, out.data_ptr(), self._stream()))
         return out
 
-    def get_state(self, max_actors):
+    def get_state(self, max_actors=None):
+        """(ego [N, 16], actors [N, max_actors, 8]) of cbev_get_state; the library always writes the engine's full
+        actor capacity, the returned block is cut to `max_actors` columns."""
+        cap = max(1, int(self.cfg.max_actors))
         ego = np.zeros((self.N, 16), dtype=np.float64)
-        act = np.zeros((self.N, max(1, max_actors), 8), dtype=np.float64)
+        act = np.zeros((self.N, cap, 8), dtype=np.float64)
         _check(self.lib, self.lib.cbev_get_state(self.handle, ego.ctypes.data, act.ctypes.data))
-        return ego, act
+        return ego, (act if max_actors is None else act[:, :max(1, max_actors)])
 
     def set_ego_state(self, ego):
         e = np.ascontiguousarray(ego, dtype=np.float64)
         _check(self.lib, self.lib.cbev_set_ego_state(self.handle, e.ctypes.data))
+
+    def set_state(self, ego=None, actors=None):
+        """Debug / parity: write back blocks in the layout of get_state (either may be None)."""
+        e = None if ego is None else np.ascontiguousarray(ego, dtype=np.float64)
+        a = None if actors is None else np.ascontiguousarray(actors, dtype=np.float64)
+        if a is not None:
+            assert a.shape == (self.N, max(1, int(self.cfg.max_actors)), 8), a.shape
+        _check(self.lib, self.lib.cbev_set_state(self.handle, None if e is None else e.ctypes.data,
+                                                 None if a is None else a.ctypes.data))
 
     def read_stats(self, reset=False):
         _check(self.lib, self.lib.cbev_read_stats(self.handle, self.stats_buf.data_ptr(), int(reset), self._stream()))
@@ -391,10 +462,11 @@ class Engine:
         _check(self.lib, self.lib.cbev_profile_enable(self.handle, int(on)))
 
     def profile_read(self):
-        """(sim_ms, render_ms, steps) summed over the profiled steps since the last read."""
-        a, b, n = C.c_double(), C.c_double(), C.c_int64()
-        _check(self.lib, self.lib.cbev_profile_read(self.handle, C.byref(a), C.byref(b), C.byref(n)))
-        return a.value, b.value, n.value
+        """(move_ms, render_ms, judge_ms, steps) summed over the profiled steps since the last read; k_judge runs on
+        the side stream concurrently with k_render."""
+        a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        _check(self.lib, self.lib.cbev_profile_read_ex(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return a.value, b.value, c.value, n.value
 
     @property
     def launches(self) -> int:

@@ -36,6 +36,7 @@ from .pool import load_shipped_pool, pack_pool, shipped_pool_for
 from .spaces import Box, Discrete
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+_CAUSE_ARRAY = np.array(E.CAUSE_NAMES, dtype=object)
 
 
 def load_town01_map() -> np.ndarray:
@@ -45,7 +46,18 @@ def load_town01_map() -> np.ndarray:
         return np.ascontiguousarray(z["cls"], dtype=np.uint8)
 
 
-class CarlaBEVVectorEnv:
+def _vector_env_base():
+    """gymnasium.vector.VectorEnv when gymnasium is importable (isinstance checks of downstream trainers then hold);
+    the image this was built in has no gymnasium wheel, so a plain object otherwise."""
+    try:
+        from gymnasium.vector import VectorEnv
+
+        return VectorEnv
+    except Exception:  # noqa: BLE001
+        return object
+
+
+class CarlaBEVVectorEnv(_vector_env_base()):
     metadata = {"render_modes": ["rgb_array"], "render_fps": 60, "autoreset_mode": "Disabled"}
 
     def __init__(self, cfg: RunConfig, *, scenes=None, autoreset: str = "disabled", device=None, ring_slots=None,
@@ -79,6 +91,7 @@ class CarlaBEVVectorEnv:
         else:
             obs_mode = E.OBS_GRAY  # wrap_env: bev_rgb -> GrayscaleObservation (envs/__init__.py:70)
         self._scenes = list(scenes) if scenes is not None else []
+        self._pool_is_user = scenes is not None  # reset() without a scene draws from a pool the caller passed in
         max_actors = max([len(s["act_kind"]) for s in self._scenes] + [env.max_vehicles + 2])
         params = dict(rspec["parameters"])
         if env.reward_mode == "shaping":
@@ -119,8 +132,11 @@ class CarlaBEVVectorEnv:
             self.single_observation_space = Box(0, 255, (F, *env.obs_size), np.uint8)
         else:
             self.single_observation_space = Box(0, 255, (env.size, env.size, 3), np.uint8)
-        self.single_action_space.seed(cfg.seed)
-        self._done_host = torch.zeros(self.num_envs, dtype=torch.uint8).pin_memory()
+        # wrap_env(eval=True) seeds the action space with 999, training envs with cfg.seed (envs/__init__.py:84-88)
+        self.single_action_space.seed(999 if eval else cfg.seed)
+        self.observation_space = self.single_observation_space  # batched spaces are not modelled; shapes are per env
+        self.action_space = self.single_action_space
+        self._act_pin = self._act_np = None  # pinned staging of host actions (allocated by the first step)
         self._needs_reset = np.ones(self.num_envs, dtype=bool)
         self._scene_of_env = np.zeros(self.num_envs, dtype=np.int64)
         self.current_hero = None
@@ -158,6 +174,10 @@ class CarlaBEVVectorEnv:
     def set_scene_pool(self, scenes):
         """Replace the device-resident pool (list of scene dicts, see pool.py)."""
         self._scenes = list(scenes)
+        self._pool_is_user = True
+        self._generated = {}
+        self.engine.invalidate()  # indices of the old pool mean nothing in the new one: every env resets first
+        self._needs_reset[:] = True
         self.engine.upload_pool(pack_pool(self._scenes))
 
     def _scenes_from_options(self, options, mask):
@@ -171,12 +191,17 @@ class CarlaBEVVectorEnv:
             return ids
         scene = options.get("scene")
         authored = options.get("config_file") or (scene if str(scene).endswith(".json") else None)
-        if authored is None and (scene is None or scene == "pool"):
-            if not self._scenes:
-                raise RuntimeError("no scene pool: pass scenes=... / call set_scene_pool(), or reset with "
-                                   "options={'scene': 'lead_brake' | 'jaywalk', ...}")
+        if authored is None and scene == "pool" and not self._scenes:
+            raise RuntimeError("no scene pool: pass scenes=... / call set_scene_pool(), or reset with "
+                               "options={'scene': 'rdm' | 'lead_brake' | 'jaywalk' | 'red_light_runner', ...}")
+        if authored is None and (scene == "pool" or (scene is None and self._scenes and self._pool_is_user)):
             base = int(options.get("scene_seed", options.get("_vector_seed", self.env_cfg.seed)))
             return (base + self.env_offset + np.arange(n)) % len(self._scenes)
+        if authored is None and scene is None:
+            # the reference's default: SceneGenerator.build_scene(scene="rdm") seeded with cfg.seed
+            # (scene_generator.py:97, carlabev.py:83-94)
+            scene = "rdm"
+            options = {**options, "scene": "rdm"}
         if authored is not None and not isinstance(authored, dict) and not os.path.exists(str(authored)):
             # the reference's own 7 scene files (assets/scenes/*.json) ship with the package, addressed by file name
             bundled = S.bundled_authored_files()
@@ -282,29 +307,48 @@ class CarlaBEVVectorEnv:
         return {"scenario": scenario, "_scenario": mask.copy(), "spawn_validation": spawn, "_spawn_validation": mask.copy()}
 
     def step(self, actions):
+        """SyncVectorEnv.step (envs/__init__.py:116-119 -> carlabev.py:223-231) for every env of the shard.
+
+        `actions` may be a host array (NumPy / list, like the reference's callers pass) or a CUDA tensor.  With host
+        infos on, rewards / flags / terminal summaries come to the host through one pinned D2H copy that overlaps the
+        raster kernel, and `step` returns as soon as THEY have landed: the observation is a device tensor whose
+        producer may still be running on the current stream (anything enqueued on that stream afterwards is ordered).
+        The observation is a zero-copy view of the frame ring: it stays valid for `engine.L - frame_stack` further
+        steps (>= frame_stack with the default ring), then its slots are rewritten -- clone it to keep it longer."""
         t = self.torch
         if self.autoreset == "disabled" and self._needs_reset.any():
             # gymnasium SyncVectorEnv(AutoresetMode.DISABLED) asserts on this
             raise AssertionError(f"step() on terminated envs {np.flatnonzero(self._needs_reset).tolist()}; "
                                  "call reset(options={'reset_mask': ...}) first")
-        if self.env_cfg.action_mode == "discrete":
-            a = t.as_tensor(actions, device=self.device).to(t.int64).contiguous().view(self.num_envs)
-        else:
-            a = t.as_tensor(actions, device=self.device).to(t.float32).contiguous().view(self.num_envs, 3)
         eng = self.engine
-        eng.step(a)
+        discrete = self.env_cfg.action_mode == "discrete"
+        on_device = isinstance(actions, t.Tensor) and actions.is_cuda
+        if on_device:
+            a = actions.to(t.int64).contiguous().view(self.num_envs) if discrete else \
+                actions.to(t.float32).contiguous().view(self.num_envs, 3)
+            if self.host_infos:
+                eng.step_host_full(a)
+            else:
+                eng.step(a)
+        else:
+            if self._act_pin is None:
+                self._act_pin = (t.zeros(self.num_envs, dtype=t.int64) if discrete
+                                 else t.zeros(self.num_envs, 3, dtype=t.float32)).pin_memory()
+                self._act_np = self._act_pin.numpy()
+            self._act_np[...] = np.asarray(actions).reshape(self._act_np.shape)
+            eng.step_host_full(self._act_pin, episode=self.host_infos)
         obs = eng.obs() if self.fusion == "stack" else eng.fuse(self.fusion)
-        rew, term, trunc = eng.reward, eng.terminated.bool(), eng.truncated.bool()
+        rew, term, trunc = eng.reward, eng.terminated.view(t.bool), eng.truncated.view(t.bool)
         self.current_hero = eng.hero
         infos = {"hero": eng.hero, "cause": eng.cause}
         if not self.host_infos:
             # fully asynchronous step: terminal summaries stay on the device (rows of finished envs are valid)
             infos["episode_block"] = eng.episode
             return obs, rew, term, trunc, infos
-        # one small D2H per step: the reference's terminal info (episode_info / episode) is host data
-        self._done_host.copy_(eng.terminated | eng.truncated, non_blocking=True)
-        t.cuda.current_stream(self.device).synchronize()
-        done_host = self._done_host.numpy().astype(bool)
+        eng.wait_host_outputs()  # reward / flags / episode block are on the host; the raster kernel may still run
+        term_h = eng.host_terminated.numpy().view(np.bool_)
+        trunc_h = eng.host_truncated.numpy().view(np.bool_)
+        done_host = term_h | trunc_h
         if self.recorder is not None:
             self._record_step(bool(done_host[0]))
         if done_host.any():
@@ -312,37 +356,38 @@ class CarlaBEVVectorEnv:
             if self.autoreset == "disabled":
                 self._needs_reset |= done_host
         if self.to_numpy:
-            return (self._out_obs(obs), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy(), infos)
+            return (self._out_obs(obs), eng.host_reward.numpy().copy(), term_h.copy(), trunc_h.copy(), infos)
         return obs, rew, term, trunc, infos
 
     def _terminal_infos(self, done_host):
         """episode_info (stats.py:127-148 + carlabev.py:177-185) and RecordEpisodeStatistics' `episode`
-        (r = sum of rewards, l = steps: the same numbers as the summary's return / length)."""
+        (r = sum of rewards, l = steps: the same numbers as the summary's return / length).  Built from the pinned
+        host copy of the episode block with a handful of vectorised NumPy operations."""
         idx = np.flatnonzero(done_host)
-        ep = self.engine.episode[self.torch.as_tensor(idx, device=self.device)].cpu().numpy()
+        ep = self.engine.host_episode.numpy()[idx]
         n = self.num_envs
         mask = done_host.copy()
+        cols = np.zeros((len(E.EPISODE_FIELDS), n), dtype=np.float64)
+        cols[:, idx] = ep.T
         episode_info = {}
         for k, name in enumerate(E.EPISODE_FIELDS):
             if name == "cause":
                 col = np.full(n, None, dtype=object)
-                col[idx] = np.array(E.CAUSE_NAMES, dtype=object)[ep[:, k].astype(np.int64)]
+                col[idx] = _CAUSE_ARRAY[ep[:, k].astype(np.int64)]
                 name = "termination"
+            elif name == "length":
+                col = cols[k].astype(np.int64)
             else:
-                col = np.zeros(n, dtype=np.int64 if name == "length" else np.float64)
-                col[idx] = ep[:, k]
+                col = cols[k]
             episode_info[name] = col
             episode_info[f"_{name}"] = mask
-        r = np.zeros(n)
-        ln = np.zeros(n, dtype=np.int64)
-        tm = np.zeros(n)
-        r[idx] = ep[:, E.EPISODE_FIELDS.index("return")]
-        ln[idx] = ep[:, E.EPISODE_FIELDS.index("length")]
         now = time.perf_counter()  # RecordEpisodeStatistics' `t`: wall-clock seconds since the episode began
+        tm = np.zeros(n)
         tm[idx] = np.round(now - self._episode_t0[idx], 6)
         self._episode_t0[idx] = now   # device auto-reset: the next episode of these envs starts now
         return {"episode_info": episode_info, "_episode_info": mask,
-                "episode": {"r": r, "_r": mask, "l": ln, "_l": mask, "t": tm, "_t": mask}, "_episode": mask}
+                "episode": {"r": episode_info["return"], "_r": mask, "l": episode_info["length"], "_l": mask,
+                            "t": tm, "_t": mask}, "_episode": mask}
 
     def _record_step(self, done0):
         rec = self.recorder

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CBEV_VERSION 100
+#define CBEV_VERSION 200
 
 /* ---- error codes -------------------------------------------------------------------------- */
 #define CBEV_OK 0
@@ -234,6 +234,32 @@ int cbev_step(cbev_handle h, const void* actions_dev, const cbev_step_out* out, 
 int cbev_step_host(cbev_handle h, const void* actions_host, double* reward_host, uint8_t* terminated_host,
                    uint8_t* truncated_host, void* stream);
 
+/* Host (pinned) destinations of one step.  reward / terminated / truncated are required; episode (the
+ * [N][CBEV_EPISODE_FIELDS] block, rows of finished envs are valid) and cause are optional.  If reward, terminated
+ * and truncated are laid out back to back they come back in one copy. */
+typedef struct {
+  double* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  uint8_t* cause;
+  double* episode;
+} cbev_host_out;
+
+/* cbev_step_host with caller-owned DEVICE outputs as well (dev_out may be NULL: internal staging, reward and flags
+ * only) and the optional host copies of cbev_host_out.  The D2H copies are issued on a side stream as soon as the
+ * simulation kernels of the step have finished, i.e. they overlap the raster kernel; `stream` is made to wait for
+ * them, and cbev_wait_host_outputs() blocks the calling thread until they have landed (without waiting for the
+ * raster kernel) -- what SyncVectorEnv.step's caller needs before it can look at rewards / dones
+ * (gymnasium vector step; envs/__init__.py:116-119). */
+int cbev_step_host_ex(cbev_handle h, const void* actions_host, const cbev_step_out* dev_out,
+                      const cbev_host_out* host, void* stream);
+/* cbev_step with DEVICE actions (a policy on the GPU) plus the host copies a cbev_host_out describes; host may be NULL. */
+int cbev_step_ex(cbev_handle h, const void* actions_dev, const cbev_step_out* dev_out, const cbev_host_out* host,
+                 void* stream);
+/* After replacing the pool with an unrelated one: every env must be reset (with mask = NULL) before the next step. */
+int cbev_invalidate(cbev_handle h);
+int cbev_wait_host_outputs(cbev_handle h);
+
 /* fov_masked (envs/fov.py:46-68, 96-99): static corner mask blitted over the composed frame before the ego
  * square is drawn.  mask_host: uint8[S*S], non-zero = pixel is painted black; NULL removes the mask.  Synchronous. */
 int cbev_upload_fov_mask(cbev_handle h, const uint8_t* mask_host);
@@ -256,6 +282,10 @@ int cbev_obs_head(cbev_handle h, int32_t* head);
  * actors: [N][max_actors][8] doubles  x,y,yaw,v,tidx,fsm,target_mps,alive */
 int cbev_get_state(cbev_handle h, double* ego_host, double* actors_host);
 int cbev_set_ego_state(cbev_handle h, const double* ego_host);
+/* Both blocks in the layout of cbev_get_state (either may be NULL).  Actor columns written: x, y, yaw, v, tidx, fsm,
+ * target_mps and the raw flags byte (column 7).  Actors are stepped from this state only while they run live
+ * (trajectory_steps = 0, or past the rolled-out steps): table look-ups are functions of (scene, step). */
+int cbev_set_state(cbev_handle h, const double* ego_host, const double* actors_host);
 
 /* Debug / parity: keep the 128x128 palette-index frame of every env (one extra 16 KB store per env-step
  * while on), and copy the last one out (uint8 [N][S][S], device pointer). */
@@ -269,11 +299,12 @@ int cbev_read_stats(cbev_handle h, double* stats_dev, int32_t reset_after, void*
 /* Number of kernel launches issued by the engine so far. */
 int64_t cbev_launch_count(cbev_handle h);
 
-/* Per-kernel device timing: when enabled, cbev_step records CUDA events on `stream` before the sim
- * kernel, between the two kernels and after the raster kernel (up to 2048 steps are kept).
- * cbev_profile_read synchronises and returns the summed durations in milliseconds. */
+/* Per-kernel device timing: when enabled, cbev_step records CUDA events around its three kernels on the streams
+ * they are launched on (k_move and k_render on `stream`, k_judge on the side stream; up to 2048 steps are kept).
+ * cbev_profile_read(_ex) synchronises and returns the summed durations in milliseconds (sim_ms = k_move). */
 int cbev_profile_enable(cbev_handle h, int32_t on);
 int cbev_profile_read(cbev_handle h, double* sim_ms, double* render_ms, int64_t* steps);
+int cbev_profile_read_ex(cbev_handle h, double* move_ms, double* render_ms, double* judge_ms, int64_t* steps);
 
 /* Test hook.  bit0: force the generic rotate path (pygame's per-pixel range tests and background colour) even
  * when the window corners prove it unnecessary -- the reference's crop sizes never need it, so this is the only

@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (/root/reference) on top of the shims.
 
 TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py in the build container
-to produce tests/golden/*; /root/reference does not exist on the GPU box, so
-nothing that runs there imports this module.
+to produce tests/golden/*; /root/reference does not exist on the GPU box: there only
+bench.py's CPU-baseline / `--impl reference` legs import this module, on the copy that
+oracle/make_ref.py staged under oracle/_ref/ (kind "reference-on-shims").
 """
 from __future__ import annotations
 
@@ -10,8 +11,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CARLABEV_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "shims")
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte copy staged by oracle/make_ref.py."""
+    for cand in (os.environ.get("CARLABEV_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "CarlaBEV")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available() -> bool:

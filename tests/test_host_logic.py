@@ -150,7 +150,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/cbev.h but not exported"
     assert set(engine.EXPORTS) == declared
-    assert lib.cbev_version() == 100
+    assert lib.cbev_version() == 200
     # struct layouts agree between the header (compiled) and the ctypes mirror
     sizes = [ctypes.c_int32() for _ in range(3)]
     lib.cbev_abi_sizes(*[ctypes.byref(s) for s in sizes])
@@ -543,17 +543,28 @@ def test_vector_env_host_logic_with_a_stub_engine(monkeypatch):
                 self.episode[1, E.EPISODE_FIELDS.index("return")] = 1.25
                 self.episode[1, E.EPISODE_FIELDS.index("cause")] = 2
 
+        def step_host_full(self, a, episode=True):   # host mirrors = the device buffers themselves on the CPU
+            self.step(a)
+            self.host_reward, self.host_terminated, self.host_truncated = self.reward, self.terminated, self.truncated
+            self.host_episode = self.episode
+
+        def wait_host_outputs(self): pass
+        def invalidate(self): pass
+
     monkeypatch.setattr(E, "Engine", StubEngine)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(synchronize=lambda: None))
     envs = V.make_env(RunConfig(env=EnvConfig(action_mode="continuous"), num_envs=4))
-    with pytest.raises(RuntimeError):   # nothing to reset from yet
-        envs.reset()
+    with pytest.raises(RuntimeError):   # an explicit draw from a pool that does not exist
+        envs.reset(options={"scene": "pool"})
+    # no pool, no scene: the reference's default, scene="rdm" seeded with cfg.seed (scene_generator.py:97)
+    obs, info = envs.reset()
+    assert info["scenario"]["scene"].tolist() == ["rdm"] * 4 and info["scenario"]["scene_seed"].tolist() == [0] * 4
     obs, info = envs.reset(seed=7, options={"scene": "lead_brake", "level": 2})
     assert obs.shape == (4, 24, 96, 96)
     assert info["scenario"]["scene_seed"].tolist() == [7, 8, 9, 10] and info["_scenario"].all()   # env i seeded s + i
     assert info["scenario"]["scene"].tolist() == ["lead_brake"] * 4 and info["spawn_validation"]["valid"].all()
-    assert envs.engine.pools[-1] == 4
+    assert envs.engine.pools[-1] == 5
     for _ in range(3):
         _, rew, term, trunc, inf = envs.step(np.zeros((4, 3), np.float32))
     assert term.tolist() == [False, True, False, False] and inf["_episode"].tolist() == [False, True, False, False]
@@ -565,7 +576,7 @@ def test_vector_env_host_logic_with_a_stub_engine(monkeypatch):
     obs, info = envs.reset(options={"scene": "rdm", "num_vehicles": 2, "scene_seed": 5, "reset_mask": mask})
     ids, m = envs.engine.resets[-1]
     assert m.tolist() == mask.tolist() and info["scenario"]["scene"].tolist() == [None, "rdm", None, None]
-    assert envs.engine.pools[-1] == 5 and not envs._needs_reset.any()
+    assert envs.engine.pools[-1] == 6 and not envs._needs_reset.any()
     envs.step(np.zeros((4, 3), np.float32))
     # the same options again hit the cache: no new upload
     n_up = len(envs.engine.pools)
@@ -580,18 +591,21 @@ def test_vector_env_host_logic_with_a_stub_engine(monkeypatch):
 
 
 def test_bench_pool_is_generated_once_per_box(tmp_path):
-    """bench.py under torchrun: rank 0 generates the scene pool and publishes the file atomically, the other ranks
-    only wait for it (no collective is pending meanwhile, nobody generates twice)."""
+    """bench.py under torchrun: every rank generates ITS share of the scene pool on its share of the host cores and
+    publishes the part atomically; all ranks assemble the same pool (no collective is pending meanwhile, nobody
+    generates a scene twice)."""
     import subprocess
     import sys
 
     code = ("import sys; sys.path.insert(0, %r); import bench; "
-            "s = bench.build_pool(96); print(len(s), int(s[95]['seed']))" % ROOT)
+            "s = bench._shared_pool('lead_brake', [dict(scene='lead_brake', level=1 + i %% 3, scene_seed=i) "
+            "for i in range(96)], 182); print(len(s), int(s[95]['seed']), int(s[0]['seed']), int(s[1]['seed']))" % ROOT)
     env = {**os.environ, "TMPDIR": str(tmp_path), "WORLD_SIZE": "2"}
     procs = [subprocess.Popen([sys.executable, "-c", code], env={**env, "RANK": str(r)}, stdout=subprocess.PIPE,
                               stderr=subprocess.PIPE, text=True) for r in (1, 0)]
     outs = [p.communicate(timeout=300) for p in procs]
     assert [p.returncode for p in procs] == [0, 0], outs
-    assert [o[0].strip() for o in outs] == ["96 95", "96 95"]
-    assert "scenes generated" in outs[1][1] and "scenes generated" not in outs[0][1]   # only rank 0 built it
-    assert os.listdir(os.path.join(tmp_path, "cbev_bench_pools")) == ["pool_lead_brake_96.npz"]
+    assert [o[0].strip() for o in outs] == ["96 95 0 1", "96 95 0 1"]
+    assert all("48 of 96 scenes generated" in o[1] for o in outs)   # each rank built its half
+    assert sorted(os.listdir(os.path.join(tmp_path, "cbev_bench_pools"))) == ["pool_lead_brake_96.w2.r0.npz",
+                                                                              "pool_lead_brake_96.w2.r1.npz"]
