@@ -83,9 +83,11 @@ def _shared_pool(tag, requests, pad):
         t0 = time.time()
         mine = build(requests[rank::world], pad=pad, workers=_host_workers())
         tmp = f"{part}.{os.getpid()}.tmp.npz"
-        save_pool(tmp, mine)
-        os.replace(tmp, part)
+        save_pool(tmp, mine, compress=False)
+        os.replace(tmp, whole if world == 1 else part)
         _log(f"pool {tag}: {len(mine)} of {n} scenes generated in {time.time() - t0:.1f} s on {_host_workers()} cores")
+        if world == 1:
+            return mine
     parts = []
     deadline = time.time() + 900.0
     for r in range(world):
@@ -98,11 +100,6 @@ def _shared_pool(tag, requests, pad):
     scenes = [None] * n
     for r in range(world):
         scenes[r::world] = parts[r]
-    if rank == 0 and world == 1:
-        try:
-            os.replace(part, whole)
-        except OSError:
-            pass
     return scenes
 
 

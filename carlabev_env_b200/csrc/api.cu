@@ -141,6 +141,89 @@ static int use_device(cbev_handle e) {
   return CBEV_OK;
 }
 
+// Second half of a pool change (cbev_upload_scene_pool / cbev_generate_scenes): per-env buffers that depend on the
+// pool, the open-loop trajectory tables, and the swap.  `d` is complete on entry and is freed on failure.
+static int install_pool(cbev_engine* e, PoolDev& d, const int32_t* actor_off_host, bool live) {
+  const int n = d.n_scenes;
+  const size_t na = (size_t)d.n_actors_total;
+  const int max_retreat = d.max_retreat, max_tl = d.max_tl;
+  int rc = 0;
+  // ---- per-env buffers that depend on the pool ----
+  const size_t Rn = (size_t)(max_retreat ? max_retreat : 1), Ro = (size_t)(e->pool.max_retreat ? e->pool.max_retreat : 1);
+  const int32_t new_max_rects = e->cfg.max_actors + CBEV_MAX_TARGETS + max_tl + 1;
+  uint32_t* rects = nullptr;
+  double* retreat = nullptr;
+  int32_t* retreat_n = nullptr;
+  const bool grow_rects = !e->rects || new_max_rects > e->max_rects;
+  const bool grow_retreat = !e->st.retreat || !live || Rn != Ro;
+  if (grow_rects) rc |= dev_alloc(&rects, (size_t)e->N * CBEV_RECT_WORDS * new_max_rects);
+  if (grow_retreat) {
+    rc |= dev_alloc(&retreat, (size_t)e->N * Rn * 3 * CBEV_SG_MAX);
+    rc |= dev_alloc(&retreat_n, (size_t)e->N * Rn);
+    if (!rc && live && e->st.retreat) {  // running envs keep the retreat routes they are following (new row stride)
+      const size_t row_o = Ro * 3 * CBEV_SG_MAX * sizeof(double), row_n = Rn * 3 * CBEV_SG_MAX * sizeof(double);
+      if (cudaMemcpy2D(retreat, row_n, e->st.retreat, row_o, row_o, (size_t)e->N, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+          cudaMemcpy2D(retreat_n, Rn * sizeof(int32_t), e->st.retreat_n, Ro * sizeof(int32_t), Ro * sizeof(int32_t),
+                       (size_t)e->N, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+        cbev_set_error("copying the retreat routes failed");
+        rc = CBEV_ERR_CUDA;
+      }
+    }
+  }
+  // ---- open-loop actor trajectories: roll every scene out once on the device (k_rollout) ----
+  int T = live ? e->pool.traj_steps : e->cfg.trajectory_steps;  // the hand-over step never moves under running envs
+  if (!rc && T > 0 && na > 0) {
+    const size_t budget = (size_t)4 << 30;  // cap the tables at 4 GiB
+    if (!live) {
+      while (T > 16 && (size_t)T * na * sizeof(double4) > budget) T /= 2;
+    } else if ((size_t)T * na * sizeof(double4) > 2 * budget) {
+      cbev_set_error("the extended pool needs %zu bytes of trajectory tables at the %d steps fixed by the first upload",
+                     (size_t)T * na * sizeof(double4), T);
+      rc = CBEV_ERR_NOMEM;
+    }
+    std::vector<long long> off((size_t)n);
+    long long acc = 0;
+    for (int s2 = 0; s2 < n; ++s2) {
+      off[s2] = acc;
+      acc += (long long)T * (actor_off_host[s2 + 1] - actor_off_host[s2]);
+    }
+    const size_t S = (size_t)n, A = (size_t)(e->cfg.max_actors > 0 ? e->cfg.max_actors : 1);
+    EnvState& r = d.roll;
+    if (!rc) {
+      rc |= dev_upload(&d.traj_off, off.data(), S);
+      rc |= dev_alloc(&d.traj, (size_t)acc);
+      rc |= dev_alloc(&r.ax, S * A); rc |= dev_alloc(&r.ay, S * A); rc |= dev_alloc(&r.ayaw, S * A);
+      rc |= dev_alloc(&r.av, S * A); rc |= dev_alloc(&r.atarget_mps, S * A); rc |= dev_alloc(&r.aelapsed, S * A);
+      rc |= dev_alloc(&r.astate_elapsed, S * A); rc |= dev_alloc(&r.atidx, S * A); rc |= dev_alloc(&r.arxlen, S * A);
+      rc |= dev_alloc(&r.aflags, S * A);
+      rc |= dev_alloc(&r.retreat, S * Rn * 3 * CBEV_SG_MAX);
+      rc |= dev_alloc(&r.retreat_n, S * Rn);
+    }
+    if (!rc) d.traj_steps = T;
+  }
+  if (rc) {
+    free_pool(d);
+    dev_free(rects); dev_free(retreat); dev_free(retreat_n);
+    return rc;
+  }
+  // ---- swap in ----
+  free_pool(e->pool);
+  e->pool = d;
+  if (grow_rects) { dev_free(e->rects); e->rects = rects; e->max_rects = new_max_rects; }
+  if (grow_retreat) { dev_free(e->st.retreat); dev_free(e->st.retreat_n); e->st.retreat = retreat; e->st.retreat_n = retreat_n; }
+  e->has_pool = true;
+  if (e->pool.traj_steps > 0) {
+    cbev_launch_rollout(e, 0);
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) {
+      cbev_set_error("trajectory roll-out failed: %s", cudaGetErrorString(ce));
+      e->has_pool = false;
+      return CBEV_ERR_CUDA;
+    }
+  }
+  return CBEV_OK;
+}
+
 extern "C" {
 
 int cbev_version(void) { return CBEV_VERSION; }
@@ -412,79 +495,137 @@ int cbev_upload_scene_pool(cbev_handle e, const cbev_pool_desc* p) {
   rc |= dev_upload(&d.tl_color, p->tl_color, ntl);
   if (p->sg_mat) rc |= dev_upload(&d.sg_mat, p->sg_mat, (size_t)(CBEV_SG_MAX + 1) * CBEV_SG_MAX * CBEV_SG_MAX);
   if (rc) { free_pool(d); return rc; }
-  // ---- per-env buffers that depend on the pool ----
-  const size_t Rn = (size_t)(max_retreat ? max_retreat : 1), Ro = (size_t)(e->pool.max_retreat ? e->pool.max_retreat : 1);
-  const int32_t new_max_rects = e->cfg.max_actors + CBEV_MAX_TARGETS + max_tl + 1;
-  uint32_t* rects = nullptr;
-  double* retreat = nullptr;
-  int32_t* retreat_n = nullptr;
-  const bool grow_rects = !e->rects || new_max_rects > e->max_rects;
-  const bool grow_retreat = !e->st.retreat || !live || Rn != Ro;
-  if (grow_rects) rc |= dev_alloc(&rects, (size_t)e->N * CBEV_RECT_WORDS * new_max_rects);
-  if (grow_retreat) {
-    rc |= dev_alloc(&retreat, (size_t)e->N * Rn * 3 * CBEV_SG_MAX);
-    rc |= dev_alloc(&retreat_n, (size_t)e->N * Rn);
-    if (!rc && live && e->st.retreat) {  // running envs keep the retreat routes they are following (new row stride)
-      const size_t row_o = Ro * 3 * CBEV_SG_MAX * sizeof(double), row_n = Rn * 3 * CBEV_SG_MAX * sizeof(double);
-      if (cudaMemcpy2D(retreat, row_n, e->st.retreat, row_o, row_o, (size_t)e->N, cudaMemcpyDeviceToDevice) != cudaSuccess ||
-          cudaMemcpy2D(retreat_n, Rn * sizeof(int32_t), e->st.retreat_n, Ro * sizeof(int32_t), Ro * sizeof(int32_t),
-                       (size_t)e->N, cudaMemcpyDeviceToDevice) != cudaSuccess) {
-        cbev_set_error("copying the retreat routes failed");
-        rc = CBEV_ERR_CUDA;
-      }
+  return install_pool(e, d, p->actor_off, live);
+}
+
+// Device-side generation of scripted scenes: see include/cbev.h.
+int cbev_generate_scenes(cbev_handle e, int32_t n, const uint8_t* kinds, const int32_t* levels, const int64_t* seeds,
+                         const double* sg_mat, int32_t* attempts_host) {
+  if (!e || !kinds || !levels || !seeds || !sg_mat) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
+  if (!e->has_map) { cbev_set_error("no map uploaded (cbev_upload_map): spawn validation needs it"); return CBEV_ERR_STATE; }
+  if (n < 1) { cbev_set_error("scene pool is empty"); return CBEV_ERR_ARG; }
+  // the layout of a scripted scene is a function of (kind, level): actors and route lengths are known up front
+  std::vector<int32_t> ego_off(n + 1), rew_off(n + 1), actor_off(n + 1), tl_off(n + 1, 0), route_off(1, 0), raw_off(1, 0), slots;
+  int max_actors = 0, max_retreat = 0;
+  for (int s = 0; s < n; ++s) {
+    const int lv = levels[s];
+    if ((kinds[s] != 1 && kinds[s] != 2) || lv < 1 || lv > 4 || (kinds[s] == 1 && lv > 3) || seeds[s] < 0) {
+      cbev_set_error("scene %d: kind must be 1 (lead_brake, levels 1-3) or 2 (jaywalk, levels 1-4) and the seed >= 0", s);
+      return CBEV_ERR_ARG;
     }
+    ego_off[s] = 6 * s; rew_off[s] = 6 * s; actor_off[s] = (int32_t)slots.size();
+    int nret = 0;
+    auto add = [&](int pts, bool retreat) {
+      route_off.push_back(route_off.back() + pts);
+      raw_off.push_back(raw_off.back() + pts);
+      slots.push_back(retreat ? nret++ : -1);
+    };
+    if (kinds[s] == 1) {            // lead_brake.py: lead (6) [+ left lane (7)] [+ rear (6)]
+      add(6, false);
+      if (lv >= 2) add(7, false);
+      if (lv >= 3) add(6, false);
+    } else {                        // jaywalk.py: [rear vehicle (6) at level 4] + pedestrian (8); StopReturn from level 3
+      if (lv >= 4) add(6, false);
+      add(8, lv >= 3);
+    }
+    max_actors = std::max(max_actors, (int)slots.size() - actor_off[s]);
+    max_retreat = std::max(max_retreat, nret);
   }
-  // ---- open-loop actor trajectories: roll every scene out once on the device (k_rollout) ----
-  int T = live ? e->pool.traj_steps : e->cfg.trajectory_steps;  // the hand-over step never moves under running envs
-  if (!rc && T > 0 && na > 0) {
-    const size_t budget = (size_t)4 << 30;  // cap the tables at 4 GiB
-    if (!live) {
-      while (T > 16 && (size_t)T * na * sizeof(double4) > budget) T /= 2;
-    } else if ((size_t)T * na * sizeof(double4) > 2 * budget) {
-      cbev_set_error("the extended pool needs %zu bytes of trajectory tables at the %d steps fixed by the first upload",
-                     (size_t)T * na * sizeof(double4), T);
-      rc = CBEV_ERR_NOMEM;
-    }
-    std::vector<long long> off((size_t)n);
-    long long acc = 0;
-    for (int s2 = 0; s2 < n; ++s2) {
-      off[s2] = acc;
-      acc += (long long)T * (p->actor_off[s2 + 1] - p->actor_off[s2]);
-    }
-    const size_t S = (size_t)n, A = (size_t)(e->cfg.max_actors > 0 ? e->cfg.max_actors : 1);
-    EnvState& r = d.roll;
-    if (!rc) {
-      rc |= dev_upload(&d.traj_off, off.data(), S);
-      rc |= dev_alloc(&d.traj, (size_t)acc);
-      rc |= dev_alloc(&r.ax, S * A); rc |= dev_alloc(&r.ay, S * A); rc |= dev_alloc(&r.ayaw, S * A);
-      rc |= dev_alloc(&r.av, S * A); rc |= dev_alloc(&r.atarget_mps, S * A); rc |= dev_alloc(&r.aelapsed, S * A);
-      rc |= dev_alloc(&r.astate_elapsed, S * A); rc |= dev_alloc(&r.atidx, S * A); rc |= dev_alloc(&r.arxlen, S * A);
-      rc |= dev_alloc(&r.aflags, S * A);
-      rc |= dev_alloc(&r.retreat, S * Rn * 3 * CBEV_SG_MAX);
-      rc |= dev_alloc(&r.retreat_n, S * Rn);
-    }
-    if (!rc) d.traj_steps = T;
+  ego_off[n] = rew_off[n] = 6 * n;
+  actor_off[n] = (int32_t)slots.size();
+  if (max_actors > e->cfg.max_actors) { cbev_set_error("generated scenes have up to %d actors but the engine was created with max_actors=%d", max_actors, e->cfg.max_actors); return CBEV_ERR_ARG; }
+  const bool live = e->was_reset && e->has_pool;
+  if (live) {
+    if (n < e->pool.n_scenes) { cbev_set_error("a pool generated while environments are running must extend the previous one"); return CBEV_ERR_ARG; }
+    CU_TRY(cudaDeviceSynchronize());
+    if (max_retreat < e->pool.max_retreat) max_retreat = e->pool.max_retreat;
   }
-  if (rc) {
-    free_pool(d);
-    dev_free(rects); dev_free(retreat); dev_free(retreat_n);
-    return rc;
-  }
-  // ---- swap in ----
-  free_pool(e->pool);
-  e->pool = d;
-  if (grow_rects) { dev_free(e->rects); e->rects = rects; e->max_rects = new_max_rects; }
-  if (grow_retreat) { dev_free(e->st.retreat); dev_free(e->st.retreat_n); e->st.retreat = retreat; e->st.retreat_n = retreat_n; }
-  e->has_pool = true;
-  if (e->pool.traj_steps > 0) {
-    cbev_launch_rollout(e, 0);
+  const size_t na = slots.size(), npts = (size_t)route_off.back();
+  PoolDev d;
+  d.n_scenes = n; d.n_actors_total = (int32_t)na; d.max_actors = max_actors; d.max_targets = 6; d.max_tl = 0;
+  d.max_retreat = max_retreat;
+  int rc = 0;
+  rc |= dev_alloc(&d.ego_state0, (size_t)n * 4); rc |= dev_alloc(&d.ego_target_speed, (size_t)n);
+  rc |= dev_alloc(&d.len_ego_route, (size_t)n); rc |= dev_alloc(&d.ego_tidx0, (size_t)n);
+  rc |= dev_alloc(&d.num_vehicles, (size_t)n);
+  rc |= dev_upload(&d.ego_off, ego_off.data(), (size_t)n + 1); rc |= dev_upload(&d.rew_off, rew_off.data(), (size_t)n + 1);
+  rc |= dev_upload(&d.actor_off, actor_off.data(), (size_t)n + 1); rc |= dev_upload(&d.tl_off, tl_off.data(), (size_t)n + 1);
+  rc |= dev_alloc(&d.ego_cx, (size_t)6 * n); rc |= dev_alloc(&d.ego_cy, (size_t)6 * n); rc |= dev_alloc(&d.ego_cyaw, (size_t)6 * n);
+  rc |= dev_alloc(&d.rew_rx, (size_t)6 * n); rc |= dev_alloc(&d.rew_ry, (size_t)6 * n); rc |= dev_alloc(&d.rew_cum, (size_t)6 * n);
+  rc |= dev_alloc(&d.act_kind, na); rc |= dev_alloc(&d.act_beh, na); rc |= dev_alloc(&d.act_state0, na * 4);
+  rc |= dev_alloc(&d.act_cruise_px, na); rc |= dev_alloc(&d.act_cruise_mps, na); rc |= dev_alloc(&d.act_beh_p, na * 4);
+  rc |= dev_alloc(&d.act_tidx0, na);
+  rc |= dev_upload(&d.act_route_off, route_off.data(), na + 1); rc |= dev_upload(&d.act_raw_off, raw_off.data(), na + 1);
+  rc |= dev_upload(&d.act_retreat_slot, slots.data(), na);
+  rc |= dev_alloc(&d.act_cx, npts); rc |= dev_alloc(&d.act_cy, npts); rc |= dev_alloc(&d.act_cyaw, npts);
+  rc |= dev_alloc(&d.act_raw_x, npts); rc |= dev_alloc(&d.act_raw_y, npts);
+  rc |= dev_alloc(&d.tl_rect, (size_t)4); rc |= dev_alloc(&d.tl_color, (size_t)1);
+  rc |= dev_upload(&d.sg_mat, sg_mat, (size_t)(CBEV_SG_MAX + 1) * CBEV_SG_MAX * CBEV_SG_MAX);
+  uint8_t* kinds_d = nullptr;
+  int32_t *levels_d = nullptr, *att_d = nullptr;
+  long long* seeds_d = nullptr;
+  rc |= dev_upload(&kinds_d, kinds, (size_t)n); rc |= dev_upload(&levels_d, levels, (size_t)n);
+  rc |= dev_upload(&seeds_d, (const long long*)seeds, (size_t)n); rc |= dev_alloc(&att_d, (size_t)n);
+  std::vector<int32_t> att((size_t)n, 0);
+  if (!rc) {
+    cbev_launch_generate(e, d, kinds_d, levels_d, seeds_d, att_d, 0);
     cudaError_t ce = cudaDeviceSynchronize();
-    if (ce != cudaSuccess) {
-      cbev_set_error("trajectory roll-out failed: %s", cudaGetErrorString(ce));
-      e->has_pool = false;
-      return CBEV_ERR_CUDA;
-    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(att.data(), att_d, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) { cbev_set_error("scene generation failed: %s", cudaGetErrorString(ce)); rc = CBEV_ERR_CUDA; }
   }
+  dev_free(kinds_d); dev_free(levels_d); dev_free(seeds_d); dev_free(att_d);
+  if (!rc)
+    for (int s = 0; s < n; ++s)
+      if (att[s] < 0) {  // the reference raises here (carlabev.py:129-131)
+        cbev_set_error("Failed to reset into a valid initial state after 10 attempts (scene %d, seed %lld)", s, (long long)seeds[s]);
+        rc = CBEV_ERR_ARG;
+        break;
+      }
+  if (attempts_host) memcpy(attempts_host, att.data(), (size_t)n * sizeof(int32_t));
+  if (rc) { free_pool(d); return rc; }
+  return install_pool(e, d, actor_off.data(), live);
+}
+
+int cbev_pool_counts(cbev_handle e, int32_t counts[8]) {
+  if (!e || !counts) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
+  if (!e->has_pool) { cbev_set_error("no scene pool"); return CBEV_ERR_STATE; }
+  const PoolDev& d = e->pool;
+  int32_t last[5] = {0, 0, 0, 0, 0};
+  const int n = d.n_scenes, na = d.n_actors_total;
+  CU_TRY(cudaMemcpy(&last[0], d.ego_off + n, 4, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(&last[1], d.rew_off + n, 4, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(&last[2], d.tl_off + n, 4, cudaMemcpyDeviceToHost));
+  if (na) {
+    CU_TRY(cudaMemcpy(&last[3], d.act_route_off + na, 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&last[4], d.act_raw_off + na, 4, cudaMemcpyDeviceToHost));
+  }
+  counts[0] = n; counts[1] = na; counts[2] = last[0]; counts[3] = last[1]; counts[4] = last[3]; counts[5] = last[4];
+  counts[6] = last[2]; counts[7] = d.traj_steps;
+  return CBEV_OK;
+}
+
+int cbev_read_scene_pool(cbev_handle e, const cbev_pool_desc* dst) {
+  if (!e || !dst) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
+  { int rc0 = use_device(e); if (rc0) return rc0; }
+  if (!e->has_pool) { cbev_set_error("no scene pool"); return CBEV_ERR_STATE; }
+  int32_t c[8];
+  int rc = cbev_pool_counts(e, c);
+  if (rc) return rc;
+  const PoolDev& d = e->pool;
+  const size_t n = (size_t)c[0], na = (size_t)c[1], nr = (size_t)c[2], nq = (size_t)c[3], np = (size_t)c[4], nw = (size_t)c[5],
+               ntl = (size_t)c[6];
+#define RD(field, count)                                                                                          \
+  if (dst->field && (count))                                                                                      \
+    CU_TRY(cudaMemcpy((void*)dst->field, d.field, (count) * sizeof(*d.field), cudaMemcpyDeviceToHost));
+  RD(ego_state0, n * 4) RD(ego_target_speed, n) RD(ego_tidx0, n) RD(len_ego_route, n) RD(num_vehicles, n)
+  RD(ego_off, n + 1) RD(rew_off, n + 1) RD(actor_off, n + 1) RD(tl_off, n + 1)
+  RD(ego_cx, nr) RD(ego_cy, nr) RD(ego_cyaw, nr) RD(rew_rx, nq) RD(rew_ry, nq) RD(rew_cum, nq)
+  RD(act_kind, na) RD(act_state0, na * 4) RD(act_tidx0, na) RD(act_cruise_px, na) RD(act_cruise_mps, na)
+  RD(act_beh, na) RD(act_beh_p, na * 4) RD(act_route_off, na + 1) RD(act_raw_off, na + 1)
+  RD(act_cx, np) RD(act_cy, np) RD(act_cyaw, np) RD(act_raw_x, nw) RD(act_raw_y, nw) RD(tl_rect, ntl * 4) RD(tl_color, ntl)
+#undef RD
   return CBEV_OK;
 }
 

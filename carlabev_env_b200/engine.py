@@ -40,7 +40,8 @@ EXPORTS = ("cbev_version", "cbev_last_error", "cbev_create", "cbev_destroy", "cb
            "cbev_read_stats", "cbev_launch_count", "cbev_profile_enable", "cbev_profile_read", "cbev_abi_sizes",
            "cbev_keep_fov", "cbev_upload_fov_mask", "cbev_fuse", "cbev_debug_rerender", "cbev_set_debug_flags",
            "cbev_debug_read_trace", "cbev_step_host_ex", "cbev_wait_host_outputs", "cbev_set_state",
-           "cbev_profile_read_ex", "cbev_step_ex", "cbev_invalidate")
+           "cbev_profile_read_ex", "cbev_step_ex", "cbev_invalidate", "cbev_generate_scenes", "cbev_pool_counts",
+           "cbev_read_scene_pool")
 
 
 class CbevConfig(C.Structure):
@@ -121,6 +122,9 @@ def load_library(build_if_missing: bool = True):
     lib.cbev_step_host_ex.argtypes = [_P, _P, C.POINTER(CbevStepOut), C.POINTER(CbevHostOut), _P]
     lib.cbev_step_ex.argtypes = [_P, _P, C.POINTER(CbevStepOut), C.POINTER(CbevHostOut), _P]
     lib.cbev_invalidate.argtypes = [_P]
+    lib.cbev_generate_scenes.argtypes = [_P, C.c_int32, _P, _P, _P, _P, _P]
+    lib.cbev_pool_counts.argtypes = [_P, _P]
+    lib.cbev_read_scene_pool.argtypes = [_P, C.POINTER(CbevPoolDesc)]
     lib.cbev_wait_host_outputs.argtypes = [_P]
     lib.cbev_set_state.argtypes = [_P, _P, _P]
     lib.cbev_profile_read_ex.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -320,6 +324,51 @@ class Engine:
         d.sg_mat = sg.ctypes.data
         _check(self.lib, self.lib.cbev_upload_scene_pool(self.handle, C.byref(d)))
         self.n_scenes = d.n_scenes
+
+    def generate_scripted_pool(self, kinds, levels, seeds):
+        """Row f2: generate lead_brake / jaywalk scenes ON THE DEVICE from (kind, level, scene_seed) and make them the
+        resident pool (cbev_generate_scenes).  kinds: "lead_brake" | "jaywalk" (or 1 | 2).  Returns the number of
+        samples every scene needed (the reference's reset retry loop)."""
+        ids = {"lead_brake": 1, "jaywalk": 2}
+        k = np.ascontiguousarray([ids.get(v, v) for v in kinds], dtype=np.uint8)
+        lv = np.ascontiguousarray(levels, dtype=np.int32)
+        sd = np.ascontiguousarray(seeds, dtype=np.int64)
+        assert len(k) == len(lv) == len(sd)
+        sg = np.ascontiguousarray(savgol_operators())
+        att = np.zeros(len(k), dtype=np.int32)
+        _check(self.lib, self.lib.cbev_generate_scenes(self.handle, len(k), k.ctypes.data, lv.ctypes.data, sd.ctypes.data,
+                                                       sg.ctypes.data, att.ctypes.data))
+        self.n_scenes = len(k)
+        return att
+
+    def read_pool(self) -> dict:
+        """The resident pool read back into host arrays (keys of pool.pack_pool that live on the device)."""
+        c = np.zeros(8, dtype=np.int32)
+        _check(self.lib, self.lib.cbev_pool_counts(self.handle, c.ctypes.data))
+        n, na, nr, nq, npts, nw, ntl = (int(v) for v in c[:7])
+        spec = (("ego_state0", np.float64, n * 4), ("ego_target_speed", np.float64, n), ("ego_tidx0", np.int32, n),
+                ("len_ego_route", np.float64, n), ("num_vehicles", np.int32, n), ("ego_off", np.int32, n + 1),
+                ("rew_off", np.int32, n + 1), ("actor_off", np.int32, n + 1), ("tl_off", np.int32, n + 1),
+                ("ego_cx", np.float64, nr), ("ego_cy", np.float64, nr), ("ego_cyaw", np.float64, nr),
+                ("rew_rx", np.int32, nq), ("rew_ry", np.int32, nq), ("rew_cum", np.float64, nq),
+                ("act_kind", np.uint8, na), ("act_state0", np.float64, na * 4), ("act_tidx0", np.int32, na),
+                ("act_cruise_px", np.float64, na), ("act_cruise_mps", np.float64, na), ("act_beh", np.uint8, na),
+                ("act_beh_p", np.float64, na * 4), ("act_route_off", np.int32, na + 1), ("act_raw_off", np.int32, na + 1),
+                ("act_cx", np.float64, npts), ("act_cy", np.float64, npts), ("act_cyaw", np.float64, npts),
+                ("act_raw_x", np.float64, nw), ("act_raw_y", np.float64, nw), ("tl_rect", np.int32, ntl * 4),
+                ("tl_color", np.uint8, ntl))
+        d = CbevPoolDesc()
+        out = {"n_scenes": n}
+        for key, dt, cnt in spec:
+            a = np.zeros(max(cnt, 1), dtype=dt)
+            out[key] = a[:cnt]
+            setattr(d, key, a.ctypes.data)
+        _check(self.lib, self.lib.cbev_read_scene_pool(self.handle, C.byref(d)))
+        out["ego_state0"] = out["ego_state0"].reshape(n, 4)
+        out["act_state0"] = out["act_state0"].reshape(na, 4)
+        out["act_beh_p"] = out["act_beh_p"].reshape(na, 4)
+        out["tl_rect"] = out["tl_rect"].reshape(ntl, 4)
+        return out
 
     # ------------------------------------------------------------------ stepping
     def _stream(self):

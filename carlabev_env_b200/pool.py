@@ -98,6 +98,9 @@ def pack_pool(scenes: list[dict]) -> dict:
 
 def unpack_pool(pool) -> list[dict]:
     """Inverse of pack_pool (accepts a dict or an open np.load handle)."""
+    # an open NpzFile decompresses the WHOLE array on every pool[key]: materialise each array exactly once
+    # (a 4096-scene pool took tens of minutes to unpack otherwise -- the round-1 "host-side pool bottleneck")
+    pool = {k: np.asarray(pool[k]) for k in (pool.files if hasattr(pool, "files") else pool.keys())}
     n = int(pool["n_scenes"])
     scenes = []
     aro, awo = pool["act_route_off"], pool["act_raw_off"]
@@ -127,8 +130,8 @@ def unpack_pool(pool) -> list[dict]:
     return scenes
 
 
-def save_pool(path, scenes: list[dict]) -> None:
-    np.savez_compressed(path, **pack_pool(scenes))
+def save_pool(path, scenes: list[dict], compress: bool = True) -> None:
+    (np.savez_compressed if compress else np.savez)(path, **pack_pool(scenes))
 
 
 def load_pool(path) -> list[dict]:

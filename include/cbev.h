@@ -212,6 +212,25 @@ int cbev_upload_map(cbev_handle h, const uint8_t* cls_host, int32_t w, int32_t h
 /* SceneGenerator output made device resident (see cbev_pool_desc).  Synchronous. */
 int cbev_upload_scene_pool(cbev_handle h, const cbev_pool_desc* pool);
 
+/* Row f2: the scripted scenarios generated ON THE DEVICE from (kind, level, scene_seed) -- SceneGenerator.build_scene
+ * for scene in {"lead_brake", "jaywalk"} (scene_generator.py:171-182 -> scenarios/lead_brake.py:18-129,
+ * scenarios/jaywalk.py:29-117) followed by Scene.load_scene with its spawn jitter and CarlaBEV.reset's validation /
+ * retry loop (carlabev.py:108-131).  One thread per scene: sha256-derived sub-seeds (randomness.py:13-16),
+ * np.random.default_rng = SeedSequence -> PCG64, Generator.integers / uniform in the reference's draw order.  The
+ * result replaces the engine's pool exactly like cbev_upload_scene_pool (append-only while envs are running).
+ * kinds[i]: 1 lead_brake (levels 1-3), 2 jaywalk (levels 1-4); sg_mat as in cbev_pool_desc; attempts_host (nullable)
+ * receives the number of samples each scene needed.  Drawn parameters, raw routes, behaviour parameters and spawn
+ * jitter are bit-identical to the reference; smoothed routes agree to ~1e-12 px (SciPy's LAPACK edge fit is not
+ * reproducible operation for operation).  Synchronous. */
+int cbev_generate_scenes(cbev_handle h, int32_t n, const uint8_t* kinds, const int32_t* levels, const int64_t* seeds,
+                         const double* sg_mat, int32_t* attempts_host);
+
+/* Debug / parity: sizes of the resident pool -- n_scenes, n_actors, ego route points, reward route points, actor
+ * route points, authored route points, traffic lights, rolled-out trajectory steps -- and a read-back of its arrays
+ * into the HOST buffers of a cbev_pool_desc (NULL members are skipped; sg_mat is not read back). */
+int cbev_pool_counts(cbev_handle h, int32_t counts[8]);
+int cbev_read_scene_pool(cbev_handle h, const cbev_pool_desc* dst_host);
+
 /* Observation ring owned by the caller: ring_slots frames per env, env-major.
  * frame bytes = cbev_frame_bytes(); layout [N][ring_slots][frame]. */
 int64_t cbev_frame_bytes(cbev_handle h);

@@ -17,6 +17,7 @@ from .sim import CAUSE_NAMES, DISCRETE9, DISCRETE13, SceneSim
 
 def unpack_pool(npz):
     """Inverse of carlabev_env_b200.pool.pack_pool: dict of concatenated arrays -> list of scene dicts."""
+    npz = {k: np.asarray(npz[k]) for k in (npz.files if hasattr(npz, "files") else npz.keys())}  # decompress once
     n = int(npz["n_scenes"])
     scenes = []
     per_scene = ["ego_state0", "ego_target_speed", "ego_tidx0", "route_length_m", "len_ego_route", "num_vehicles",

@@ -1,0 +1,243 @@
+"""Round-2 GPU tests: limits lifted since round 1 (ego routes with more than 64 targets, camera anchors whose crop
+exceeds one TMA box), pool growth while environments are mid-episode, the actor half of cbev_set_state, the set_point
+columns of the `vector` observation, and a second engine on another device."""
+import numpy as np
+import pytest
+
+from golden_util import load_map
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def _check(t, i, eng_hero, rew, term, obs, oracle, action):
+    o, r, te, tr, _ = oracle.step(action)
+    e = oracle.sim.ego
+    assert np.allclose(eng_hero[:4], [e.x, e.y, e.yaw, e.v], rtol=1e-9, atol=1e-9), (t, i, "pose")
+    assert abs(r - rew) < 1e-9 and te == term, (t, i, "reward / done", r, rew)
+    assert np.array_equal(obs, o), (t, i, "observation", int((obs != o).sum()))
+    return te
+
+
+def _pursuit(oracle, rng):
+    e = oracle.sim.ego
+    k = min(int(e.tidx) + 2, len(e.cx) - 1)
+    err = np.arctan2(e.cy[k] - e.y, e.cx[k] - e.x) - e.yaw
+    err = (err + np.pi) % (2 * np.pi) - np.pi
+    return np.clip([0.7 if e.v < 25.0 else 0.0, 2.0 * err + rng.normal(0, 0.05), 1.0 if e.v > 32.0 else 0.0],
+                   [0, -1, 0], [1, 1, 1]).astype(np.float32)
+
+
+def test_ego_routes_with_more_than_64_targets():
+    """Round 1 rejected ego routes of more than 64 points (one 64-bit visibility word); now two words = 128 targets.
+    The ego drives the route (pursuit), so targets beyond index 63 are drawn, consumed and rewarded."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.pool import pack_pool
+    from oracle.env import OracleEnv
+
+    cls = load_map()
+    scenes = []
+    seed = 0
+    while len(scenes) < 4 and seed < 200:
+        try:
+            s = S.build_scene(dict(scene="rdm", num_vehicles=3, route_dist_range=[230, 330], scene_seed=seed), cls_map=cls)
+            if len(s["ego_cx"]) > 70:
+                scenes.append(s)
+        except RuntimeError:
+            pass
+        seed += 1
+    assert len(scenes) == 4, "no long routes found"
+    assert max(len(s["ego_cx"]) for s in scenes) <= 128
+    n = len(scenes)
+    eng = E.Engine(n, action_mode=E.ACTION_CONTINUOUS, max_actors=4, ring_budget_bytes=64 << 20, trajectory_steps=0)
+    eng.upload_map(cls)
+    eng.upload_pool(pack_pool(scenes))
+    oracles = [OracleEnv(cls, action_mode="continuous") for _ in range(n)]
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i]))
+    rng = np.random.default_rng(0)
+    alive = np.ones(n, bool)
+    best = 0
+    for t in range(700):
+        a = np.stack([_pursuit(o, rng) for o in oracles])
+        eng.step(torch.from_numpy(a).cuda())
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, hero = eng.terminated.cpu().numpy().astype(bool), eng.hero.cpu().numpy()
+        for i in range(n):
+            if alive[i]:
+                alive[i] = not _check(t, i, hero[i], rew[i], term[i], obs[i], oracles[i], a[i])
+                best = max(best, int(oracles[i].sim.ego.tidx))
+        if not alive.any():
+            break
+    assert best > 64, f"no env drove past target 64 (best {best})"
+    eng.close()
+
+
+@pytest.mark.parametrize("anchor", [(0.1, 0.9), (0.0, 1.0), (0.95, 0.5)])
+def test_camera_anchor_near_a_border(anchor):
+    """Anchors close to a border need crops of up to 360 px (round 1 rejected anything above 241 px): the raster kernel
+    fetches only the 184 x 208 window a frame can sample, whatever the crop size."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import pack_pool
+    from carlabev_env_b200.scenes import build_scene
+    from oracle.env import OracleEnv
+    from oracle.raster import FovGeometry
+
+    cls = load_map()
+    pad = FovGeometry(128, *anchor).pad
+    assert pad > 241
+    reqs = [dict(scene="rdm", num_vehicles=12, route_dist_range=[30, 90], scene_seed=300 + i) for i in range(6)]
+    reqs += [dict(scene="lead_brake", level=3, scene_seed=7), dict(scene="jaywalk", level=3, scene_seed=8)]
+    scenes = [build_scene(r, cls_map=cls, pad=pad) for r in reqs]
+    n = len(scenes)
+    eng = E.Engine(n, action_mode=E.ACTION_CONTINUOUS, max_actors=14, ring_budget_bytes=64 << 20, anchor=anchor,
+                   mask_mode="7-class")
+    eng.upload_map(cls)
+    eng.upload_pool(pack_pool(scenes))
+    oracles = [OracleEnv(cls, action_mode="continuous", anchor=anchor, semantic_mask_ch="7-class") for _ in range(n)]
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i])), (i, "reset observation")
+    rng = np.random.default_rng(1)
+    alive = np.ones(n, bool)
+    for t in range(120):
+        a = np.stack([_pursuit(o, rng) if i % 2 == 0 else
+                      np.array([rng.uniform(0, 1), rng.uniform(-1, 1), rng.uniform(0, 0.3)], np.float32)
+                      for i, o in enumerate(oracles)])
+        eng.step(torch.from_numpy(a).cuda())
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, hero = eng.terminated.cpu().numpy().astype(bool), eng.hero.cpu().numpy()
+        for i in range(n):
+            if alive[i]:
+                alive[i] = not _check(t, i, hero[i], rew[i], term[i], obs[i], oracles[i], a[i])
+        if not alive.any():
+            break
+    assert t > 20
+    eng.close()
+
+
+def test_pool_grows_while_envs_are_mid_episode():
+    """re-uploading the pool while environments run must not disturb them -- in particular not the
+    StopReturn retreat route a pedestrian is following, and not the table -> live hand-over step."""
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import pack_pool
+    from carlabev_env_b200.scenes import build_scripted_scene
+    from oracle.env import OracleEnv
+
+    cls = load_map()
+    first = [build_scripted_scene("jaywalk", 40 + i, level=3, cls_map=cls) for i in range(4)]
+    first += [build_scripted_scene("lead_brake", 60 + i, level=2, cls_map=cls) for i in range(2)]
+    more = [build_scripted_scene("jaywalk", 80 + i, level=3 + i % 2, cls_map=cls) for i in range(4)]
+    more += [build_scripted_scene("lead_brake", 90, level=3, cls_map=cls)]
+    n = len(first)
+    eng = E.Engine(n, action_mode=E.ACTION_CONTINUOUS, max_actors=4, ring_budget_bytes=64 << 20, trajectory_steps=24)
+    eng.upload_map(cls)
+    eng.upload_pool(pack_pool(first))
+    oracles = [OracleEnv(cls, action_mode="continuous") for _ in range(n)]
+    scene_of = list(range(n))
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(first[i]))
+    pool = list(first)
+    crawl = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (n, 1))  # brake: the ego waits, the pedestrians play out
+    retreating = 0
+    for t in range(110):
+        if t in (30, 45, 70):  # past the hand-over (24 steps); some pedestrians are on their retreat route by now
+            pool = pool + more[: {30: 2, 45: 4, 70: 5}[t] - (len(pool) - n)]
+            eng.upload_pool(pack_pool(pool))
+            # a finished or arbitrary env moves to one of the NEW scenes, everyone else keeps running
+            j = t % n
+            mask = np.zeros(n, bool)
+            mask[j] = True
+            ids = np.array(scene_of, dtype=np.int32)
+            ids[j] = len(pool) - 1
+            scene_of[j] = len(pool) - 1
+            o = eng.reset(torch.from_numpy(ids), mask).cpu().numpy()
+            assert np.array_equal(o[j], oracles[j].reset(pool[scene_of[j]])), (t, j, "masked reset onto a new scene")
+        eng.step(torch.from_numpy(crawl).cuda())
+        obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+        term, hero = eng.terminated.cpu().numpy().astype(bool), eng.hero.cpu().numpy()
+        _, act = eng.get_state(4)
+        for i in range(n):
+            done = _check(t, i, hero[i], rew[i], term[i], obs[i], oracles[i], crawl[i])
+            ref = np.array([[b.x, b.y, b.yaw, b.v] for b in oracles[i].sim.actors])
+            assert np.allclose(act[i, :len(ref), :4], ref, rtol=1e-9, atol=1e-9), (t, i, "actor poses")
+            retreating += int(any(int(f) & 32 for f in act[i, :len(ref), 7]))
+            assert not done, "braking egos do not terminate in these scenes"
+    assert retreating > 0, "no pedestrian was on its retreat route during the test"
+    with pytest.raises(E.CbevError, match="extend"):
+        eng.upload_pool(pack_pool(first[:2]))
+    eng.close()
+
+
+def test_set_state_round_trip_and_vector_observation_set_point():
+    import torch
+
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+    from carlabev_env_b200.pool import load_shipped_pool
+    from oracle.env import OracleEnv
+
+    cls = load_map()
+    scenes = load_shipped_pool("rdm_rt_medium_v1")[:5]
+    n = len(scenes)
+    envs = make_env(RunConfig(env=EnvConfig(action_mode="continuous"), num_envs=n), scenes=scenes,
+                    ring_budget_bytes=64 << 20)
+    eng = envs.engine
+    envs.reset(options={"scene_ids": np.arange(n)})
+    oracles = [OracleEnv(cls, action_mode="continuous") for _ in range(n)]
+    for i in range(n):
+        oracles[i].reset(scenes[i])
+    rng = np.random.default_rng(5)
+    for t in range(25):
+        a = np.stack([_pursuit(o, rng) for o in oracles])
+        obs, rew, term, trunc, infos = envs.step(a)
+        for i in range(n):
+            oracles[i].step(a[i])
+        vec = envs.vector_observation().cpu().numpy()   # state ++ set_point (carlabev.py:237-244), float32
+        for i in range(n):
+            e = oracles[i].sim.ego
+            want = np.array([e.x, e.y, e.yaw, e.v, e.cx[e.tidx], e.cy[e.tidx], e.cyaw[e.tidx]]).astype(np.float32)
+            assert np.array_equal(vec[i], want), (t, i, vec[i], want)
+        if t == 10:  # cbev_get_state -> cbev_set_state is the identity, for the ego and for every actor column
+            ego, act = eng.get_state()
+            eng.set_state(ego, act)
+            ego2, act2 = eng.get_state()
+            assert np.array_equal(ego, ego2) and np.array_equal(act, act2)
+    # actors can be moved (live stepping): park actor 0 of env 0 somewhere else and read it back
+    ego, act = eng.get_state()
+    act[0, 0, 0] += 5.0
+    eng.set_state(None, act)
+    assert eng.get_state()[1][0, 0, 0] == act[0, 0, 0]
+    envs.close()
+
+
+def test_two_engines_on_two_devices():
+    """constant tables / shared-memory opt-in are per device, entry points select the engine's device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import pack_pool
+    from carlabev_env_b200.scenes import build_scripted_scene
+
+    cls = load_map()
+    scenes = [build_scripted_scene("lead_brake", 3 + i, level=1 + i % 3, cls_map=cls) for i in range(4)]
+    outs = []
+    for dev in (0, 1):
+        eng = E.Engine(4, action_mode=E.ACTION_CONTINUOUS, max_actors=4, ring_budget_bytes=64 << 20, device=dev)
+        eng.upload_map(cls)
+        eng.upload_pool(pack_pool(scenes))
+        torch.cuda.set_device(0)  # the caller's current device is not the engine's
+        eng.reset(torch.arange(4, dtype=torch.int32, device=f"cuda:{dev}"))
+        eng.step(torch.full((4, 3), 0.5, device=f"cuda:{dev}"))
+        outs.append((eng.obs().cpu().numpy().copy(), eng.reward.cpu().numpy().copy()))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])

@@ -14,6 +14,11 @@ from golden_util import load_map
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 M64 = (1 << 64) - 1
+# Poses: the bar is 1e-5 relative after 1000 steps (BASELINE.json).  Live-stepped actors in closed-loop Stanley control
+# amplify the 1-2 ulp differences between CUDA's and glibc's sincos / tan / atan2: 2e-9 was observed on a turning
+# red_light_runner adversary after 76 steps; 1e-7 leaves two decades of margin to the bar.  Flags, rewards (1e-9) and
+# every observation value stay exact.
+POSE_TOL = 1e-7
 
 
 def _splitmix64(z):
@@ -86,13 +91,13 @@ def run_scale_parity(scenes, n_envs, *, steps, make_actions, engine_kw, oracle_k
                     done[j] = False
                     n_auto += 1
                     continue
-                assert np.allclose(hero[j][:4], r["ego"], rtol=1e-9, atol=1e-9), (t, i, "ego pose")
+                assert np.allclose(hero[j][:4], r["ego"], rtol=POSE_TOL, atol=POSE_TOL), (t, i, "ego pose")
                 assert abs(r["reward"] - rew[j]) < 1e-9, (t, i, "reward", r["reward"], rew[j])
                 assert r["term"] == term[j] and r["trunc"] == trunc[j], (t, i, "flags")
                 assert np.array_equal(obs[j], r["obs"]), (t, i, "observation", int((obs[j] != r["obs"]).sum()))
                 if act is not None and len(r["actors"]):
                     na = len(r["actors"])
-                    assert np.allclose(act[j, :na, :4], r["actors"], rtol=1e-9, atol=1e-9), (t, i, "actor poses")
+                    assert np.allclose(act[j, :na, :4], r["actors"], rtol=POSE_TOL, atol=POSE_TOL), (t, i, "actor poses")
                 if r["term"] or r["trunc"]:
                     done[j] = True
                     episodes[j] += 1
