@@ -373,6 +373,8 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
     envs = make_env(cfg, scenes=scenes, autoreset="next_step", device=local, ring_slots=ring_slots,
                     raw_rgb=not semantic, host_infos=True)
     eng = envs.engine
+    if args.debug_flags:
+        eng.set_debug_flags(args.debug_flags)
     frame_bytes = eng.frame_bytes
     ids = ((torch.arange(N, dtype=torch.int64) + rank * N) % len(scenes)).numpy()
     envs.reset(options={"scene_ids": ids})
@@ -575,6 +577,8 @@ def main():
     ap.add_argument("--extras-budget", type=float, default=240.0,
                     help="seconds after which no further extra workload is started")
     ap.add_argument("--brake", action="store_true", help="diagnostic: constant full-brake actions (no resets)")
+    ap.add_argument("--debug-flags", type=int, default=0,
+                    help="diagnostic (cbev_set_debug_flags): 2 = k_judge serial on the main stream, 32 = identity CTA order")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

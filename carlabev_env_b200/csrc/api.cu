@@ -350,6 +350,8 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   rc |= dev_alloc(&e->st.arxlen, N * A);
   rc |= dev_alloc(&e->st.aflags, N * A);
   rc |= dev_alloc(&e->desc, N * CBEV_DESC_WORDS);
+  rc |= dev_alloc(&e->order, N);
+  rc |= dev_alloc(&e->order_cnt, (size_t)2);
   rc |= dev_alloc(&e->fov, N * (size_t)cfg->fov_size * cfg->fov_size);
   rc |= dev_alloc(&e->gstats, (size_t)CBEV_STATS_FIELDS);
   rc |= build_resize_tables(e);
@@ -369,6 +371,7 @@ int cbev_destroy(cbev_handle e) {
   free_pool(e->pool);
   free_state(e->st);
   dev_free(e->fov_mask); dev_free(e->rs_tab); dev_free(e->trace);
+  dev_free(e->order); dev_free(e->order_cnt);
   dev_free(e->map); dev_free(e->desc); dev_free(e->rects); dev_free(e->fov); dev_free(e->gstats);
   dev_free(e->h_reward_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }
@@ -708,12 +711,16 @@ int cbev_step_ex(cbev_handle e, const void* actions_dev, const cbev_step_out* ou
   cbev_launch_move(e, actions_dev, out, 0, e->N, s);
   if (prof) cudaEventRecord(pe[1], s);
   if ((rc = debug_sync("k_move", s))) return rc;
-  CU_TRY(cudaEventRecord(e->ev_sim, s));
-  CU_TRY(cudaStreamWaitEvent(e->side_stream, e->ev_sim, 0));
-  if (prof) cudaEventRecord(pe[3], e->side_stream);
-  cbev_launch_judge(e, out, 0, e->N, e->side_stream);
-  if (prof) cudaEventRecord(pe[4], e->side_stream);
-  if ((rc = debug_sync("k_judge", e->side_stream))) return rc;
+  // debug flag 2 (timing probe): k_judge on the caller's stream, i.e. serial between k_move and k_render
+  cudaStream_t js = (e->debug_flags & 2) ? s : e->side_stream;
+  if (js != s) {
+    CU_TRY(cudaEventRecord(e->ev_sim, s));
+    CU_TRY(cudaStreamWaitEvent(js, e->ev_sim, 0));
+  }
+  if (prof) cudaEventRecord(pe[3], js);
+  cbev_launch_judge(e, out, 0, e->N, js);
+  if (prof) cudaEventRecord(pe[4], js);
+  if ((rc = debug_sync("k_judge", js))) return rc;
   if (host) {  // reward / flags are final after k_judge: copy them out while the raster kernel runs
     const size_t N = (size_t)e->N;
     const cbev_host_out* ho = host;
@@ -721,20 +728,20 @@ int cbev_step_ex(cbev_handle e, const void* actions_dev, const cbev_step_out* ou
     const bool packed_host = ho->terminated == (uint8_t*)ho->reward + N * 8 && ho->truncated == ho->terminated + N;
     if (packed_dev && packed_host) {
       // both sides laid the three outputs out back to back: one D2H copy instead of three
-      CU_TRY(cudaMemcpyAsync(ho->reward, out->reward, N * 10, cudaMemcpyDeviceToHost, e->side_stream));
+      CU_TRY(cudaMemcpyAsync(ho->reward, out->reward, N * 10, cudaMemcpyDeviceToHost, js));
     } else {
-      CU_TRY(cudaMemcpyAsync(ho->reward, out->reward, N * 8, cudaMemcpyDeviceToHost, e->side_stream));
-      CU_TRY(cudaMemcpyAsync(ho->terminated, out->terminated, N, cudaMemcpyDeviceToHost, e->side_stream));
-      CU_TRY(cudaMemcpyAsync(ho->truncated, out->truncated, N, cudaMemcpyDeviceToHost, e->side_stream));
+      CU_TRY(cudaMemcpyAsync(ho->reward, out->reward, N * 8, cudaMemcpyDeviceToHost, js));
+      CU_TRY(cudaMemcpyAsync(ho->terminated, out->terminated, N, cudaMemcpyDeviceToHost, js));
+      CU_TRY(cudaMemcpyAsync(ho->truncated, out->truncated, N, cudaMemcpyDeviceToHost, js));
     }
-    if (ho->cause && out->cause) CU_TRY(cudaMemcpyAsync(ho->cause, out->cause, N, cudaMemcpyDeviceToHost, e->side_stream));
+    if (ho->cause && out->cause) CU_TRY(cudaMemcpyAsync(ho->cause, out->cause, N, cudaMemcpyDeviceToHost, js));
     if (ho->episode && out->episode)
       CU_TRY(cudaMemcpyAsync(ho->episode, out->episode, N * CBEV_EPISODE_FIELDS * sizeof(double), cudaMemcpyDeviceToHost,
-                             e->side_stream));
-    CU_TRY(cudaEventRecord(e->ev_copy, e->side_stream));
+                             js));
+    CU_TRY(cudaEventRecord(e->ev_copy, js));
     e->host_copy_pending = true;
   }
-  CU_TRY(cudaEventRecord(e->ev_judge, e->side_stream));
+  CU_TRY(cudaEventRecord(e->ev_judge, js));
   if (cbev_launch_render(e, head, mirror, 0, e->N, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
   if (prof) { cudaEventRecord(pe[2], s); e->prof_n += 1; }
   if ((rc = debug_sync("k_render", s))) return rc;

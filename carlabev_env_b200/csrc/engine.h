@@ -108,6 +108,9 @@ struct cbev_engine {
   int32_t debug_flags = 0;         // cbev_set_debug_flags
   int32_t* desc = nullptr;         // [N][CBEV_DESC_WORDS]
   uint32_t* rects = nullptr;       // [N][max_rects][CBEV_RECT_WORDS]
+  int32_t* order = nullptr;        // [N] raster CTA b renders env order[b]: envs that fill the whole frame window (reset
+                                   //     frames, F times the stores) first, so they do not form the tail of the launch
+  int32_t* order_cnt = nullptr;    // [2] heavy / light counters of the step (zeroed by the raster kernel)
   uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)
   unsigned long long* trace = nullptr;  // [N][8] phase timestamps (debug flag 4)
   int32_t rs_mode = 0, rs_words = 0;  // CBEV_RS_*: how ResizeObservation is computed for this obs_size

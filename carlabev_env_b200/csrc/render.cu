@@ -89,6 +89,8 @@ struct RenderParams {
   int32_t pad0, pad1;
   const int32_t* desc;
   const uint32_t* rects;
+  const int32_t* order;       // CTA -> env (heavy envs first), or null
+  int32_t* order_cnt;         // zeroed here for the next step's k_move
   int32_t max_rects;
   uint8_t* fov_out;  // [N][S][S] palette-index frames (nullable)
   const uint8_t* fov_mask;  // [S][S] 0x00 / 0xff or null (fov_masked)
@@ -197,9 +199,10 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   int* s_count = (int*)(s_lut + 16);
   uint32_t* s_rects = (uint32_t*)(s_count + 4);  // draw list (max_rects x 2 words); the resize tables follow (GEN)
 
-  const int env = P.env_lo + blockIdx.x;
+  const int env = P.order != nullptr ? P.order[P.env_lo + blockIdx.x] : P.env_lo + blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x == 0 && tid < 2 && P.order_cnt != nullptr) P.order_cnt[tid] = 0;
   const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
   const int flags = d[RD_FLAGS];
   if (flags & 2) return;  // masked-out env of a partial reset
@@ -722,6 +725,8 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.frame_bytes = e->frame_bytes;
   P.desc = e->desc;
   P.rects = e->rects;
+  P.order = (e->debug_flags & 32) ? nullptr : e->order;  // debug flag 32: identity CTA -> env mapping (timing probe)
+  P.order_cnt = e->order_cnt;
   P.max_rects = e->max_rects;
   P.fov_out = e->keep_fov ? e->fov : nullptr;
   P.fov_mask = e->fov_mask;
