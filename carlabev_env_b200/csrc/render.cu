@@ -64,6 +64,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float d) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 1.0f (0x3f800000) if bit `pos` of m is set, else 0.0f: sign-extending 1-bit field extract, then one AND
+__device__ __forceinline__ uint32_t bit_to_f32(uint32_t m, int pos) {
+  int32_t s;
+  asm("bfe.s32 %0, %1, %2, 1;" : "=r"(s) : "r"(m), "r"(pos));
+  return (uint32_t)s & 0x3f800000u;
+}
+__device__ __forceinline__ void st_b4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void st_u4(void* p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
@@ -416,16 +425,37 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     }
     __syncthreads();
     uint8_t* s_rgb = s_region;
+    // palette index -> R, G, B through byte LUTs held in registers (PRMT), four pixels at a time: entries 0..7 come
+    // from two registers per channel, entries 8 (black) and 9 (unlit traffic light, 100) are patched in by mask --
+    // no shared-memory look-ups (they were a fifth of this path's shared wavefronts, ncu round 2)
+    uint32_t tab[3][2];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      tab[ch][0] = tab[ch][1] = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tab[ch][e >> 2] |= ((s_key[e] >> (8 * ch)) & 255u) << (8 * (e & 3));
+    }
+    const uint32_t v9 = s_key[9] & 255u;  // TL_OFF is a grey: R = G = B
 #pragma unroll
     for (int i = 0; i < S * S / 4 / RT; ++i) {  // 4 pixels -> 12 bytes = 3 words
       const int u = tid + i * RT;
       const uint32_t p4 = f[i];
-      const uint32_t k0 = s_key[p4 & 255u], k1 = s_key[(p4 >> 8) & 255u], k2 = s_key[(p4 >> 16) & 255u],
-                     k3 = s_key[p4 >> 24];
+      // selector nibbles = index & 7 of the four pixels
+      const uint32_t lo7 = p4 & 0x07070707u;
+      const uint32_t sel = (lo7 | (lo7 >> 4)) & 0xffu | (((lo7 >> 8) | (lo7 >> 12)) & 0xff00u);
+      const uint32_t hi = (p4 >> 3) & 0x01010101u;           // 1 where index >= 8
+      const uint32_t himask = hi * 0xffu;
+      const uint32_t patch = ((p4 & hi) * v9) & himask;      // index 9 -> 100, index 8 -> 0
+      const uint32_t R = (__byte_perm(tab[0][0], tab[0][1], sel) & ~himask) | patch;
+      const uint32_t G = (__byte_perm(tab[1][0], tab[1][1], sel) & ~himask) | patch;
+      const uint32_t B = (__byte_perm(tab[2][0], tab[2][1], sel) & ~himask) | patch;
+      // interleave: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+      const uint32_t rg01 = __byte_perm(R, G, 0x5140);       // R0 G0 R1 G1
+      const uint32_t rg23 = __byte_perm(R, G, 0x7362);       // R2 G2 R3 G3
       uint32_t* o = (uint32_t*)s_rgb + 3 * u;
-      o[0] = k0 | (k1 << 24);
-      o[1] = (k1 >> 8) | (k2 << 16);
-      o[2] = (k2 >> 16) | (k3 << 8);
+      o[0] = __byte_perm(rg01, B, 0x2410);                   // R0 G0 B0 R1
+      o[1] = __byte_perm(__byte_perm(rg01, B, 0x0053), rg23, 0x5410);  // G1 B1 | R2 G2
+      o[2] = __byte_perm(rg23, B, 0x7326);                   // B2 R3 G3 B3
     }
     __syncthreads();
     uint8_t* dst = (uint8_t*)P.ring + (size_t)env * P.ring_slots * P.frame_bytes + (size_t)P.head * P.frame_bytes;
@@ -598,14 +628,27 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
       if (OBS_MODE == CBEV_OBS_SEMANTIC) {
         float* fb = (float*)base;
         const int plane = OH * OW;
-        for (int q = tid; q < plane / 4; q += RT) {
-          const uint32_t m4 = ((const uint32_t*)s_out)[q];
+        if (P.pad0 & 64) {  // round-1 expansion through the shared-memory float4 LUT (A/B probe)
+          for (int q = tid; q < plane / 4; q += RT) {
+            const uint32_t m4 = ((const uint32_t*)s_out)[q];
 #pragma unroll
-          for (int c = 0; c < CHANNELS; ++c) {
-            // bit c of each of the 4 pixels -> 4-bit index (multiply gathers the bits into the top byte)
-            const uint32_t t = (m4 >> c) & 0x01010101u;
-            const float4 v = s_lut[(t * 0x01020408u) >> 24];
-            st_f4(fb + c * plane + 4 * q, v.x, v.y, v.z, v.w);
+            for (int c = 0; c < CHANNELS; ++c) {
+              // bit c of each of the 4 pixels -> 4-bit index (multiply gathers the bits into the top byte)
+              const uint32_t t = (m4 >> c) & 0x01010101u;
+              const float4 v = s_lut[(t * 0x01020408u) >> 24];
+              st_f4(fb + c * plane + 4 * q, v.x, v.y, v.z, v.w);
+            }
+          }
+        } else {
+          // bit c of each of the 4 pixel bytes -> 0.0f / 1.0f in registers: no shared-memory traffic at all in the
+          // store loop (the LUT reads were 57 % of the kernel's shared-load wavefronts, ncu round 2; top stall
+          // mio_throttle)
+          for (int q = tid; q < plane / 4; q += RT) {
+            const uint32_t m4 = ((const uint32_t*)s_out)[q];
+#pragma unroll
+            for (int c = 0; c < CHANNELS; ++c)
+              st_b4(fb + c * plane + 4 * q, bit_to_f32(m4, c), bit_to_f32(m4, c + 8), bit_to_f32(m4, c + 16),
+                    bit_to_f32(m4, c + 24));
           }
         }
       } else {

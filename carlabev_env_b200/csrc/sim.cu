@@ -569,6 +569,59 @@ __device__ __forceinline__ void actor_chunk_step(const SimParams& P, const PoolD
     }
 }
 
+// Cold paths of k_move, kept out of line: the common case (table look-ups, no reset) then runs a compact
+// instruction stream (ncu round 2: "no instruction" was the second stall reason of the 7.6 k-instruction kernel).
+template <int G>
+__device__ __noinline__ void live_actor_chunk(const SimParams& P, const PoolDev& pool, const EnvState& S, size_t row, int ga,
+                                              size_t o, bool has, double t_sim, int lane, int gb, unsigned GM, Body& b,
+                                              int& kind) {
+  actor_chunk_step<G>(P, pool, S, row, ga, o, has, t_sim, lane, gb, GM, b, kind);
+}
+
+template <int G>
+__device__ __noinline__ void hand_over_to_live(const SimParams& P, const PoolDev& pool, const EnvState& st, int env, int scene,
+                                               int A, int lane, unsigned GM) {
+  for (int a = lane; a < A; a += G) {
+    const size_t o = (size_t)env * P.max_actors + a, r = (size_t)scene * P.max_actors + a;
+    st.ax[o] = pool.roll.ax[r]; st.ay[o] = pool.roll.ay[r]; st.ayaw[o] = pool.roll.ayaw[r]; st.av[o] = pool.roll.av[r];
+    st.atarget_mps[o] = pool.roll.atarget_mps[r]; st.aelapsed[o] = pool.roll.aelapsed[r];
+    st.astate_elapsed[o] = pool.roll.astate_elapsed[r]; st.atidx[o] = pool.roll.atidx[r];
+    st.arxlen[o] = pool.roll.arxlen[r]; st.aflags[o] = pool.roll.aflags[r];
+  }
+  for (int k = lane; k < P.max_retreat * 3 * CBEV_SG_MAX; k += G)
+    st.retreat[(size_t)env * P.max_retreat * 3 * CBEV_SG_MAX + k] = pool.roll.retreat[(size_t)scene * P.max_retreat * 3 * CBEV_SG_MAX + k];
+  for (int k = lane; k < P.max_retreat; k += G)
+    st.retreat_n[(size_t)env * P.max_retreat + k] = pool.roll.retreat_n[(size_t)scene * P.max_retreat + k];
+  __syncwarp(GM);
+}
+
+template <int G>
+__device__ __noinline__ void auto_reset_env(const SimParams& P, const PoolDev& pool, const EnvState& st, const cbev_step_out& out,
+                                            int32_t* d, int32_t* order, int32_t* order_cnt, int env, int lane, unsigned GM) {
+  int ep = st.episode[env];
+  uint64_t h = splitmix64(P.seed + (uint64_t)env * 0x9E3779B97F4A7C15ull + (uint64_t)ep * 0xD1B54A32D192ED03ull);
+  int scene = (int)(h % (uint64_t)pool.n_scenes);
+  __syncwarp(GM);
+  reset_env(P, pool, st, env, scene, lane, G);
+  if (lane == 0) {
+    order[atomicAdd(order_cnt, 1)] = env;  // heavy: the reset frame goes to all F window slots -> rendered first
+    const double* s0 = pool.ego_state0 + (size_t)scene * 4;
+    View v;
+    compute_view(P, s0[0], s0[1], 0.0, v);
+    write_desc_header(P, d, v, 0, 1, crop_corner_class(P, v));  // bit0: reset frame; k_judge skips this env
+    out.reward[env] = 0.0;
+    out.terminated[env] = 0;
+    out.truncated[env] = 0;
+    if (out.cause) out.cause[env] = CBEV_CAUSE_NONE;
+    if (out.hero) {
+      double* hb = out.hero + (size_t)env * CBEV_HERO_FIELDS;
+      for (int k = 0; k < CBEV_HERO_FIELDS; ++k) hb[k] = 0.0;
+      hb[CBEV_H_X] = s0[0]; hb[CBEV_H_Y] = s0[1]; hb[CBEV_H_YAW] = s0[2]; hb[CBEV_H_V] = s0[3];
+      hb[CBEV_H_SCENE] = (double)scene;
+    }
+  }
+}
+
 // ---- the step kernels ---------------------------------------------------------------------------
 // The step is split where the reference's data flow allows it (envs/carlabev.py:223-231, scenes/scene.py:90-140):
 //   k_move  -- everything that MOVES: action decode, ego bicycle physics, scripted actors (trajectory tables or live
@@ -612,28 +665,7 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
 
   // ---- device auto-reset (gymnasium NEXT_STEP semantics) from the pool -------------------------
   if (P.autoreset == CBEV_AUTORESET_NEXT_STEP && st.done[env]) {
-    int ep = st.episode[env];
-    uint64_t h = splitmix64(P.seed + (uint64_t)env * 0x9E3779B97F4A7C15ull + (uint64_t)ep * 0xD1B54A32D192ED03ull);
-    int scene = (int)(h % (uint64_t)pool.n_scenes);
-    __syncwarp(GM);
-    reset_env(P, pool, st, env, scene, lane, G);
-    if (lane == 0) {
-      order[atomicAdd(order_cnt, 1)] = env;  // heavy: the reset frame goes to all F window slots -> rendered first
-      const double* s0 = pool.ego_state0 + (size_t)scene * 4;
-      View v;
-      compute_view(P, s0[0], s0[1], 0.0, v);
-      write_desc_header(P, d, v, 0, 1, crop_corner_class(P, v));  // bit0: reset frame; k_judge skips this env
-      out.reward[env] = 0.0;
-      out.terminated[env] = 0;
-      out.truncated[env] = 0;
-      if (out.cause) out.cause[env] = CBEV_CAUSE_NONE;
-      if (out.hero) {
-        double* hb = out.hero + (size_t)env * CBEV_HERO_FIELDS;
-        for (int k = 0; k < CBEV_HERO_FIELDS; ++k) hb[k] = 0.0;
-        hb[CBEV_H_X] = s0[0]; hb[CBEV_H_Y] = s0[1]; hb[CBEV_H_YAW] = s0[2]; hb[CBEV_H_V] = s0[3];
-        hb[CBEV_H_SCENE] = (double)scene;
-      }
-    }
+    auto_reset_env<G>(P, pool, st, out, d, order, order_cnt, env, lane, GM);
     return;
   }
 
@@ -707,20 +739,7 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
   // The first traj_steps steps of every scene were rolled out at pool upload by the same device code
   // (k_rollout); afterwards the env continues live from the roll-out's final state.
   int nrects = 0;
-  if (!use_table && pool.traj_steps > 0 && step_idx == pool.traj_steps) {
-    for (int a = lane; a < A; a += G) {
-      const size_t o = (size_t)env * P.max_actors + a, r = (size_t)scene * P.max_actors + a;
-      st.ax[o] = pool.roll.ax[r]; st.ay[o] = pool.roll.ay[r]; st.ayaw[o] = pool.roll.ayaw[r]; st.av[o] = pool.roll.av[r];
-      st.atarget_mps[o] = pool.roll.atarget_mps[r]; st.aelapsed[o] = pool.roll.aelapsed[r];
-      st.astate_elapsed[o] = pool.roll.astate_elapsed[r]; st.atidx[o] = pool.roll.atidx[r];
-      st.arxlen[o] = pool.roll.arxlen[r]; st.aflags[o] = pool.roll.aflags[r];
-    }
-    for (int k = lane; k < P.max_retreat * 3 * CBEV_SG_MAX; k += G)
-      st.retreat[(size_t)env * P.max_retreat * 3 * CBEV_SG_MAX + k] = pool.roll.retreat[(size_t)scene * P.max_retreat * 3 * CBEV_SG_MAX + k];
-    for (int k = lane; k < P.max_retreat; k += G)
-      st.retreat_n[(size_t)env * P.max_retreat + k] = pool.roll.retreat_n[(size_t)scene * P.max_retreat + k];
-    __syncwarp(GM);
-  }
+  if (!use_table && pool.traj_steps > 0 && step_idx == pool.traj_steps) hand_over_to_live<G>(P, pool, st, env, scene, A, lane, GM);
   for (int base = 0; base < A; base += G) {
     const int a = base + lane;
     const bool has = a < A;
@@ -736,7 +755,7 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
         st.ax[o] = b.x; st.ay[o] = b.y; st.ayaw[o] = b.yaw; st.av[o] = b.v;  // read back by k_judge / cbev_get_state
       }
     } else {
-      actor_chunk_step<G>(P, pool, st, (size_t)env, ga, o, has, t_sim, lane, gb, GM, b, kind);
+      live_actor_chunk<G>(P, pool, st, (size_t)env, ga, o, has, t_sim, lane, gb, GM, b, kind);
     }
     // ---- a6: draw list (vehicles then pedestrians; pool stores them in that order) ----
     const int size = kind == 0 ? 4 : 2;  // vehicle.py:24, pedestrian.py:24
