@@ -569,17 +569,19 @@ __device__ __forceinline__ void actor_chunk_step(const SimParams& P, const PoolD
     }
 }
 
-// Cold paths of k_move, kept out of line: the common case (table look-ups, no reset) then runs a compact
-// instruction stream (ncu round 2: "no instruction" was the second stall reason of the 7.6 k-instruction kernel).
+// Cold paths of k_move.  Keeping them OUT of line (to shrink the hot instruction stream: ncu round 2 shows "no
+// instruction" as the second stall reason of the 7.6 k-instruction kernel) was measured on B200 and is much slower --
+// k_move 17 -> 29 us at 4096 envs: the call ABI forces the live values of the caller through local memory -- so they
+// are inlined.
 template <int G>
-__device__ __noinline__ void live_actor_chunk(const SimParams& P, const PoolDev& pool, const EnvState& S, size_t row, int ga,
+__device__ __forceinline__ void live_actor_chunk(const SimParams& P, const PoolDev& pool, const EnvState& S, size_t row, int ga,
                                               size_t o, bool has, double t_sim, int lane, int gb, unsigned GM, Body& b,
                                               int& kind) {
   actor_chunk_step<G>(P, pool, S, row, ga, o, has, t_sim, lane, gb, GM, b, kind);
 }
 
 template <int G>
-__device__ __noinline__ void hand_over_to_live(const SimParams& P, const PoolDev& pool, const EnvState& st, int env, int scene,
+__device__ __forceinline__ void hand_over_to_live(const SimParams& P, const PoolDev& pool, const EnvState& st, int env, int scene,
                                                int A, int lane, unsigned GM) {
   for (int a = lane; a < A; a += G) {
     const size_t o = (size_t)env * P.max_actors + a, r = (size_t)scene * P.max_actors + a;
@@ -596,7 +598,7 @@ __device__ __noinline__ void hand_over_to_live(const SimParams& P, const PoolDev
 }
 
 template <int G>
-__device__ __noinline__ void auto_reset_env(const SimParams& P, const PoolDev& pool, const EnvState& st, const cbev_step_out& out,
+__device__ __forceinline__ void auto_reset_env(const SimParams& P, const PoolDev& pool, const EnvState& st, const cbev_step_out& out,
                                             int32_t* d, int32_t* order, int32_t* order_cnt, int env, int lane, unsigned GM) {
   int ep = st.episode[env];
   uint64_t h = splitmix64(P.seed + (uint64_t)env * 0x9E3779B97F4A7C15ull + (uint64_t)ep * 0xD1B54A32D192ED03ull);
@@ -663,27 +665,20 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
   int32_t* d = desc + (size_t)env * CBEV_DESC_WORDS;
   uint32_t* rl = rects + (size_t)env * P.max_rects * CBEV_RECT_WORDS;
 
-  // ---- device auto-reset (gymnasium NEXT_STEP semantics) from the pool -------------------------
-  if (P.autoreset == CBEV_AUTORESET_NEXT_STEP && st.done[env]) {
-    auto_reset_env<G>(P, pool, st, out, d, order, order_cnt, env, lane, GM);
-    return;
-  }
-
+  // First level of loads, all independent of each other and issued together (the kernel is a chain of dependent
+  // global loads, ~0.7 us each under load: done -> scene -> offsets -> table): the done flag, the scene index, the
+  // ego state and the action.  An env that auto-resets simply does not use them.
+  const uint8_t was_done = st.done[env];
   const int scene = st.scene[env];
   double* eg = st.ego + (size_t)env * E_SLOTS;
   const int32_t* ei = st.egoi + (size_t)env * I_SLOTS;
-  // everything that depends only on the scene index / env state is fetched up front, so that these dependent loads
-  // are in flight together while the physics below runs (each costs ~0.7 us under the raster kernel's store traffic)
-  const int r0 = pool.ego_off[scene], nt = pool.ego_off[scene + 1] - r0;
-  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
-  const int tl0 = pool.tl_off[scene], ntl = pool.tl_off[scene + 1] - tl0;
+  Body e;
+  e.x = eg[E_X]; e.y = eg[E_Y]; e.yaw = eg[E_YAW]; e.v = eg[E_V];
+  double acc = eg[E_ACC];
+  const double etarget = eg[E_TARGET];
+  const double t_sim = eg[E_T] + DT;  // scene.py:91 (k_judge stores it)
   const int step_idx = ei[I_STEP];
-  const bool use_table = step_idx < pool.traj_steps;
-  const long long toff = pool.traj_steps > 0 ? pool.traj_off[scene] : 0;
   const unsigned long long tv0 = st.tgt_vis[(size_t)env * CBEV_TGT_WORDS], tv1 = st.tgt_vis[(size_t)env * CBEV_TGT_WORDS + 1];
-  const double* __restrict__ ecx = pool.ego_cx + r0;
-  const double* __restrict__ ecy = pool.ego_cy + r0;
-
   // ---- a1: decode action (spaces.py:43-47, hero.py:165-187) ----------------------------------------
   float gas, steer, brake;
   if (P.action_mode == CBEV_ACTION_DISCRETE) {
@@ -699,12 +694,22 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
     brake = fminf(fmaxf(a[2], 0.0f), 1.0f);
   }
 
+  // ---- device auto-reset (gymnasium NEXT_STEP semantics) from the pool -------------------------
+  if (P.autoreset == CBEV_AUTORESET_NEXT_STEP && was_done) {
+    auto_reset_env<G>(P, pool, st, out, d, order, order_cnt, env, lane, GM);
+    return;
+  }
+
+  // second level: everything that depends only on the scene index
+  const int r0 = pool.ego_off[scene], nt = pool.ego_off[scene + 1] - r0;
+  const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
+  const int tl0 = pool.tl_off[scene], ntl = pool.tl_off[scene + 1] - tl0;
+  const bool use_table = step_idx < pool.traj_steps;
+  const long long toff = pool.traj_steps > 0 ? pool.traj_off[scene] : 0;
+  const double* __restrict__ ecx = pool.ego_cx + r0;
+  const double* __restrict__ ecy = pool.ego_cy + r0;
+
   // ---- a2/a3: ego physics (uniform across lanes) ------------------------------------------------
-  Body e;
-  e.x = eg[E_X]; e.y = eg[E_Y]; e.yaw = eg[E_YAW]; e.v = eg[E_V];
-  double acc = eg[E_ACC];
-  const double etarget = eg[E_TARGET];
-  const double t_sim = eg[E_T] + DT;  // scene.py:91 (k_judge stores it)
   double acc_val = gas > 0.0f ? (double)__fmul_rn(gas, 8.0f) : 0.0;
   double delta;
   if (fabs(e.v) < 0.1) {
@@ -740,6 +745,14 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
   // (k_rollout); afterwards the env continues live from the roll-out's final state.
   int nrects = 0;
   if (!use_table && pool.traj_steps > 0 && step_idx == pool.traj_steps) hand_over_to_live<G>(P, pool, st, env, scene, A, lane, GM);
+  // table look-ups are software-pipelined: the pose and kind of the next chunk of G actors are fetched while the
+  // current chunk is clipped and packed (50-vehicle scenes take 7 chunks at G = 8)
+  double4 qn = make_double4(0.0, 0.0, 0.0, 0.0);
+  int kn = 0;
+  if (use_table && lane < A) {
+    qn = pool.traj[toff + (size_t)step_idx * A + lane];
+    kn = pool.act_kind[A0 + lane];
+  }
   for (int base = 0; base < A; base += G) {
     const int a = base + lane;
     const bool has = a < A;
@@ -748,10 +761,14 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
     Body b;
     int kind = 0;
     if (use_table) {
+      const double4 q = qn;
+      kind = kn;
+      if (a + G < A) {
+        qn = pool.traj[toff + (size_t)step_idx * A + a + G];
+        kn = pool.act_kind[ga + G];
+      }
       if (has) {  // open-loop actors: pose after this step was rolled out once per scene at pool upload
-        const double4 q = pool.traj[toff + (size_t)step_idx * A + a];
         b.x = q.x; b.y = q.y; b.yaw = q.z; b.v = q.w;
-        kind = pool.act_kind[ga];
         st.ax[o] = b.x; st.ay[o] = b.y; st.ayaw[o] = b.yaw; st.av[o] = b.v;  // read back by k_judge / cbev_get_state
       }
     } else {
