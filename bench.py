@@ -153,7 +153,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -417,7 +417,6 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
     prof_ms = _timed_block(ctx, lambda i: eng.step(acts_dev[i % bank]), K)
     move_ms, render_ms, judge_ms, prof_steps = eng.profile_read()
     eng.profile(False)
-    clock_info = clocks.stop() if clocks else None
     n_prof = max(prof_steps, 1)
     move_avg, render_avg, judge_avg = move_ms / n_prof, render_ms / n_prof, judge_ms / n_prof
 
@@ -456,6 +455,7 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
     venv_pipe_ms = statistics.median([_timed_block(ctx, venv_step_pipelined, K) for _ in range(3)])
     venv_pipe_value = world * N * K / (venv_pipe_ms * 1e-3)
 
+    clock_info = clocks.stop() if clocks else None   # sampled under load over every timed leg of this workload
     # ---- episode statistics: the only collective (all-reduce of a 21-double vector over NCCL) ----
     stats = summarize_stats(allreduce_stats(eng.read_stats().clone()))
     res = None

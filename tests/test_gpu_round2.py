@@ -245,3 +245,52 @@ def test_two_engines_on_two_devices():
         outs.append((eng.obs().cpu().numpy().copy(), eng.reward.cpu().numpy().copy()))
         eng.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_vector_env_step_paths_agree():
+    """VectorEnv.step with host NumPy actions (cbev_step_host_ex), with a CUDA tensor (cbev_step_ex) and with
+    host_infos=False (cbev_step) gives the same observations / rewards / flags; to_numpy returns host copies of the
+    pinned mirrors; the terminal infos come from the pinned episode block."""
+    import torch
+
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+    from carlabev_env_b200.scenes import build_scripted_scene
+
+    cls = load_map()
+    scenes = [build_scripted_scene("lead_brake", 50 + i, level=1 + i % 3, cls_map=cls) for i in range(12)]
+    cfg = RunConfig(env=EnvConfig(action_mode="continuous"), num_envs=12)
+    kinds = [dict(), dict(), dict(host_infos=False), dict(to_numpy=True)]
+    envs = [make_env(cfg, scenes=scenes, autoreset="next_step", ring_budget_bytes=64 << 20, seed=3, **kw) for kw in kinds]
+    for e in envs:
+        e.reset(options={"scene_ids": np.arange(12)})
+    rng = np.random.default_rng(9)
+    finished = 0
+    for t in range(60):
+        a = np.stack([rng.uniform(0.3, 1, 12), rng.uniform(-1, 1, 12), rng.uniform(0, 0.3, 12)], axis=1).astype(np.float32)
+        outs = [envs[0].step(a), envs[1].step(torch.from_numpy(a).cuda()), envs[2].step(torch.from_numpy(a).cuda()),
+                envs[3].step(a)]
+        torch.cuda.synchronize()
+        obs0, rew0, term0, trunc0, info0 = outs[0]
+        for k in (1, 2):
+            o, r, te, tr, _ = outs[k]
+            assert torch.equal(o, obs0) and torch.equal(r, rew0) and torch.equal(te, term0) and torch.equal(tr, trunc0), (t, k)
+        o, r, te, tr, info3 = outs[3]
+        assert isinstance(o, np.ndarray) and r.dtype == np.float64 and te.dtype == np.bool_
+        assert np.array_equal(o, obs0.cpu().numpy()) and np.array_equal(r, rew0.cpu().numpy())
+        assert np.array_equal(te, term0.cpu().numpy())
+        assert "episode_block" in outs[2][4] and "episode_info" not in outs[2][4]
+        if bool(term0.any()):
+            done = term0.cpu().numpy()
+            finished += int(done.sum())
+            for info in (info0, outs[1][4], info3):
+                assert np.array_equal(info["_episode"], done)
+                i = int(np.flatnonzero(done)[0])
+                assert info["episode"]["l"][i] >= 1 and info["episode_info"]["termination"][i] in ("collision", "success", "out_of_bounds")
+                assert abs(info["episode"]["r"][i] - info["episode_info"]["return"][i]) < 1e-12
+            blk = outs[2][4]["episode_block"].cpu().numpy()
+            assert np.allclose(blk[done, 0], info0["episode_info"]["return"][done])
+        else:
+            assert "episode" not in info0
+    assert finished > 0
+    for e in envs:
+        e.close()
