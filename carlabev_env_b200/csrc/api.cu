@@ -352,6 +352,8 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   rc |= dev_alloc(&e->desc, N * CBEV_DESC_WORDS);
   rc |= dev_alloc(&e->order, N);
   rc |= dev_alloc(&e->order_cnt, (size_t)2);
+  rc |= dev_alloc(&e->move_order, N);
+  rc |= dev_alloc(&e->move_cnt, (size_t)2);
   rc |= dev_alloc(&e->fov, N * (size_t)cfg->fov_size * cfg->fov_size);
   rc |= dev_alloc(&e->gstats, (size_t)CBEV_STATS_FIELDS);
   rc |= build_resize_tables(e);
@@ -371,7 +373,7 @@ int cbev_destroy(cbev_handle e) {
   free_pool(e->pool);
   free_state(e->st);
   dev_free(e->fov_mask); dev_free(e->rs_tab); dev_free(e->trace);
-  dev_free(e->order); dev_free(e->order_cnt);
+  dev_free(e->order); dev_free(e->order_cnt); dev_free(e->move_order); dev_free(e->move_cnt);
   dev_free(e->map); dev_free(e->desc); dev_free(e->rects); dev_free(e->fov); dev_free(e->gstats);
   dev_free(e->h_reward_dev);
   { uint8_t* p = (uint8_t*)e->h_actions_dev; dev_free(p); }

@@ -111,6 +111,10 @@ struct cbev_engine {
   int32_t* order = nullptr;        // [N] raster CTA b renders env order[b]: envs that fill the whole frame window (reset
                                    //     frames, F times the stores) first, so they do not form the tail of the launch
   int32_t* order_cnt = nullptr;    // [2] heavy / light counters of the step (zeroed by the raster kernel)
+  int32_t* move_order = nullptr;   // [N] group g of k_move steps env move_order[g]: k_judge puts the envs that will
+                                   //     auto-reset next step first, so that the (long) reset path and the normal path
+                                   //     do not serialise inside the same warps
+  int32_t* move_cnt = nullptr;     // [2] counters behind move_order (zeroed by k_move)
   uint8_t* fov = nullptr;          // [N][S][S] last palette-index frame (debug / RGB path)
   unsigned long long* trace = nullptr;  // [N][8] phase timestamps (debug flag 4)
   int32_t rs_mode = 0, rs_words = 0;  // CBEV_RS_*: how ResizeObservation is computed for this obs_size

@@ -320,11 +320,12 @@ __device__ void reset_env(const SimParams& P, const PoolDev& pool, const EnvStat
 
 __global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK)
 k_reset(SimParams P, PoolDev pool, EnvState st, const uint8_t* __restrict__ mask,
-        const int32_t* __restrict__ scene_ids, int32_t* __restrict__ desc, int32_t* __restrict__ order) {
+        const int32_t* __restrict__ scene_ids, int32_t* __restrict__ desc, int32_t* __restrict__ order,
+        int32_t* __restrict__ move_order) {
   const int env = blockIdx.x * CBEV_WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (env >= P.N) return;
-  if (lane == 0) order[env] = env;
+  if (lane == 0) { order[env] = env; move_order[env] = env; }
   if (mask != nullptr && mask[env] == 0) {
     if (lane == 0) desc[(size_t)env * CBEV_DESC_WORDS + RD_FLAGS] = 2;  // bit1: skip rendering this env
     return;
@@ -641,7 +642,7 @@ struct Group {
   int warp, lane, gb, grp;
   unsigned GM;
   int env;
-  __device__ __forceinline__ Group(const SimParams& P) {
+  __device__ __forceinline__ Group(const SimParams& P, const int32_t* __restrict__ perm = nullptr) {
     constexpr int EPW = 32 / G;
     warp = threadIdx.x >> 5;
     const int wl = threadIdx.x & 31;
@@ -650,6 +651,7 @@ struct Group {
     grp = wl / G;
     GM = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gb);
     env = P.env_lo + (blockIdx.x * CBEV_WARPS_PER_BLOCK + warp) * EPW + grp;
+    if (perm != nullptr && env < P.env_hi) env = perm[env];
   }
 };
 
@@ -657,10 +659,11 @@ template <int G>
 __global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, G == 32 ? CBEV_SIM_BLOCKS_PER_SM : 4)
 k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions, cbev_step_out out,
        int32_t* __restrict__ desc, uint32_t* __restrict__ rects, int32_t* __restrict__ order,
-       int32_t* __restrict__ order_cnt) {
-  const Group<G> g(P);
+       int32_t* __restrict__ order_cnt, const int32_t* __restrict__ move_order, int32_t* __restrict__ move_cnt) {
+  const Group<G> g(P, move_order);
   const int lane = g.lane, gb = g.gb, env = g.env;
   const unsigned GM = g.GM;
+  if (blockIdx.x == 0 && threadIdx.x < 2 && move_cnt != nullptr) move_cnt[threadIdx.x] = 0;  // k_judge counts afresh
   if (env >= P.env_hi) return;
   int32_t* d = desc + (size_t)env * CBEV_DESC_WORDS;
   uint32_t* rl = rects + (size_t)env * P.max_rects * CBEV_RECT_WORDS;
@@ -848,14 +851,17 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
 template <int G>
 __global__ void __launch_bounds__(32 * CBEV_WARPS_PER_BLOCK, G == 32 ? CBEV_SIM_BLOCKS_PER_SM : 4)
 k_judge(SimParams P, PoolDev pool, EnvState st, cbev_step_out out, const int32_t* __restrict__ desc,
-        double* __restrict__ gstats) {
+        double* __restrict__ gstats, int32_t* __restrict__ move_order, int32_t* __restrict__ move_cnt) {
   constexpr int EPW = 32 / G;  // environments per warp
   __shared__ double s_hero[CBEV_WARPS_PER_BLOCK][EPW][CBEV_HERO_FIELDS];
   const Group<G> g(P);
   const int warp = g.warp, lane = g.lane, gb = g.gb, grp = g.grp, env = g.env;
   const unsigned GM = g.GM;
   if (env >= P.env_hi) return;
-  if (desc[(size_t)env * CBEV_DESC_WORDS + RD_FLAGS] & 1) return;  // auto-reset this step: k_move wrote the outputs
+  if (desc[(size_t)env * CBEV_DESC_WORDS + RD_FLAGS] & 1) {  // auto-reset this step: k_move wrote the outputs
+    if (lane == 0) move_order[P.N - 1 - atomicAdd(move_cnt + 1, 1)] = env;
+    return;
+  }
 
   const int scene = st.scene[env];
   const int r0 = pool.ego_off[scene], nt = pool.ego_off[scene + 1] - r0;
@@ -1173,8 +1179,10 @@ k_judge(SimParams P, PoolDev pool, EnvState st, cbev_step_out out, const int32_t
       atomicAdd(gstats + CBEV_S_HARSH_RATE, ep_harsh * inv);
       st.episode[env] += 1;
       st.done[env] = 1;
+      move_order[atomicAdd(move_cnt, 1)] = env;  // resets next step: grouped at the front of k_move's env order
       for (int k = 0; k < S_SLOTS; ++k) sa[k] = 0.0;  // stats.reset() after terminated(), stats.py:107-112
     } else {
+      move_order[P.N - 1 - atomicAdd(move_cnt + 1, 1)] = env;
       sa[S_RET] = ep_ret; sa[S_LEN] = ep_len; sa[S_SPEED] = ep_speed;
       for (int k = 0; k < 6; ++k) sa[S_C0 + k] += cm6[k];
       sa[S_VIOL] = ep_viol; sa[S_HARSH] = ep_harsh; sa[S_CAUSE] = ep_cause;
@@ -1258,7 +1266,7 @@ static SimParams make_params(cbev_engine* e) {
 void cbev_launch_reset(cbev_engine* e, const uint8_t* mask, const int32_t* scene_ids, cudaStream_t s) {
   SimParams P = make_params(e);
   int blocks = (e->N + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
-  k_reset<<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, mask, scene_ids, e->desc, e->order);
+  k_reset<<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, mask, scene_ids, e->desc, e->order, e->move_order);
   e->launches += 1;
 }
 
@@ -1270,16 +1278,18 @@ void cbev_launch_move(cbev_engine* e, const void* actions, const cbev_step_out* 
   SimParams P = make_params(e);
   P.env_lo = lo;
   P.env_hi = hi;
+  // debug flag 128: identity group -> env mapping in k_move (timing probe)
+  const int32_t* mo = (e->debug_flags & 128) || lo != 0 || hi != e->N ? nullptr : e->move_order;
   if (narrow_groups(e)) {
     constexpr int G = 8;
     int per_block = CBEV_WARPS_PER_BLOCK * (32 / G);
     int blocks = (hi - lo + per_block - 1) / per_block;
     k_move<G><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->order,
-                                                           e->order_cnt);
+                                                           e->order_cnt, mo, e->move_cnt);
   } else {
     int blocks = (hi - lo + CBEV_WARPS_PER_BLOCK - 1) / CBEV_WARPS_PER_BLOCK;
     k_move<32><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, actions, *out, e->desc, e->rects, e->order,
-                                                            e->order_cnt);
+                                                            e->order_cnt, mo, e->move_cnt);
   }
   e->launches += 1;
 }
@@ -1292,7 +1302,8 @@ void cbev_launch_judge(cbev_engine* e, const cbev_step_out* out, int lo, int hi,
   constexpr int G = 8;
   int per_block = CBEV_WARPS_PER_BLOCK * (32 / G);
   int blocks = (hi - lo + per_block - 1) / per_block;
-  k_judge<G><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, *out, e->desc, e->gstats);
+  k_judge<G><<<blocks, 32 * CBEV_WARPS_PER_BLOCK, 0, s>>>(P, e->pool, e->st, *out, e->desc, e->gstats, e->move_order,
+                                                          e->move_cnt);
   e->launches += 1;
 }
 
