@@ -377,6 +377,12 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
         eng.set_debug_flags(args.debug_flags)
     frame_bytes = eng.frame_bytes
     ids = ((torch.arange(N, dtype=torch.int64) + rank * N) % len(scenes)).numpy()
+    pool_note = "host generator (carlabev_env_b200/scenes.py), bit-identical to the reference's post-reset state"
+    if args.device_pool and name == "c2":
+        k = len(scenes)
+        att = eng.generate_scripted_pool(["lead_brake"] * k, [1 + i % 3 for i in range(k)], list(range(k)))
+        pool_note = (f"generated on the device (cbev_generate_scenes; {int((att > 1).sum())} of {k} scenes needed a retry): "
+                     "draws bit-identical to the reference, smoothed routes within 1e-9 px")
     envs.reset(options={"scene_ids": ids})
     gen = torch.Generator(device="cpu").manual_seed(0 + rank)
     bank = 16
@@ -486,7 +492,7 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
                                 "counted in `value` like any other step",
             "value_excluding_reset_steps": world * (N * K - resets_in_blocks) / (ms_med * 1e-3),
             "config": {"workload": W["desc"].format(N=N, K=len(scenes)), "envs_per_gpu": N, "envs_total": world * N,
-                       "ring_slots": eng.L, "mean_actors_per_scene": a_mean,
+                       "ring_slots": eng.L, "mean_actors_per_scene": a_mean, "pool": pool_note,
                        "l2": f"each step writes {alg_bytes / 1e6:.0f} MB of observations per GPU (> 126 MB L2), "
                              "no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -564,7 +570,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config; c2 is the bench line")
@@ -577,6 +583,8 @@ def main():
     ap.add_argument("--extras-budget", type=float, default=240.0,
                     help="seconds after which no further extra workload is started")
     ap.add_argument("--brake", action="store_true", help="diagnostic: constant full-brake actions (no resets)")
+    ap.add_argument("--device-pool", action="store_true",
+                    help="c2 only: generate the lead_brake pool ON THE DEVICE (cbev_generate_scenes) instead of on the host")
     ap.add_argument("--debug-flags", type=int, default=0,
                     help="diagnostic (cbev_set_debug_flags): 2 = k_judge serial on the main stream, 32 = identity CTA order")
     args = ap.parse_args()
