@@ -330,13 +330,19 @@ class CarlaBEVVectorEnv(_vector_env_base()):
                 eng.step_host_full(a)
             else:
                 eng.step(a)
+        elif not self.host_infos:
+            # fully asynchronous mode: the host never waits for the device, so a pinned staging buffer could be
+            # overwritten while an earlier step's copy is still queued -- take a stream-ordered copy of the actions
+            a = t.as_tensor(np.asarray(actions), dtype=t.int64 if discrete else t.float32).to(self.device)
+            eng.step(a.view(self.num_envs) if discrete else a.view(self.num_envs, 3))
         else:
             if self._act_pin is None:
                 self._act_pin = (t.zeros(self.num_envs, dtype=t.int64) if discrete
                                  else t.zeros(self.num_envs, 3, dtype=t.float32)).pin_memory()
                 self._act_np = self._act_pin.numpy()
+            # safe to overwrite: the previous step waited for its host outputs, which follow its H2D copy
             self._act_np[...] = np.asarray(actions).reshape(self._act_np.shape)
-            eng.step_host_full(self._act_pin, episode=self.host_infos)
+            eng.step_host_full(self._act_pin, episode=True)
         obs = eng.obs() if self.fusion == "stack" else eng.fuse(self.fusion)
         rew, term, trunc = eng.reward, eng.terminated.view(t.bool), eng.truncated.view(t.bool)
         self.current_hero = eng.hero
