@@ -2,14 +2,14 @@
 Prints phase durations and how many CTAs are in their store phase over time."""
 import sys, torch, numpy as np
 sys.path.insert(0, ".")
-import bench
 from carlabev_env_b200 import engine as E
 from carlabev_env_b200.pool import pack_pool
 from carlabev_env_b200.vector_env import load_town01_map
 if __name__ == "__main__":
     N = 4096
     brake = len(sys.argv) > 1 and sys.argv[1] == "brake"
-    scenes = bench.build_pool(1024)
+    from carlabev_env_b200.scenes import build_pool
+    scenes = build_pool([dict(scene="lead_brake", level=1 + i % 3, scene_seed=i) for i in range(1024)])
     eng = E.Engine(N, action_mode=E.ACTION_CONTINUOUS, max_actors=4, autoreset=E.AUTORESET_NEXT_STEP, ring_slots=64)
     eng.upload_map(load_town01_map()); eng.upload_pool(pack_pool(scenes))
     eng.reset(torch.arange(N, dtype=torch.int32) % len(scenes))
