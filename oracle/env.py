@@ -98,7 +98,7 @@ class OracleEnv:
 
     # -- gym surface ------------------------------------------------------------
     def reset(self, scene):
-        self.sim = SceneSim(scene, self.cls_map, self.geom.pad, self.reward_mode, self.reward_params)
+        self.sim = SceneSim(scene, self.cls_map, self.geom.pad, self.reward_mode, self.reward_params, size=self.geom.size)
         self.ep_return = 0.0
         self.ep_len = 0
         frame = self._wrap_frame(self.render_index(reset_frame=True))

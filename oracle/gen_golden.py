@@ -41,11 +41,11 @@ FSM_IDS = {"idle": 0, "waiting": 1, "entering": 2, "yielding": 3, "crossing": 4,
            "cleared": 7, "retreated": 8}
 
 
-def dump_map():
+def dump_map(size=128):
     from PIL import Image
 
-    sem = np.array(Image.open(os.path.join(REFERENCE_ROOT, "CarlaBEV/assets/Town01/Town01-128-sem.png")))
-    rgb = np.array(Image.open(os.path.join(REFERENCE_ROOT, "CarlaBEV/assets/Town01/Town01-128-rgb.png")).convert("RGB"))
+    sem = np.array(Image.open(os.path.join(REFERENCE_ROOT, f"CarlaBEV/assets/Town01/Town01-{size}-sem.png")))
+    rgb = np.array(Image.open(os.path.join(REFERENCE_ROOT, f"CarlaBEV/assets/Town01/Town01-{size}-rgb.png")).convert("RGB"))
     cls = np.zeros(sem.shape, dtype=np.uint8)
     cls[sem == 127] = 1   # DRIVABLE   (semantics.py:34-38)
     cls[sem == 255] = 2   # SIDEWALK
@@ -53,8 +53,8 @@ def dump_map():
     assert np.array_equal(raster.PALETTE[cls], rgb), "rgb map is not LUT(sem)"
     out = os.path.join(ROOT, "carlabev_env_b200", "assets")
     os.makedirs(out, exist_ok=True)
-    np.savez_compressed(os.path.join(out, "town01_128_cls.npz"), cls=cls)
-    print("map", cls.shape, np.bincount(cls.ravel()))
+    np.savez_compressed(os.path.join(out, f"town01_{size}_cls.npz"), cls=cls)
+    print("map", size, cls.shape, np.bincount(cls.ravel()))
 
 
 def behaviour_of(actor):
@@ -382,10 +382,54 @@ def fusion_weighted():
                   semantic_mask_ch="5-class"), opts, acts, frame_every=3, obs_every=10)
 
 
+# ---- other map scales.  The unmodified reference resets and steps `rdm` scenes at size 64 and 256 for
+# the seeds below (its generators hard-code map_size=128, quirk C-11, so routes keep their 128-scale coordinates; the
+# other seeds, the scripted scenarios and sizes 512 / 1024 end in "hero_on_obstacle").
+VALID_SEEDS = {64: [0, 2, 3, 5, 6, 10, 11, 12, 16, 18, 19, 20, 21, 22, 23, 26, 29, 32, 34, 36, 37, 38],
+               256: [0, 1, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 21, 22, 23, 24, 25, 26, 27, 28]}
+
+
+def _scale_case(name, size, env_kwargs, acts, frame_every):
+    seeds = VALID_SEEDS[size]
+    opts = lambda ep: dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100), scene_seed=seeds[ep % len(seeds)])  # noqa: E731
+    run_case(name, dict(size=size, **env_kwargs), opts, acts, frame_every=frame_every)
+
+
+@case
+def size256_rdm_discrete():
+    acts = np.random.default_rng(21).integers(0, 9, 300)
+    acts[40:120] = 1  # a stretch of plain throttle so that the ego gets somewhere
+    _scale_case("size256_rdm_discrete", 256, dict(obs_mode="bev_semantic"), acts, 6)
+
+
+@case
+def size256_rdm_gray_lookahead():
+    acts = cont_actions(22, 160, gas_bias=0.3)
+    acts[:, 2] *= 0.2
+    _scale_case("size256_rdm_gray_lookahead", 256,
+                dict(obs_mode="bev_rgb", action_mode="continuous", ego_anchor_x_frac=0.5, ego_anchor_y_frac=0.75), acts, 6)
+
+
+@case
+def size64_rdm_discrete():
+    acts = np.random.default_rng(23).integers(0, 9, 300)
+    acts[40:120] = 1
+    _scale_case("size64_rdm_discrete", 64, dict(obs_mode="bev_semantic"), acts, 3)
+
+
+@case
+def size64_rdm_gray_lookahead():
+    acts = cont_actions(24, 160, gas_bias=0.3)
+    acts[:, 2] *= 0.2
+    _scale_case("size64_rdm_gray_lookahead", 64,
+                dict(obs_mode="bev_rgb", action_mode="continuous", ego_anchor_x_frac=0.5, ego_anchor_y_frac=0.75), acts, 3)
+
+
 if __name__ == "__main__":
     pat = sys.argv[1] if len(sys.argv) > 1 else ""
     if pat in ("", "map"):
-        dump_map()
+        for size in (128, 64, 256):
+            dump_map(size)
     for name, fn in CASES.items():
         if pat in name:
             fn()

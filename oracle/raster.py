@@ -221,7 +221,8 @@ def render_fov(cls_map, geom: FovGeometry, x, y, theta, rects, fov_mask=None):
     if fov_mask is not None:                       # apply_mask before the ego is drawn (world.py:150-156)
         out[fov_mask] = PAL_BLACK
     ax, ay = geom.anchor
-    out[max(ay - 2, 0):ay + 2, max(ax - 2, 0):ax + 2] = PAL_BLACK   # ego square, rect centred on the anchor
+    hw = int(32 / int(1024 / size))                # hero.py:14-17: 4 px at the 128 scale
+    out[max(ay - (hw >> 1), 0):ay - (hw >> 1) + hw, max(ax - (hw >> 1), 0):ax - (hw >> 1) + hw] = PAL_BLACK   # ego square, rect centred on the anchor
     return out
 
 
@@ -251,6 +252,42 @@ def _area_table(ssize, dsize):
     return tab
 
 
+def _linear_area_tab(ssize, dsize):
+    """One axis of cv::resize's bilinear set-up in `area_mode` (OpenCV imgproc/resize.cpp, the dx loop of
+    cv::resize): source index and the two 11-bit fixed-point taps (INTER_RESIZE_COEF_BITS = 11)."""
+    scale = ssize / dsize
+    inv = 1.0 / scale
+    ofs = np.zeros(dsize, np.int32)
+    taps = np.zeros((dsize, 2), np.int32)
+    for dx in range(dsize):
+        sx = math.floor(dx * scale)
+        fx = np.float32((dx + 1) - (sx + 1) * inv)
+        fx = np.float32(0.0) if fx <= 0 else np.float32(fx - np.floor(fx))
+        if sx >= ssize - 1:
+            fx, sx = np.float32(0.0), ssize - 1
+        ofs[dx] = sx
+        taps[dx, 0] = int(np.rint(np.float32((np.float32(1.0) - fx) * np.float32(2048))))
+        taps[dx, 1] = int(np.rint(np.float32(fx * np.float32(2048))))
+    return ofs, taps
+
+
+def resize_linear_area_mode(img, out_hw):
+    """cv2.resize(..., INTER_AREA) when an axis ENLARGES (EnvConfig.size = 64 with obs_size 96):
+    OpenCV only implements true area interpolation for scale >= 1 on both axes and otherwise emulates it with its 8-bit
+    bilinear kernel on area-mode coefficients -- HResizeLinear (int32 rows = S0 * a0 + S1 * a1) then VResizeLinear
+    ((b0 * (S0 >> 4) >> 16) + (b1 * (S1 >> 4) >> 16) + 2) >> 2.  Pinned on cv2 itself in tests/test_oracle_contracts.py."""
+    sh, sw = img.shape[:2]
+    dh, dw = out_hw
+    xo, xa = _linear_area_tab(sw, dw)
+    yo, ya = _linear_area_tab(sh, dh)
+    tail = (1,) * (img.ndim - 2)
+    src = img.astype(np.int32)
+    rows = src[:, xo] * xa[:, 0].reshape((1, dw) + tail) + src[:, np.minimum(xo + 1, sw - 1)] * xa[:, 1].reshape((1, dw) + tail)
+    b0, b1 = ya[:, 0].reshape((dh, 1) + tail), ya[:, 1].reshape((dh, 1) + tail)
+    out = (((b0 * (rows[yo] >> 4)) >> 16) + ((b1 * (rows[np.minimum(yo + 1, sh - 1)] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def resize_area(img, out_hw):
     """gymnasium ResizeObservation -> cv2.resize(..., INTER_AREA) when shrinking (envs/__init__.py:62):
     equal size -> copy; exactly half on both axes -> OpenCV's 2x2 integer path (a + b + c + d + 2) >> 2;
@@ -260,6 +297,8 @@ def resize_area(img, out_hw):
     dh, dw = out_hw
     if (dh, dw) == (sh, sw):
         return img.copy()
+    if dh > sh or dw > sw:
+        return resize_linear_area_mode(img, out_hw)
     if (2 * dh, 2 * dw) == (sh, sw):
         s = img.astype(np.int32)
         return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)

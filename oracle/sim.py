@@ -267,8 +267,10 @@ def rects_overlap(ax, ay, aw, bx, by, bw):
 class SceneSim:
     """One environment's world: ego + scripted actors + targets (scene.py, actor_manager.py, hero.py)."""
 
-    def __init__(self, scene, cls_map, pad, reward_mode="carl", reward_params=None):
+    def __init__(self, scene, cls_map, pad, reward_mode="carl", reward_params=None, size=128):
         self.scene = scene
+        self.scale = int(1024 / int(size))   # hero.py:14 (EnvConfig.size: 8 at the 128 scale)
+        self.hero_w = int(32 / self.scale)   # hero.py:17: the ego square, 4 px at the 128 scale
         self.cls_map = cls_map  # (H, W) uint8 classes
         self.pad = int(pad)
         self.reward_mode = reward_mode
@@ -343,14 +345,14 @@ class SceneSim:
         e = self.ego
         _, e.tidx = e.stanley()
         f32 = np.float32
-        acc_val = float(f32(gas) * f32(8.0)) if gas > 0 else 0.0          # hero.py:140-142
+        acc_val = float(f32(gas) * f32(self.scale)) if gas > 0 else 0.0          # hero.py:140-142
         if abs(e.v) < 0.1:                                                  # hero.py:144-158
             delta = 0.0
         else:
             steer_deg = np.clip(18.0 / (1.0 + 0.35 * abs(e.v)), 8.0, 18.0)
             delta = math.radians(float(f32(steer)) * steer_deg)
         speed_factor = np.clip(abs(e.v) / 5.0, 0.3, 1.0)                    # hero.py:160-162
-        brake_val = (float((f32(brake) * f32(0.6)) * f32(8.0)) if brake > 0 else 0.0) * speed_factor
+        brake_val = (float((f32(brake) * f32(0.6)) * f32(self.scale)) if brake > 0 else 0.0) * speed_factor
         target_acc = acc_val - brake_val - 0.05 * e.v
         alpha = 0.2
         self.acc = (1 - alpha) * self.acc + alpha * target_acc
@@ -427,8 +429,9 @@ class SceneSim:
         """Scene.collision_check, scene.py:110-140: (hit, hit_id, nearby, tile_class)."""
         pad = self.pad
         e = self.ego
-        hx, hy = rect_left(e.x, pad, 4), rect_left(e.y, pad, 4)
-        hcx, hcy = hx + 2, hy + 2
+        hw = self.hero_w
+        hx, hy = rect_left(e.x, pad, hw), rect_left(e.y, pad, hw)
+        hcx, hcy = hx + (hw >> 1), hy + (hw >> 1)
         hit, hit_id = HIT_NONE, -1
         nearby = []
         for kind in (KIND_VEHICLE, KIND_PEDESTRIAN):  # dict order: vehicle, pedestrian (actor_manager.py:25-31)
@@ -440,7 +443,7 @@ class SceneSim:
                 dist = math.hypot(hcx - (ax + half), hcy - (ay + half))
                 if abs(dist) < MIN_DIST:
                     nearby.append((a.x, a.y, a.v * np.cos(a.yaw), a.v * np.sin(a.yaw)))
-                if rects_overlap(hx, hy, 4, ax, ay, a.size):
+                if rects_overlap(hx, hy, hw, ax, ay, a.size):
                     hit, hit_id = (HIT_VEHICLE if kind == KIND_VEHICLE else HIT_PEDESTRIAN), kind
         n = len(self.tgt_x)
         for i in range(n):  # target.py:37-44
@@ -448,7 +451,7 @@ class SceneSim:
                 continue
             size = 4 if i == n - 1 else 2
             tx, ty = rect_left(self.tgt_x[i], pad, size), rect_left(self.tgt_y[i], pad, size)
-            if rects_overlap(hx, hy, 4, tx, ty, size):
+            if rects_overlap(hx, hy, hw, tx, ty, size):
                 self.tgt_visible[i] = False
                 hit, hit_id = HIT_TARGET, i
         return hit, hit_id, nearby, self.tile_class()

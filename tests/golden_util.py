@@ -12,10 +12,12 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 ALL_CASES = ("lead_brake_continuous", "rdm_medium_discrete", "jaywalk_levels", "jaywalk_drive", "red_light_runner",
              "rdm_shaping_discrete13", "rdm_rgb_lookahead", "fusion_temporal_masked", "fusion_weighted")
+# EnvConfig.size 64 / 256 (the reference runs `rdm` scenes there; oracle/gen_golden.py)
+SCALE_CASES = ("size256_rdm_discrete", "size256_rdm_gray_lookahead", "size64_rdm_discrete", "size64_rdm_gray_lookahead")
 
 
-def load_map():
-    with np.load(os.path.join(ROOT, "carlabev_env_b200", "assets", "town01_128_cls.npz")) as z:
+def load_map(size=128):
+    with np.load(os.path.join(ROOT, "carlabev_env_b200", "assets", f"town01_{size}_cls.npz")) as z:
         return np.ascontiguousarray(z["cls"])
 
 
@@ -28,6 +30,7 @@ class Golden:
         self.episode_infos = {int(k): v for k, v in json.loads(str(self.d["episode_infos"])).items()}
         self.pool = {k[len("pool_"):]: v for k, v in self.d.items() if k.startswith("pool_")}
         self.T = len(self.d["reward"])
+        self.size = int(self.env_kwargs.get("size", 128))
 
     def __getitem__(self, k):
         return self.d[k]
@@ -46,6 +49,7 @@ class Golden:
             anchor=(kw.get("ego_anchor_x_frac", 0.5), kw.get("ego_anchor_y_frac", 0.5)),
             fov_masked=kw.get("fov_masked", False),
             temporal_fusion_mode=kw.get("temporal_fusion_mode", "stack"),
+            size=self.size,
         )
 
     def full_obs(self, key="obs_full"):

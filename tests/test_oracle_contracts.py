@@ -48,6 +48,28 @@ def test_area_resize_any_obs_size_matches_cv2(size):
         assert np.array_equal(raster.resize_area(img, size), want)
 
 
+@pytest.mark.parametrize("view,size", [(256, (96, 96)), (256, (128, 128)), (256, (84, 84)), (256, (64, 96)), (256, (100, 60)),
+                                       (64, (96, 96)), (64, (84, 84)), (64, (128, 128)), (64, (64, 64)), (64, (32, 32)),
+                                       (64, (48, 96)), (64, (96, 48)), (64, (72, 100)), (64, (65, 65))])
+def test_resize_from_other_view_sizes_matches_cv2(view, size):
+    """EnvConfig.size 256 shrinks by 8/3 (area tables); size 64 ENLARGES, where cv2's INTER_AREA is its
+    8-bit bilinear kernel on area-mode coefficients (raster.resize_linear_area_mode), also when only one axis enlarges."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(view * 7 + size[0] * 131 + size[1])
+    for k in range(4):
+        if k % 2 == 0:
+            img = raster.PALETTE[rng.integers(0, 10, (view, view))]
+        else:
+            idx = np.ones((view, view), dtype=np.int64)
+            for _ in range(40):
+                x, y, w, h = (rng.integers(0, view - 8), rng.integers(0, view - 8), rng.integers(1, view // 3),
+                              rng.integers(1, view // 3))
+                idx[y:y + h, x:x + w] = rng.integers(0, 10)
+            img = raster.PALETTE[idx]
+        want = cv2.resize(img, (size[1], size[0]), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(raster.resize_area(img, size), want)
+
+
 def test_mask_coincidence_is_kept():
     # 1/2 white + 1/4 gray150 + 1/4 sidewalk220 = 220 = SIDEWALK (SURVEY.md A.7): the blend path must report it
     img = np.zeros((128, 128, 3), np.uint8)

@@ -4,18 +4,18 @@ must be bit-identical on the CPU; flags, palette frames and observations exact."
 import numpy as np
 import pytest
 
-from golden_util import ALL_CASES, Golden, crc, load_map
+from golden_util import ALL_CASES, SCALE_CASES, Golden, crc, load_map
 from oracle import raster
 from oracle.env import OracleEnv, unpack_pool
 
 STEP_LIMIT = {"rdm_medium_discrete": 160, "jaywalk_levels": 330, "rdm_rgb_lookahead": 120}  # keep the CPU suite short
 
 
-@pytest.mark.parametrize("case", ALL_CASES)
+@pytest.mark.parametrize("case", ALL_CASES + SCALE_CASES)
 def test_oracle_replays_reference_golden(case):
     g = Golden(case)
     scenes = unpack_pool(g.pool)
-    env = OracleEnv(load_map(), **g.oracle_kwargs())
+    env = OracleEnv(load_map(g.size), **g.oracle_kwargs())
     resets = dict(zip(g["reset_steps"].tolist(), g["reset_scene"].tolist()))
     fsteps = {int(s): i for i, s in enumerate(g["frame_steps"])}
     osteps = {int(s): i for i, s in enumerate(g["obs_steps"])}
