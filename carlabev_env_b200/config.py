@@ -93,8 +93,8 @@ def list_difficulty_ids() -> list:
 
 
 def get_env_capabilities() -> dict:
-    """config/env.py:328-355: what this implementation of the environment accepts (one map scale: Town01 at
-    size 128; `vector` observations are reachable through `CarlaBEVVectorEnv.vector_observation()`, not make_env)."""
+    """config/env.py:328-355: what this implementation of the environment accepts (Town01 at the map scales
+    64 / 128 / 256; `vector` observations are reachable through `CarlaBEVVectorEnv.vector_observation()`, not make_env)."""
     from .scenes import SCENARIO_PRESETS, _SPEC_DEFAULTS
 
     masks = ["binary", "2-class", "4-class", "5-class", "6-class", "7-class"]
@@ -193,6 +193,10 @@ class EnvConfig:
                              f"{reward_spec['family']!r}, but EnvConfig.reward_mode={self.reward_mode!r}")
         if self.map_name != "Town01":
             raise ValueError(f"map_name='{self.map_name}' is missing required assets (only Town01 ships)")
+        if self.size not in (64, 128, 256):
+            # config/env.py:146-160 checks that Town01-<size>-{sem,rgb}.png exist (64 ... 1024 do); the unmodified
+            # reference cannot reset at 512 / 1024 ("hero_on_obstacle" for every seed: quirk C-11), so those are not served
+            raise ValueError(f"size={self.size}: Town01 ships at the map scales 64, 128 and 256")
 
     # legacy computed fields, config/env.py:162-181
     @property

@@ -118,15 +118,20 @@ int build_tensor_map(cbev_engine* e) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)e->map_w, (cuuint64_t)e->map_h};
   cuuint64_t strides[1] = {(cuuint64_t)e->map_w};
-  cuuint32_t box[2] = {(cuuint32_t)CBEV_TILE_W, (cuuint32_t)CBEV_TILE_H};  // the fetch window (sim.cu:compute_view)
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = ((EncodeTiledFn)fn)(reinterpret_cast<CUtensorMap*>(e->tmap), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, e->map,
-                                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    cbev_set_error("cuTensorMapEncodeTiled failed with CUresult %d (map %dx%d, box %dx%d)", (int)r, e->map_w, e->map_h,
-                   CBEV_TILE_W, CBEV_TILE_H);
-    return CBEV_ERR_CUDA;
+  // two views of the same map: the one-box fetch window of k_render, and the strip box of k_render_any
+  for (int which = 0; which < 2; ++which) {
+    cuuint32_t box[2] = {(cuuint32_t)(which ? CBEV_ANY_BOX_W : CBEV_TILE_W),
+                         (cuuint32_t)(which ? e->any_box_h : CBEV_TILE_H)};  // sim.cu:compute_view
+    CUresult r = ((EncodeTiledFn)fn)(reinterpret_cast<CUtensorMap*>(which ? e->tmap_any : e->tmap),
+                                     CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, e->map, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      cbev_set_error("cuTensorMapEncodeTiled failed with CUresult %d (map %dx%d, box %dx%d)", (int)r, e->map_w, e->map_h,
+                     (int)box[0], (int)box[1]);
+      return CBEV_ERR_CUDA;
+    }
   }
   return CBEV_OK;
 }
@@ -252,12 +257,40 @@ static void area_table(int ssize, int dsize, std::vector<int32_t>& off, std::vec
   }
 }
 
-// rs_tab = [nx, ny, xoff[ow+1], yoff[oh+1], xsi[nx], ysi[ny], xalpha[nx], yalpha[ny]]
+// One axis of cv::resize's bilinear set-up in area mode (the dx loop of cv::resize, imgproc/src/resize.cpp): source
+// index and the two 11-bit fixed-point taps.  INTER_AREA takes this branch when an axis enlarges (size 64 -> 96).
+// Checked against cv2 itself through the oracle's identical table (oracle/raster.py:_linear_area_tab).
+static void linear_area_table(int ssize, int dsize, std::vector<int32_t>& ofs, std::vector<int32_t>& a0,
+                              std::vector<int32_t>& a1) {
+  const double scale = (double)ssize / dsize, inv = 1.0 / scale;
+  for (int dx = 0; dx < dsize; ++dx) {
+    int sx = (int)std::floor(dx * scale);
+    float fx = (float)((dx + 1) - (sx + 1) * inv);
+    fx = fx <= 0 ? 0.f : fx - std::floor(fx);
+    if (sx >= ssize - 1) { fx = 0.f; sx = ssize - 1; }
+    ofs.push_back(sx);
+    a0.push_back((int32_t)std::lrintf((1.f - fx) * 2048.f));
+    a1.push_back((int32_t)std::lrintf(fx * 2048.f));
+  }
+}
+
+// area:     rs_tab = [nx, ny, xoff[ow+1], yoff[oh+1], xsi[nx], ysi[ny], xalpha[nx], yalpha[ny]]
+// bilinear: rs_tab = [0, 0, xofs[ow], yofs[oh], xa0[ow], xa1[ow], yb0[oh], yb1[oh]]
 static int build_resize_tables(cbev_engine* e) {
   const int S = e->cfg.fov_size, oh = e->cfg.obs_h, ow = e->cfg.obs_w;
   e->rs_words = 0;
-  if (e->cfg.obs_mode == CBEV_OBS_RGB || (oh == 96 && ow == 96)) { e->rs_mode = CBEV_RS_FAST96; return CBEV_OK; }
-  if (oh == S && ow == S) e->rs_mode = CBEV_RS_COPY;
+  if (e->cfg.obs_mode == CBEV_OBS_RGB) { e->rs_mode = CBEV_RS_FAST96; return CBEV_OK; }
+  if (oh > S || ow > S) {
+    e->rs_mode = CBEV_RS_LINEAR;
+    std::vector<int32_t> xo, xa0, xa1, yo, yb0, yb1, tab(2, 0);
+    linear_area_table(S, ow, xo, xa0, xa1);
+    linear_area_table(S, oh, yo, yb0, yb1);
+    for (auto* v : {&xo, &yo, &xa0, &xa1, &yb0, &yb1}) tab.insert(tab.end(), v->begin(), v->end());
+    e->rs_words = (int32_t)tab.size();
+    return dev_upload(&e->rs_tab, tab.data(), tab.size());
+  }
+  if (S == 128 && oh == 96 && ow == 96) e->rs_mode = CBEV_RS_FAST96;  // k_render; the tables serve debug flag 256
+  else if (oh == S && ow == S) e->rs_mode = CBEV_RS_COPY;
   else if (2 * oh == S && 2 * ow == S) e->rs_mode = CBEV_RS_HALF;
   else e->rs_mode = CBEV_RS_TABLE;
   std::vector<int32_t> xo, yo, xs, ys;
@@ -281,15 +314,20 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   if (!cfg || !out) { cbev_set_error("null argument"); return CBEV_ERR_ARG; }
   *out = nullptr;
   if (cfg->num_envs < 1) { cbev_set_error("num_envs must be >= 1"); return CBEV_ERR_ARG; }
-  if (cfg->fov_size != 128) { cbev_set_error("only size=128 (Town01-128 map scale) is implemented, got %d", cfg->fov_size); return CBEV_ERR_ARG; }
+  if (cfg->fov_size != 64 && cfg->fov_size != 128 && cfg->fov_size != 256) {
+    // the unmodified reference cannot reset at 512 / 1024 either ("hero_on_obstacle": its scene generators keep the
+    // 128-scale coordinates, quirk C-11); a 512-px view would also need a banded raster kernel
+    cbev_set_error("size must be 64, 128 or 256 (Town01 map scales the reference can reset on), got %d", cfg->fov_size);
+    return CBEV_ERR_ARG;
+  }
   if (cfg->obs_mode < 0 || cfg->obs_mode > 2) { cbev_set_error("bad obs_mode %d", cfg->obs_mode); return CBEV_ERR_ARG; }
   if (cfg->obs_mode != CBEV_OBS_RGB) {
-    // ResizeObservation = cv2.resize(INTER_AREA) of the 128 x 128 frame; enlarging takes OpenCV's bilinear branch
-    // (not built), and the observation planes are streamed with 16-byte stores
+    // ResizeObservation = cv2.resize(INTER_AREA) of the size x size frame (enlarging takes OpenCV's bilinear branch);
+    // the observation planes are streamed with 16-byte stores
     const int px = cfg->obs_h * cfg->obs_w;
-    if (cfg->obs_h < 8 || cfg->obs_w < 8 || cfg->obs_h > 128 || cfg->obs_w > 128 ||
+    if (cfg->obs_h < 8 || cfg->obs_w < 8 || cfg->obs_h > 256 || cfg->obs_w > 256 ||
         px % (cfg->obs_mode == CBEV_OBS_SEMANTIC ? 4 : 16) != 0) {
-      cbev_set_error("obs_size must be within 8..128 per side with height*width a multiple of %d, got (%d, %d)",
+      cbev_set_error("obs_size must be within 8..256 per side with height*width a multiple of %d, got (%d, %d)",
                      cfg->obs_mode == CBEV_OBS_SEMANTIC ? 4 : 16, cfg->obs_h, cfg->obs_w);
       return CBEV_ERR_ARG;
     }
@@ -323,8 +361,19 @@ int cbev_create(const cbev_config* cfg, cbev_handle* out) {
   int mx = ax > m - ax ? ax : m - ax, my = ay > m - ay ? ay : m - ay;
   int crop = (int)ceil(2.0 * hypot((double)mx, (double)my));
   if (crop < cfg->fov_size) crop = cfg->fov_size;
-  e->crop = crop;  // any size: the raster kernel only ever fetches the CBEV_TILE_H x CBEV_TILE_W window a frame can sample
+  e->crop = crop;  // any size: the raster kernel only ever fetches the window a frame can sample
   e->pad = crop;
+  {
+    // fetch window of one frame: <= ceil(S * sqrt(2)) + 2 px on a side (sim.cu:compute_view).  k_render_any lands it as
+    // column strips of CBEV_ANY_BOX_W bytes (15 bytes of TMA alignment slack) x row boxes of <= 256 rows.
+    const int S = cfg->fov_size;
+    const int win = (int)ceil(S * sqrt(2.0)) + 2;
+    const int tile_h = (win + 7) & ~7;
+    e->any_nby = (tile_h + 255) / 256;
+    e->any_box_h = ((tile_h + e->any_nby - 1) / e->any_nby + 7) & ~7;
+    e->any_nbx = (win + 15 + CBEV_ANY_BOX_W - 1) / CBEV_ANY_BOX_W;
+    e->win_max = S == 128 ? CBEV_TILE_H : e->any_box_h * e->any_nby;
+  }
   e->channels = cfg->obs_mode == CBEV_OBS_SEMANTIC ? channels_of(cfg->mask_mode) : 1;
   if (cfg->obs_mode == CBEV_OBS_SEMANTIC) e->frame_bytes = (int64_t)e->channels * cfg->obs_h * cfg->obs_w * 4;
   else if (cfg->obs_mode == CBEV_OBS_GRAY) e->frame_bytes = (int64_t)cfg->obs_h * cfg->obs_w;

@@ -81,6 +81,8 @@ struct PoolDev {
 struct SimParams {
   int32_t N, env_lo, env_hi, max_actors, max_rects, max_retreat;
   int32_t map_w, map_h, fov, crop, pad, anchor_x, anchor_y;
+  int32_t hero_w, win_max;  // ego square (hero.py:17); largest fetch window the raster kernel holds
+  float hero_scale;         // hero.py:14: int(1024 / size)
   int32_t action_mode, n_discrete, reward_mode, autoreset;
   uint64_t seed;
   const uint8_t* map;
@@ -88,11 +90,14 @@ struct SimParams {
   cbev_config cfg;  // reward parameters
 };
 
-// ResizeObservation variants (cv2.resize INTER_AREA from the 128 x 128 field of view)
-#define CBEV_RS_FAST96 0  /* (96, 96): 4x4-block two-pass kernel, weights in 1/16            */
-#define CBEV_RS_TABLE 1   /* any size <= 128: OpenCV's float32 area tables                    */
-#define CBEV_RS_HALF 2    /* (64, 64): OpenCV's 2x2 fast path, (a + b + c + d + 2) >> 2        */
-#define CBEV_RS_COPY 3    /* (128, 128): cv2.resize returns a copy                            */
+// ResizeObservation variants (cv2.resize INTER_AREA from the S x S field of view, S = EnvConfig.size)
+#define CBEV_RS_FAST96 0  /* 128 -> (96, 96): 4x4-block two-pass kernel, weights in 1/16 (k_render)        */
+#define CBEV_RS_TABLE 1   /* shrinking on both axes: OpenCV's float32 area tables                          */
+#define CBEV_RS_HALF 2    /* exactly S/2 on both axes: OpenCV's 2x2 fast path, (a + b + c + d + 2) >> 2    */
+#define CBEV_RS_COPY 3    /* (S, S): cv2.resize returns a copy                                             */
+#define CBEV_RS_LINEAR 4  /* an axis enlarges (size 64 -> 96): OpenCV's 8-bit bilinear kernel on area-mode */
+                          /* coefficients (11-bit fixed point)                                             */
+#define CBEV_ANY_BOX_W 128  /* k_render_any: the fetch window lands as column strips of 128 bytes (one TMA box each) */
 
 struct cbev_engine {
   cbev_config cfg;
@@ -100,7 +105,10 @@ struct cbev_engine {
   int32_t N = 0, crop = 0, pad = 0, anchor_x = 0, anchor_y = 0;
   int32_t map_w = 0, map_h = 0;
   uint8_t* map = nullptr;
-  alignas(64) unsigned char tmap[128];  // CUtensorMap of the class map
+  alignas(64) unsigned char tmap[128];  // CUtensorMap of the class map, box = CBEV_TILE_W x CBEV_TILE_H (k_render)
+  alignas(64) unsigned char tmap_any[128];  // same map, box = CBEV_ANY_BOX_W x any_box_h (k_render_any)
+  int32_t win_max = 0;                  // largest fetch window (rows / columns) the raster kernel in use can hold
+  int32_t any_nbx = 0, any_nby = 0, any_box_h = 0;  // k_render_any: strips x row boxes of the fetch window
   bool has_map = false, has_pool = false, was_reset = false, keep_fov = false;
   PoolDev pool;
   EnvState st;

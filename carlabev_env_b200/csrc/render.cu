@@ -107,6 +107,8 @@ struct RenderParams {
   int32_t obs_h, obs_w, rs_mode, rs_words;  // rs_mode: CBEV_RS_* (engine.h); rs_words = size of rs_tab
   const int32_t* rs_tab;                    // cv2 area tables of both axes (api.cu: build_resize_tables)
   unsigned long long* trace;                // [N][8] phase timestamps or null (cbev_debug_read_trace)
+  int32_t hero_w;                           // ego square (hero.py:17), 4 px at size 128
+  int32_t nbx, nby, box_h, region_bytes;    // k_render_any: strips x row boxes of the fetch window; tile / output region
 };
 
 __device__ __forceinline__ void trace_mark(const RenderParams& P, int env, int slot) {
@@ -184,9 +186,9 @@ __device__ __forceinline__ uint32_t classify_key(uint32_t key, const uint32_t* s
 __device__ __forceinline__ int fov_word(int row, int cw) { return row * 32 + ((((cw >> 2) ^ row) & 7) << 2) + (cw & 3); }
 __device__ __forceinline__ int fov_byte(int row, int x) { return row * 128 + ((((x >> 4) ^ row) & 7) << 4) + (x & 15); }
 
-// GEN = false: the 128 -> 96 x 96 specialisation (4x4-block two-pass resize).  GEN = true: any obs_size <= 128 through
-// OpenCV's area tables (float32 accumulate in OpenCV's order), the 2x2 integer average for 64 x 64, or a copy for 128.
-template <int OBS_MODE, int CHANNELS, bool GEN>
+// The EnvConfig.size = 128, obs_size = (96, 96) specialisation (4x4-block two-pass resize) -- every BASELINE
+// configuration.  Other view sizes and observation sizes go through k_render_any below.
+template <int OBS_MODE, int CHANNELS>
 __global__ void __launch_bounds__(RT, 4)
 k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -206,7 +208,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   uint8_t* s_cm = (uint8_t*)(s_bar + 2);     // channel bits per palette index for this mask mode
   float4* s_lut = (float4*)(s_cm + 16);      // 16 x float4: 4 mask bits -> four 0.0f / 1.0f values
   int* s_count = (int*)(s_lut + 16);
-  uint32_t* s_rects = (uint32_t*)(s_count + 4);  // draw list (max_rects x 2 words); the resize tables follow (GEN)
+  uint32_t* s_rects = (uint32_t*)(s_count + 4);  // draw list (max_rects x 2 words)
 
   const int env = P.order != nullptr ? P.order[P.env_lo + blockIdx.x] : P.env_lo + blockIdx.x;
   const int tid = threadIdx.x;
@@ -444,60 +446,9 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
     return;
   }
 
-  const int OH = GEN ? P.obs_h : 96, OW = GEN ? P.obs_w : 96;
+  constexpr int OH = 96, OW = 96;
   uint8_t* s_out = s_region;                        // OH x OW bytes: channel bitmask (semantic) or gray level
-  if (GEN) {
-    // ---- 4g. cv2.resize(INTER_AREA) for any obs_size <= 128 (ResizeObservation, envs/__init__.py:62) ----
-    int32_t* s_tab = (int32_t*)(s_rects + ((P.max_rects * CBEV_RECT_WORDS + 3) & ~3));
-    for (int u = tid; u < P.rs_words; u += RT) s_tab[u] = P.rs_tab[u];
-    __syncthreads();
-    const int nx = s_tab[0], ny = s_tab[1];
-    const int32_t* xoff = s_tab + 2;
-    const int32_t* yoff = xoff + OW + 1;
-    const int32_t* xsi = yoff + OH + 1;
-    const int32_t* ysi = xsi + nx;
-    const float* xal = (const float*)(ysi + ny);
-    const float* yal = xal + nx;
-    for (int o = tid; o < OH * OW; o += RT) {
-      const int dy = o / OW, dx = o - dy * OW;
-      uint32_t key;
-      if (P.rs_mode == CBEV_RS_COPY) {
-        key = s_key[s_fov[fov_byte(dy, dx)]];
-      } else if (P.rs_mode == CBEV_RS_HALF) {
-        // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
-        const uint8_t* q0 = s_fov + fov_byte(2 * dy, 2 * dx);
-        const uint8_t* q1 = s_fov + fov_byte(2 * dy + 1, 2 * dx);
-        const uint32_t c0 = q0[0], c1 = q0[1], c2 = q1[0], c3 = q1[1];
-        const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
-        const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
-        key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
-      } else {
-        // ResizeArea_Invoker: buf = sum_x S * alpha (from 0, in table order); sum = sum_y beta * buf; float32, no FMA
-        float sr = 0.f, sg = 0.f, sb = 0.f;
-        const int y0 = yoff[dy], y1 = yoff[dy + 1], x0 = xoff[dx], x1 = xoff[dx + 1];
-        for (int j = y0; j < y1; ++j) {
-          const int srow = ysi[j];
-          float br = 0.f, bg = 0.f, bb = 0.f;
-          for (int k = x0; k < x1; ++k) {
-            const uint32_t kk = s_key[s_fov[fov_byte(srow, xsi[k])]];
-            const float a = xal[k];
-            br = __fadd_rn(br, __fmul_rn((float)(kk & 255u), a));
-            bg = __fadd_rn(bg, __fmul_rn((float)((kk >> 8) & 255u), a));
-            bb = __fadd_rn(bb, __fmul_rn((float)(kk >> 16), a));
-          }
-          const float beta = yal[j];
-          sr = __fadd_rn(sr, __fmul_rn(beta, br));
-          sg = __fadd_rn(sg, __fmul_rn(beta, bg));
-          sb = __fadd_rn(sb, __fmul_rn(beta, bb));
-        }
-        const int R = min(max(__float2int_rn(sr), 0), 255), G = min(max(__float2int_rn(sg), 0), 255),
-                  B = min(max(__float2int_rn(sb), 0), 255);
-        key = (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
-      }
-      s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
-    }
-    __syncthreads();
-  } else {
+  {
   // ---- 4. area resize 128 -> 96 + colour equality -> one byte per output pixel ----
   // Every 4x4 source block maps to a 3x3 output block (period of the 4/3 scale on both axes).
   // Pass A: a block whose 16 texels are equal resolves to one table lookup for all 9 outputs; the other
@@ -561,7 +512,7 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   // ---- 5. expand + stream out ----
   trace_mark(P, env, 4);
   if (P.pad0 & 8) return;  // timing probe: no observation stores
-  if (!GEN && OBS_MODE == CBEV_OBS_SEMANTIC && (P.pad0 & 16)) {  // experiment (profiles/README.md): slower than direct stores
+  if (OBS_MODE == CBEV_OBS_SEMANTIC && (P.pad0 & 16)) {  // experiment (profiles/README.md): slower than direct stores
     // Expand one third of a channel plane (12 KB) at a time into a double-buffered staging area in the dead tile
     // region and hand it to the copy engine, once per ring slot the frame belongs to (a reset frame fills the whole
     // window, frames near the wrap are mirrored): the expansion is done once whatever the number of destinations.
@@ -640,6 +591,286 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
   trace_mark(P, env, 5);
 }
 
+// ---- any view size, any observation size ------------------------------------------------------------------------
+// EnvConfig.size in {64, 128, 256} (hero.py:14-17, world.py:38-49; the view, the crop and
+// the map scale with it) and any EnvConfig.obs_size.  Same pipeline as k_render without its 128 / 96 specialisations:
+//   * the fetch window (<= ceil(S * sqrt 2) + 2 px on a side, 365 px at S = 256) exceeds one TMA box (<= 256 per
+//     dimension), so it lands as `nbx` column strips of CBEV_ANY_BOX_W bytes x `nby` row boxes, all on one mbarrier;
+//     window pixel (x, y) lives at s_tile[((x >> 7) * tile_h + y) * 128 + (x & 127)];
+//   * the rotate is pygame's range-tested per-pixel walk; the frame is stored row-major;
+//   * cv2.resize(INTER_AREA): copy / 2x2 integer path / float32 area tables when shrinking, and OpenCV's 8-bit
+//     bilinear kernel on area-mode coefficients when an axis enlarges (size 64 -> 96).
+// One CTA per env: 256 threads (S <= 128), 1024 threads and ~215 KB of shared memory at S = 256 (one CTA per SM).
+template <int OBS_MODE, int CHANNELS>
+__global__ void __launch_bounds__(1024, 1)
+k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: [tile strips | re-used as the OH x OW output bytes] [frame S x S] [tables] [mbar] [draw list] [resize tables]
+  const int S = P.fov, NT = blockDim.x;
+  constexpr int BW = CBEV_ANY_BOX_W;
+  const int tile_h = P.box_h * P.nby;
+  const int tile_bytes = BW * P.nbx * tile_h;
+  uint8_t* const s_tile = smem;
+  uint8_t* const s_fov = smem + P.region_bytes;
+  uint32_t* s_rg = (uint32_t*)(s_fov + S * S);
+  uint32_t* s_b = s_rg + 16;
+  uint32_t* s_key = s_b + 16;
+  int32_t* s_desc = (int32_t*)(s_key + 16);
+  uint64_t* s_bar = (uint64_t*)(s_desc + CBEV_DESC_WORDS);
+  uint8_t* s_cm = (uint8_t*)(s_bar + 2);
+  uint32_t* s_rects = (uint32_t*)(s_cm + 16);
+  int32_t* s_tab = (int32_t*)(s_rects + ((P.max_rects * CBEV_RECT_WORDS + 3) & ~3));
+
+  const int env = P.order != nullptr ? P.order[P.env_lo + blockIdx.x] : P.env_lo + blockIdx.x;
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid < 2 && P.order_cnt != nullptr) P.order_cnt[tid] = 0;
+  const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
+  const int flags = d[RD_FLAGS];
+  if (flags & 2) return;  // masked-out env of a partial reset
+  trace_mark(P, env, 0);
+
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(s_bar, (uint32_t)tile_bytes);
+    const int x0 = d[RD_OX] & ~15, y0 = d[RD_OY];  // 16-byte aligned inner coordinate (k_render)
+    for (int bx = 0; bx < P.nbx; ++bx)
+      for (int by = 0; by < P.nby; ++by)
+        tma_load_2d(s_tile + (size_t)(bx * tile_h + by * P.box_h) * BW, &tmap, x0 + bx * BW, y0 + by * P.box_h, s_bar);
+  }
+  if (tid < CBEV_DESC_WORDS) s_desc[tid] = d[tid];
+  if (tid < CBEV_PAL_COUNT) {
+    s_rg[tid] = c_pal_rg[tid];
+    s_b[tid] = c_pal_b[tid];
+    s_key[tid] = c_pal_key[tid];
+  }
+  if (tid <= CBEV_PAL_COUNT) s_cm[tid] = c_chan_mask[mask_mode][tid];
+  const int nrects = d[RD_NRECTS];
+  {
+    const uint32_t* rl = P.rects + (size_t)env * P.max_rects * CBEV_RECT_WORDS;
+    for (int r = tid; r < P.max_rects * CBEV_RECT_WORDS; r += NT) s_rects[r] = rl[r];
+  }
+  for (int u = tid; u < P.rs_words; u += NT) s_tab[u] = P.rs_tab[u];
+  __syncthreads();
+  mbar_wait(s_bar, 0);
+  const int shift = s_desc[RD_OX] & 15;
+  const int xmax = BW * P.nbx - 1, ymax = tile_h - 1;
+  // window pixel (x, y) -> byte offset in the strips (clamped: a degenerate view can point outside the window)
+  auto tile_off = [&](int x, int y) {
+    x = min(max(x + shift, 0), xmax);
+    y = min(max(y, 0), ymax);
+    return ((x >> 7) * tile_h + y) * BW + (x & (BW - 1));
+  };
+  trace_mark(P, env, 1);
+
+  // ---- 2. draw list, in order: one rect per thread inside a run of equal colour (k_render) ----
+  {
+    int r = 0;
+    while (r < nrects) {
+      const uint32_t pal = s_rects[2 * r + 1] >> 24;
+      int e = r + 1;
+      while (e < nrects && (s_rects[2 * e + 1] >> 24) == pal) ++e;
+      for (int q = r + tid; q < e; q += NT) {
+        const uint32_t w0 = s_rects[2 * q], w1 = s_rects[2 * q + 1];
+        const int x0 = w0 & 0xffff, y0 = w0 >> 16, w = (w1 & 0xfff) + 1, h = ((w1 >> 12) & 0xfff) + 1;
+        for (int yy = 0; yy < h; ++yy)
+          for (int xx = 0; xx < w; ++xx) s_tile[tile_off(x0 + xx, y0 + yy)] = (uint8_t)pal;
+      }
+      r = e;
+      __syncthreads();
+    }
+  }
+  trace_mark(P, env, 2);
+
+  // ---- 3. rotate + compose + ego square -> S x S palette-index frame (fov.py:84-94) ----
+  uint32_t* fov32 = (uint32_t*)s_fov;
+  {
+    const int mode = s_desc[RD_MODE], turns = s_desc[RD_TURNS];
+    const int nx = s_desc[RD_NX], ny = s_desc[RD_NY];
+    const int isin = s_desc[RD_ISIN], icos = s_desc[RD_ICOS];
+    const int rax = s_desc[RD_AX] + s_desc[RD_XD], ray = s_desc[RD_AY] + s_desc[RD_YD], rcy = s_desc[RD_CY];
+    const int left = P.anchor_x - (nx >> 1), top = P.anchor_y - (ny >> 1);  // get_rect(center=anchor)
+    const int crop = P.crop;
+    const int lim = (crop << 16) - 1;
+    const uint32_t bg = (uint32_t)s_desc[RD_BG];
+    const int fx = s_desc[RD_FX], fy = s_desc[RD_FY];
+    const int wq = S >> 2;  // words per frame row
+    for (int u = tid; u < S * wq; u += NT) {
+      const int oy = u / wq, ox0 = (u - oy * wq) * 4;
+      const int ryp = oy - top;
+      const bool row_in = ryp >= 0 && ryp < ny;
+      const int bx = rax + isin * (rcy - ryp);
+      const int by = ray - icos * (rcy - ryp);
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rxp = ox0 + k - left;
+        uint32_t v = CBEV_PAL_BLACK;
+        if (row_in && rxp >= 0 && rxp < nx) {
+          if (mode == 0) {
+            int sx, sy;
+            if (turns == 0) { sx = rxp; sy = ryp; }
+            else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
+            else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
+            else { sx = ryp; sy = crop - 1 - rxp; }
+            v = s_tile[tile_off(sx - fx, sy - fy)];
+          } else {
+            const int dx = bx + rxp * icos, dy = by + rxp * isin;
+            if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
+            else v = s_tile[tile_off((dx >> 16) - fx, (dy >> 16) - fy)];
+          }
+        }
+        packed |= v << (8 * k);
+      }
+      fov32[u] = packed;
+    }
+    __syncthreads();
+    if (P.fov_mask != nullptr) {  // apply_mask (fov.py:96-99) before the ego is drawn
+      for (int u = tid; u < S * wq; u += NT) {
+        const uint32_t mk = ((const uint32_t*)P.fov_mask)[u];
+        fov32[u] = (fov32[u] & ~mk) | ((CBEV_PAL_BLACK * 0x01010101u) & mk);
+      }
+      __syncthreads();
+    }
+    // Hero.draw: hero_w x hero_w black square, rect centred on the anchor (hero.py:17-32), clipped to the surface
+    const int hw = P.hero_w;
+    if (tid < hw * hw) {
+      const int x = P.anchor_x - (hw >> 1) + tid % hw, y = P.anchor_y - (hw >> 1) + tid / hw;
+      if (x >= 0 && x < S && y >= 0 && y < S) s_fov[y * S + x] = CBEV_PAL_BLACK;
+    }
+  }
+  __syncthreads();
+  trace_mark(P, env, 3);
+  if (P.fov_out != nullptr) {
+    uint4* dst = (uint4*)(P.fov_out + (size_t)env * S * S);
+    for (int u = tid; u < S * S / 16; u += NT) dst[u] = ((const uint4*)s_fov)[u];
+  }
+
+  const int F = P.frame_stack;
+  const int first = (flags & 1) ? P.head - F + 1 : P.head;
+
+  if (OBS_MODE == CBEV_OBS_RGB) {
+    // raw render(): (S, S, 3) uint8; 16 pixels -> 48 bytes = three 16-byte stores per thread
+    uint8_t* dst = (uint8_t*)P.ring + (size_t)env * P.ring_slots * P.frame_bytes + (size_t)P.head * P.frame_bytes;
+    for (int u = tid; u < S * S / 16; u += NT) {
+      const uint4 p16 = ((const uint4*)s_fov)[u];
+      uint32_t o[12];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t p4 = (&p16.x)[g];
+        const uint32_t k0 = s_key[p4 & 255u], k1 = s_key[(p4 >> 8) & 255u], k2 = s_key[(p4 >> 16) & 255u],
+                       k3 = s_key[p4 >> 24];
+        o[3 * g] = k0 | (k1 << 24);
+        o[3 * g + 1] = (k1 >> 8) | (k2 << 16);
+        o[3 * g + 2] = (k2 >> 16) | (k3 << 8);
+      }
+#pragma unroll
+      for (int g = 0; g < 3; ++g) st_b4(dst + 48 * (size_t)u + 16 * g, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    }
+    return;
+  }
+
+  // ---- 4. cv2.resize(INTER_AREA) (ResizeObservation, envs/__init__.py:62) + colour equality / gray level ----
+  const int OH = P.obs_h, OW = P.obs_w;
+  uint8_t* s_out = smem;  // the tile is dead
+  {
+    const int rs_mode = P.rs_mode == CBEV_RS_FAST96 ? CBEV_RS_TABLE : P.rs_mode;
+    // area tables: [nx, ny, xoff[OW+1], yoff[OH+1], xsi[nx], ysi[ny], xalpha[nx], yalpha[ny]]
+    // bilinear tables: [0, 0, xofs[OW], yofs[OH], xa0[OW], xa1[OW], yb0[OH], yb1[OH]]
+    const int nxt = s_tab[0], nyt = s_tab[1];
+    const int32_t* xoff = s_tab + 2;
+    const int32_t* yoff = xoff + OW + 1;
+    const int32_t* xsi = yoff + OH + 1;
+    const int32_t* ysi = xsi + nxt;
+    const float* xal = (const float*)(ysi + nyt);
+    const float* yal = xal + nxt;
+    const int32_t* lxo = s_tab + 2;
+    const int32_t* lyo = lxo + OW;
+    const int32_t* lxa = lyo + OH;       // [2][OW]
+    const int32_t* lyb = lxa + 2 * OW;   // [2][OH]
+    for (int o = tid; o < OH * OW; o += NT) {
+      const int dy = o / OW, dx = o - dy * OW;
+      uint32_t key;
+      if (rs_mode == CBEV_RS_COPY) {
+        key = s_key[s_fov[dy * S + dx]];
+      } else if (rs_mode == CBEV_RS_HALF) {
+        // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
+        const uint8_t* q0 = s_fov + (2 * dy) * S + 2 * dx;
+        const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[S], c3 = q0[S + 1];
+        const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
+        const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
+        key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
+      } else if (rs_mode == CBEV_RS_LINEAR) {
+        // HResizeLinear: int32 rows = S0 * a0 + S1 * a1; VResizeLinear: ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2
+        const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
+        const int a0 = lxa[dx], a1 = lxa[OW + dx], b0 = lyb[dy], b1 = lyb[OH + dy];
+        const uint32_t k00 = s_key[s_fov[sy0 * S + sx0]], k01 = s_key[s_fov[sy0 * S + sx1]],
+                       k10 = s_key[s_fov[sy1 * S + sx0]], k11 = s_key[s_fov[sy1 * S + sx1]];
+        key = 0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const int r0 = (int)((k00 >> (8 * ch)) & 255u) * a0 + (int)((k01 >> (8 * ch)) & 255u) * a1;
+          const int r1 = (int)((k10 >> (8 * ch)) & 255u) * a0 + (int)((k11 >> (8 * ch)) & 255u) * a1;
+          const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+          key |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
+        }
+      } else {
+        // ResizeArea_Invoker: buf = sum_x S * alpha (from 0, in table order); sum = sum_y beta * buf; float32, no FMA
+        float sr = 0.f, sg = 0.f, sb = 0.f;
+        const int y0 = yoff[dy], y1 = yoff[dy + 1], x0 = xoff[dx], x1 = xoff[dx + 1];
+        for (int j = y0; j < y1; ++j) {
+          const uint8_t* srow = s_fov + ysi[j] * S;
+          float br = 0.f, bg = 0.f, bb = 0.f;
+          for (int k = x0; k < x1; ++k) {
+            const uint32_t kk = s_key[srow[xsi[k]]];
+            const float a = xal[k];
+            br = __fadd_rn(br, __fmul_rn((float)(kk & 255u), a));
+            bg = __fadd_rn(bg, __fmul_rn((float)((kk >> 8) & 255u), a));
+            bb = __fadd_rn(bb, __fmul_rn((float)(kk >> 16), a));
+          }
+          const float beta = yal[j];
+          sr = __fadd_rn(sr, __fmul_rn(beta, br));
+          sg = __fadd_rn(sg, __fmul_rn(beta, bg));
+          sb = __fadd_rn(sb, __fmul_rn(beta, bb));
+        }
+        const int R = min(max(__float2int_rn(sr), 0), 255), G = min(max(__float2int_rn(sg), 0), 255),
+                  B = min(max(__float2int_rn(sb), 0), 255);
+        key = (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
+      }
+      s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. expand + stream out (as k_render) ----
+  trace_mark(P, env, 4);
+  for (int slot = first; slot <= P.head; ++slot) {
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+      int sl = slot;
+      if (rep == 1) {
+        sl = slot - P.mirror;
+        if (P.mirror <= 0 || sl < 0) break;
+      }
+      uint8_t* base = (uint8_t*)P.ring + ((size_t)env * P.ring_slots + sl) * P.frame_bytes;
+      if (OBS_MODE == CBEV_OBS_SEMANTIC) {
+        float* fb = (float*)base;
+        const int plane = OH * OW;
+        for (int q = tid; q < plane / 4; q += NT) {
+          const uint32_t m4 = ((const uint32_t*)s_out)[q];
+#pragma unroll
+          for (int c = 0; c < CHANNELS; ++c)
+            st_b4(fb + c * plane + 4 * q, bit_to_f32(m4, c), bit_to_f32(m4, c + 8), bit_to_f32(m4, c + 16),
+                  bit_to_f32(m4, c + 24));
+        }
+      } else {
+        for (int q = tid; q < OH * OW / 16; q += NT) st_u4(base + 16 * q, ((const uint4*)s_out)[q]);
+      }
+    }
+  }
+  trace_mark(P, env, 5);
+}
+
 // ---- temporal fusion of the stacked masks (wrappers/rgb_to_semantic.py:152-193) ---------------------
 // One thread per float4 of one output plane; planes are gathered from the ring window.
 __global__ void __launch_bounds__(256)
@@ -706,23 +937,27 @@ void upload_tables() {
   cudaMemcpyToSymbol(c_chan_mask, cm, sizeof(cm));
 }
 
-template <int MODE, int CH, bool GEN>
-int launch2(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
-  auto kern = k_render<MODE, CH, GEN>;
-  static bool attr_done[MAX_DEVICES] = {};
+template <int MODE, int CH>
+int launch(cbev_engine* e, const RenderParams& P, size_t smem, size_t smem_any, bool any, cudaStream_t s) {
+  static bool attr_done[MAX_DEVICES][2] = {};
   const int dev = e->device >= 0 && e->device < MAX_DEVICES ? e->device : 0;
-  if (!attr_done[dev]) {
+  if (any) {
+    auto kern = k_render_any<MODE, CH>;
+    if (!attr_done[dev][1]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 1;
+      attr_done[dev][1] = true;
+    }
+    kern<<<P.N, P.fov > 128 ? 1024 : 256, smem_any, s>>>(P, *reinterpret_cast<const CUtensorMap*>(e->tmap_any),
+                                                        e->cfg.mask_mode);
+    return 0;
+  }
+  auto kern = k_render<MODE, CH>;
+  if (!attr_done[dev][0]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return 1;
-    attr_done[dev] = true;
+    attr_done[dev][0] = true;
   }
   kern<<<P.N, RT, smem, s>>>(P, *reinterpret_cast<const CUtensorMap*>(e->tmap), e->cfg.mask_mode);
   return 0;
-}
-
-template <int MODE, int CH>
-int launch(cbev_engine* e, const RenderParams& P, size_t smem, cudaStream_t s) {
-  if (MODE != CBEV_OBS_RGB && P.rs_mode != CBEV_RS_FAST96) return launch2<MODE, CH, true>(e, P, smem, s);
-  return launch2<MODE, CH, false>(e, P, smem, s);
 }
 
 }  // namespace
@@ -756,7 +991,7 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.fov_mask = e->fov_mask;
   P.ring = e->ring;
   const int S = P.fov;
-  const size_t tile = (size_t)CBEV_TILE_W * CBEV_TILE_H;  // >= 96*96 + 2*12288 (staging), >= any obs_h * obs_w <= 128^2
+  const size_t tile = (size_t)CBEV_TILE_W * CBEV_TILE_H;  // >= 96*96 + 2*12288 (staging)
   P.pad1 = 0;
   P.pad0 = e->debug_flags;  // bit0: force the generic (range-tested) rotate path
   P.obs_h = e->cfg.obs_h;
@@ -765,20 +1000,36 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.rs_words = e->rs_words;
   P.rs_tab = e->rs_tab;
   P.trace = (e->debug_flags & 4) ? e->trace : nullptr;
-  size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16 +
-                (size_t)((e->max_rects * CBEV_RECT_WORDS + 3) & ~3) * 4 +
-                (e->rs_mode == CBEV_RS_FAST96 ? 0 : (size_t)e->rs_words * 4);
+  P.hero_w = 32 / (1024 / S);
+  P.nbx = e->any_nbx;
+  P.nby = e->any_nby;
+  P.box_h = e->any_box_h;
+  // k_render: size 128 with the (96, 96) observation or the raw frame; everything else (and debug flag 256) k_render_any
+  const bool any = S != 128 || (e->cfg.obs_mode != CBEV_OBS_RGB && e->rs_mode != CBEV_RS_FAST96) || (e->debug_flags & 256);
+  const size_t rects_bytes = (size_t)((e->max_rects * CBEV_RECT_WORDS + 3) & ~3) * 4;
+  const size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16 + rects_bytes;
+  size_t region = (size_t)CBEV_ANY_BOX_W * P.nbx * P.box_h * P.nby;
+  const size_t out_bytes = ((size_t)e->cfg.obs_h * e->cfg.obs_w + 15) & ~(size_t)15;
+  if (e->cfg.obs_mode != CBEV_OBS_RGB && out_bytes > region) region = out_bytes;
+  P.region_bytes = (int32_t)region;
+  const size_t smem_any = region + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + rects_bytes +
+                          (size_t)e->rs_words * 4;
+  if (any && smem_any > 227 * 1024) {
+    cbev_set_error("k_render_any needs %zu bytes of shared memory (max_rects %d): over the 227 KB of one CTA", smem_any,
+                   e->max_rects);
+    return 1;
+  }
   int rc = 1;
-  if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, s);
-  else if (e->cfg.obs_mode == CBEV_OBS_GRAY) rc = launch<CBEV_OBS_GRAY, 1>(e, P, smem, s);
+  if (e->cfg.obs_mode == CBEV_OBS_RGB) rc = launch<CBEV_OBS_RGB, 1>(e, P, smem, smem_any, any, s);
+  else if (e->cfg.obs_mode == CBEV_OBS_GRAY) rc = launch<CBEV_OBS_GRAY, 1>(e, P, smem, smem_any, any, s);
   else {
     switch (e->channels) {
-      case 1: rc = launch<CBEV_OBS_SEMANTIC, 1>(e, P, smem, s); break;
-      case 2: rc = launch<CBEV_OBS_SEMANTIC, 2>(e, P, smem, s); break;
-      case 4: rc = launch<CBEV_OBS_SEMANTIC, 4>(e, P, smem, s); break;
-      case 5: rc = launch<CBEV_OBS_SEMANTIC, 5>(e, P, smem, s); break;
-      case 6: rc = launch<CBEV_OBS_SEMANTIC, 6>(e, P, smem, s); break;
-      case 7: rc = launch<CBEV_OBS_SEMANTIC, 7>(e, P, smem, s); break;
+      case 1: rc = launch<CBEV_OBS_SEMANTIC, 1>(e, P, smem, smem_any, any, s); break;
+      case 2: rc = launch<CBEV_OBS_SEMANTIC, 2>(e, P, smem, smem_any, any, s); break;
+      case 4: rc = launch<CBEV_OBS_SEMANTIC, 4>(e, P, smem, smem_any, any, s); break;
+      case 5: rc = launch<CBEV_OBS_SEMANTIC, 5>(e, P, smem, smem_any, any, s); break;
+      case 6: rc = launch<CBEV_OBS_SEMANTIC, 6>(e, P, smem, smem_any, any, s); break;
+      case 7: rc = launch<CBEV_OBS_SEMANTIC, 7>(e, P, smem, smem_any, any, s); break;
       default: rc = 1;
     }
   }

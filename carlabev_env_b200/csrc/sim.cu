@@ -206,8 +206,8 @@ __device__ void compute_view(const SimParams& P, double x, double y, double thet
   if (x_hi < x_lo || y_hi < y_lo) { x_lo = y_lo = 0; x_hi = y_hi = 0; }  // the view misses the crop: nothing is sampled
   v.fx = x_lo;
   v.fy = y_lo;
-  v.bw = min(x_hi - x_lo + 1, CBEV_TILE_H);  // <= 183 by the bound above
-  v.bh = min(y_hi - y_lo + 1, CBEV_TILE_H);
+  v.bw = min(x_hi - x_lo + 1, P.win_max);  // <= ceil(S * sqrt(2)) + 2 by the bound above (183 at size 128)
+  v.bh = min(y_hi - y_lo + 1, P.win_max);
 }
 
 __device__ void write_desc_header(const SimParams& P, int32_t* __restrict__ d, const View& v, int nrects, int flags,
@@ -713,7 +713,7 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
   const double* __restrict__ ecy = pool.ego_cy + r0;
 
   // ---- a2/a3: ego physics (uniform across lanes) ------------------------------------------------
-  double acc_val = gas > 0.0f ? (double)__fmul_rn(gas, 8.0f) : 0.0;
+  double acc_val = gas > 0.0f ? (double)__fmul_rn(gas, P.hero_scale) : 0.0;  // hero.py:14,142: 8 at size 128
   double delta;
   if (fabs(e.v) < 0.1) {
     delta = 0.0;
@@ -722,7 +722,7 @@ k_move(SimParams P, PoolDev pool, EnvState st, const void* __restrict__ actions,
     delta = ((double)steer * steer_deg) * DEG2RAD;
   }
   double speed_factor = clipd(fabs(e.v) / 5.0, 0.3, 1.0);
-  double brake_val = (brake > 0.0f ? (double)__fmul_rn(__fmul_rn(brake, 0.6f), 8.0f) : 0.0) * speed_factor;
+  double brake_val = (brake > 0.0f ? (double)__fmul_rn(__fmul_rn(brake, 0.6f), P.hero_scale) : 0.0) * speed_factor;
   double target_acc = acc_val - brake_val - 0.05 * e.v;
   acc = (1.0 - 0.2) * acc + 0.2 * target_acc;
   const double applied_delta = delta;
@@ -905,8 +905,9 @@ k_judge(SimParams P, PoolDev pool, EnvState st, cbev_step_out out, const int32_t
 
   // ego rect (hero.sync_rect, hero.py:34-35)
   const int pad = P.pad;
-  const int hx = rect_left(e.x, pad, 4), hy = rect_left(e.y, pad, 4);
-  const int hcx = hx + 2, hcy = hy + 2;
+  const int hw = P.hero_w;  // hero.py:17: int(32 / scale), 4 px at size 128
+  const int hx = rect_left(e.x, pad, hw), hy = rect_left(e.y, pad, hw);
+  const int hcx = hx + (hw >> 1), hcy = hy + (hw >> 1);
 
   // ---- a9: collision / proximity (scene.py:110-140, actor.py:166-176) on the actor poses of this step ----
   const int A0 = pool.actor_off[scene], A = pool.actor_off[scene + 1] - A0;
@@ -932,7 +933,7 @@ k_judge(SimParams P, PoolDev pool, EnvState st, cbev_step_out out, const int32_t
       ry = rect_left(st.ay[o], pad, size);
       int dcx = hcx - (rx + (size >> 1)), dcy = hcy - (ry + (size >> 1));
       near = dcx * dcx + dcy * dcy < 35 * 35;  // math.hypot(ints) < min_dist
-      coll = overlap(hx, hy, 4, rx, ry, size);
+      coll = overlap(hx, hy, hw, rx, ry, size);
     }
     unsigned cm = __ballot_sync(GM, coll) >> gb;
     if (cm) {
@@ -974,7 +975,7 @@ k_judge(SimParams P, PoolDev pool, EnvState st, cbev_step_out out, const int32_t
     bool coll = false;
     if (has) {
       const int tx = rect_left(ecx[i], pad, size), ty = rect_left(ecy[i], pad, size);
-      coll = overlap(hx, hy, 4, tx, ty, size);
+      coll = overlap(hx, hy, hw, tx, ty, size);
     }
     unsigned cm = __ballot_sync(GM, coll) >> gb;
     if (cm) {
@@ -1251,6 +1252,9 @@ static SimParams make_params(cbev_engine* e) {
   P.map_w = e->map_w;
   P.map_h = e->map_h;
   P.fov = e->cfg.fov_size;
+  P.hero_scale = (float)(1024 / e->cfg.fov_size);  // hero.py:14
+  P.hero_w = 32 / (1024 / e->cfg.fov_size);        // hero.py:17
+  P.win_max = e->win_max;
   P.crop = e->crop;
   P.pad = e->pad;
   P.anchor_x = e->anchor_x;

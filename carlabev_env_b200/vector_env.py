@@ -39,10 +39,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _CAUSE_ARRAY = np.array(E.CAUSE_NAMES, dtype=object)
 
 
-def load_town01_map() -> np.ndarray:
-    """Class map of Town01 at size=128 (1280 x 1024; 0 non-drivable, 1 drivable, 2 sidewalk), derived
-    from the reference's Town01-128-sem.png by oracle/gen_golden.py:dump_map (envs/utils.py:49-62)."""
-    with np.load(os.path.join(HERE, "assets", "town01_128_cls.npz")) as z:
+def load_town01_map(size: int = 128) -> np.ndarray:
+    """Class map of Town01 at EnvConfig.size (64: 640 x 512, 128: 1280 x 1024, 256: 2560 x 2048 (rows x columns);
+    0 non-drivable, 1 drivable, 2 sidewalk), derived from the reference's Town01-<size>-sem.png by
+    oracle/gen_golden.py:dump_map (envs/utils.py:49-62)."""
+    path = os.path.join(HERE, "assets", f"town01_{int(size)}_cls.npz")
+    if not os.path.exists(path):
+        raise ValueError(f"size={size}: no Town01 class map of that scale ships (64, 128, 256)")
+    with np.load(path) as z:
         return np.ascontiguousarray(z["cls"], dtype=np.uint8)
 
 
@@ -107,7 +111,7 @@ class CarlaBEVVectorEnv(_vector_env_base()):
             seed=(cfg.seed if seed is None else seed) + (int(shard[0]) if shard is not None else 0),  # auto-reset draws
             device=device, size=env.size, obs_size=env.obs_size)
         self.device = self.engine.device
-        self.cls_map = load_town01_map()
+        self.cls_map = load_town01_map(env.size)
         self.engine.upload_map(self.cls_map)
         self.pad = self._crop_size(env)
         if env.fov_masked:  # FovRenderSpec(mask_fov=True), envs/world.py:39-46
@@ -226,14 +230,15 @@ class CarlaBEVVectorEnv(_vector_env_base()):
             new = [int(sd) for sd in np.unique(seeds[sel]) if int(sd) not in cache]
             if new:
                 # snapshots exported from the reference with exactly these options (entry i <-> scene_seed i)
-                shipped = None if authored is not None else shipped_pool_for(options, self.env_cfg.max_vehicles)
+                shipped = None if authored is not None or self.env_cfg.size != 128 else \
+                    shipped_pool_for(options, self.env_cfg.max_vehicles)  # exported at size 128 (spawn validation)
                 ready = {}
                 if shipped is not None:
                     pool = self._shipped_scenes(shipped)
                     ready = {sd: pool[sd] for sd in new if 0 <= sd < len(pool)}
                 todo = [sd for sd in new if sd not in ready]
                 built = S.build_pool([{**base_opts, "scene_seed": sd} for sd in todo], pad=self.pad,
-                                     max_vehicles=self.env_cfg.max_vehicles)
+                                     max_vehicles=self.env_cfg.max_vehicles, size=self.env_cfg.size)
                 ready.update(zip(todo, built))
                 for sd in new:
                     self._scenes.append(ready[sd])

@@ -33,14 +33,15 @@ def make_engine_for(g: Golden, num_envs=1, autoreset=0, ring_slots=None, raw_rgb
         max_actors=int(max(1, np.diff(g.pool["actor_off"]).max())),
         seed=seed,
         trajectory_steps=trajectory_steps,
+        size=g.size,
     )
-    eng.upload_map(load_map())
+    eng.upload_map(load_map(g.size))
     eng.upload_pool(g.pool)
     eng.keep_fov(True)
     if kw.get("fov_masked"):
         from carlabev_env_b200.fovmask import corner_mask
 
-        eng.upload_fov_mask(corner_mask(128, 0.5))
+        eng.upload_fov_mask(corner_mask(g.size, 0.5))
     fusion = kw.get("temporal_fusion_mode", "stack")
     eng.current_obs = (lambda: eng.obs()) if fusion == "stack" else (lambda: eng.fuse(fusion))
     return eng

@@ -7,7 +7,7 @@ rewards within 1e-9; episode summaries within 1e-7 relative.
 """
 import pytest
 
-from golden_util import ALL_CASES
+from golden_util import ALL_CASES, SCALE_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -31,4 +31,27 @@ def test_generic_rotate_path(case):
     from engine_util import replay_golden
 
     bad = replay_golden(case, debug_flags=1)
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("trajectory_steps", [0, 1024])
+@pytest.mark.parametrize("case", SCALE_CASES)
+def test_other_map_scales_replay_reference_golden(case, trajectory_steps):
+    """EnvConfig.size 64 and 256 (ego gains and ego square scale with 1024 / size, the view,
+    the crop and the map scale with size; 64 -> 96 ENLARGES, 256 -> 96 shrinks by 8/3) through k_render_any, against
+    goldens recorded from the unmodified reference at those sizes."""
+    from engine_util import replay_golden
+
+    bad = replay_golden(case, trajectory_steps=trajectory_steps)
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("case", ["rdm_medium_discrete", "rdm_rgb_lookahead", "fusion_temporal_masked", "jaywalk_drive",
+                                  "red_light_runner"])
+def test_any_size_kernel_at_the_default_scale(case):
+    """k_render_any (strip-tiled fetch window, row-major frame, table resize) forced at size 128 / obs 96 x 96 with
+    debug flag 256: it must reproduce the reference goldens exactly like the specialised k_render."""
+    from engine_util import replay_golden
+
+    bad = replay_golden(case, debug_flags=256)
     assert not bad, "\n".join(bad)

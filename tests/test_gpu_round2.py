@@ -294,3 +294,49 @@ def test_vector_env_step_paths_agree():
     assert finished > 0
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("size,seeds", [(256, (0, 1, 3, 4, 5, 6)), (64, (0, 2, 3, 5, 6, 10))])
+def test_make_env_at_other_map_scales(size, seeds):
+    """SURVEY.md section 8 row f4 through the reference-facing boundary: make_env(EnvConfig(size=...)).reset(options=
+    {"scene": "rdm", ...}).step(actions) against the oracle (pinned on goldens recorded from the reference at that size):
+    stacked masks, rewards, flags; then the raw (size, size, 3) frames of the raw_rgb engine mode."""
+    import numpy as np
+
+    from carlabev_env_b200 import EnvConfig, RunConfig, make_env
+    from carlabev_env_b200 import scenes as S
+    from golden_util import load_map
+    from oracle.env import OracleEnv
+
+    n = len(seeds)
+    cls = load_map(size)
+    for raw in (False, True):
+        env_cfg = EnvConfig(size=size, action_mode="continuous", obs_mode="bev_rgb" if raw else "bev_semantic")
+        envs = make_env(RunConfig(env=env_cfg, num_envs=n), ring_budget_bytes=64 << 20, to_numpy=True, raw_rgb=raw)
+        assert envs.single_observation_space.shape == ((size, size, 3) if raw else (24, 96, 96))
+        opts = dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100))
+        oracles = [OracleEnv(cls, action_mode="continuous", size=size, obs_mode="bev_raw" if raw else "bev_semantic")
+                   for _ in range(n)]
+        want, scenes = [], []
+        for i, sd in enumerate(seeds):  # SyncVectorEnv hands every env the same options: one reset per seed, masked
+            mask = np.ones(n, bool) if i == 0 else np.arange(n) == i   # the first reset covers every env
+            obs, _ = envs.reset(options={**opts, "scene_seed": sd, "reset_mask": mask})
+            scenes.append(S.build_scene({**opts, "scene_seed": sd}, cls_map=cls, pad=envs.pad))
+            want.append(oracles[i].reset(scenes[i]))
+        assert np.array_equal(np.asarray(obs), np.stack(want)), "reset observations"
+        rng = np.random.default_rng(size)
+        episodes = 0
+        for t in range(60):
+            a = np.stack([rng.uniform(0.3, 1, n), rng.uniform(-0.4, 0.4, n), rng.uniform(0, 0.2, n)], axis=1).astype(np.float32)
+            obs, rew, term, trunc, _ = envs.step(a)
+            obs, rew, term, trunc = np.asarray(obs), np.asarray(rew), np.asarray(term), np.asarray(trunc)
+            for i in range(n):
+                o, r, te, tr, _ = oracles[i].step(a[i])
+                assert np.array_equal(obs[i], o), (size, raw, t, i)
+                assert abs(r - rew[i]) <= 1e-9 and te == term[i] and tr == trunc[i], (size, raw, t, i)
+                if te or tr:  # masked reset of the finished env, as a SyncVectorEnv caller does
+                    episodes += 1
+                    obs_r, _ = envs.reset(options={**opts, "scene_seed": seeds[i], "reset_mask": np.arange(n) == i})
+                    assert np.array_equal(np.asarray(obs_r)[i], oracles[i].reset(scenes[i])), (size, raw, t, i, "reset")
+        assert episodes >= 1
+        envs.close()

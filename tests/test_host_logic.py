@@ -39,6 +39,9 @@ def test_env_config_validation_errors():
         validate_run_config(RunConfig(env=EnvConfig(obs_mode="vector")))
     with pytest.raises(ValueError):
         RunConfig(num_envs=0)
+    with pytest.raises(ValueError):
+        EnvConfig(size=512)  # the reference cannot reset there either (every seed ends in hero_on_obstacle)
+    assert EnvConfig(size=256).size == 256 and EnvConfig(size=64).size == 64
 
 
 def test_engine_construction_fails_loudly_without_cuda():
@@ -260,6 +263,30 @@ def test_rdm_generation_matches_reference_snapshots(name, seeds):
     for i in seeds:
         got = S.build_scene({**SHIPPED_POOLS[name], "scene_seed": i}, cls_map=cls)
         assert _same_scene(ref[i], got) == [], (name, i)
+
+
+@pytest.mark.parametrize("case,size,crop,bad_seed", [("size256_rdm_discrete", 256, 363, 2), ("size64_rdm_discrete", 64, 91, 1),
+                                                     ("size256_rdm_gray_lookahead", 256, 460, None)])
+def test_rdm_generation_at_other_map_scales(case, size, crop, bad_seed):
+    """at EnvConfig.size 64 / 256 the reference's generators keep their 128-scale coordinates
+    (quirk C-11) and only the spawn validation reads the map of that scale.  build_scene with that map == the post-reset
+    snapshots recorded from the unmodified reference (the pools inside the size goldens); a seed the reference cannot
+    reset ("hero_on_obstacle" after 10 attempts) fails here in the same way."""
+    from carlabev_env_b200 import scenes as S
+    from carlabev_env_b200.pool import unpack_pool
+    from golden_util import Golden
+
+    g = Golden(case)
+    ref = unpack_pool(g.pool)
+    cls = load_map(size)
+    for sc in ref:
+        got = S.build_scene(dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100), scene_seed=int(sc["seed"])),
+                            cls_map=cls, pad=crop)
+        assert _same_scene(sc, got) == [], (case, int(sc["seed"]))
+    if bad_seed is not None:
+        with pytest.raises(RuntimeError, match="valid initial state"):
+            S.build_scene(dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100), scene_seed=bad_seed),
+                          cls_map=cls, pad=crop)
 
 
 def test_red_light_generation_matches_reference_snapshots():
