@@ -62,7 +62,7 @@ def _host_workers():
     return max(1, min((os.cpu_count() or 1) // world, 32))
 
 
-def _shared_pool(tag, requests, pad):
+def _shared_pool(tag, requests, pad, size=128):
     """Scene pool `tag`, generated once per box by ALL ranks together: rank r builds requests[r::world] on its share
     of the host cores and publishes its part atomically; every rank then assembles the parts in order.  No collective
     is pending while the host works and nobody generates a scene twice.  Parts are cached under $TMPDIR."""
@@ -81,7 +81,9 @@ def _shared_pool(tag, requests, pad):
     part = f"{base}.w{world}.r{rank}.npz"
     if not os.path.exists(part):
         t0 = time.time()
-        mine = build(requests[rank::world], pad=pad, workers=_host_workers())
+        # other map scales: seeds the reference itself cannot reset ("hero_on_obstacle") are left out of the pool
+        mine = [sc for sc in build(requests[rank::world], pad=pad, workers=_host_workers(), size=size,
+                                   skip_invalid=size != 128) if sc is not None]
         tmp = f"{part}.{os.getpid()}.tmp.npz"
         save_pool(tmp, mine, compress=False)
         os.replace(tmp, whole if world == 1 else part)
@@ -97,6 +99,8 @@ def _shared_pool(tag, requests, pad):
                 raise RuntimeError(f"rank {rank}: pool part {pr} did not appear within 900 s")
             time.sleep(0.2)
         parts.append(load_pool(pr))
+    if size != 128:  # parts have unequal lengths (invalid seeds dropped): concatenate in rank order
+        return [sc for part in parts for sc in part]
     scenes = [None] * n
     for r in range(world):
         scenes[r::world] = parts[r]
@@ -117,6 +121,11 @@ WORKLOADS = {
     "c5": dict(desc="configs[4]: {N} envs/GPU raw RGB (128,128,3) uint8 obs, lookahead_75 camera, rdm with 50 vehicles "
                     "(pool of {K} host-generated scenes), continuous actions, auto-reset", envs=8192, obs="rgb",
                actions="continuous", anchor=(0.5, 0.75), pool="rdm_dense_50"),
+    # SURVEY.md section 8 row f4 (not a BASELINE config): the other map scale the reference can run, EnvConfig.size = 256
+    "f4": dict(desc="row f4: {N} envs/GPU at EnvConfig.size=256 (256x256 view of the Town01-256 map, 256 -> 96 area resize), "
+                    "rdm with 12 vehicles (pool of {K} host-generated scenes the reference can reset at that scale), "
+                    "discrete9 actions, 6-class semantic F=4, auto-reset", envs=4096, obs="semantic", actions="discrete",
+               anchor=(0.5, 0.5), pool="rdm_size256", size=256),
 }
 
 
@@ -137,6 +146,10 @@ def workload_pool(name, args):
         k = min(args.pool, 2048)
         return _shared_pool("mixed_edge", [dict(scene="jaywalk", level=1 + (i // 2) % 4, scene_seed=i) if i % 2 == 0
                                            else dict(scene="red_light_runner", scene_seed=i) for i in range(k)], 182)
+    if w["pool"] == "rdm_size256":        # row f4: seeds 0..511 minus those the reference cannot reset at size 256
+        k = min(args.pool, 512)
+        return _shared_pool("rdm_size256", [dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100), scene_seed=i)
+                                            for i in range(k)], 363, size=256)
     # configs[4]: rdm with num_vehicles = max_vehicles = 50, lookahead_75 camera (crop 230 px)
     k = min(args.pool, 1024)
     return _shared_pool("rdm_dense_50", [dict(scene="rdm", num_vehicles=50, route_dist_range=(30, 130), scene_seed=i)
@@ -368,7 +381,8 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
     # engine through the C ABI directly, the e2e_vector_env leg goes through VectorEnv.step itself.
     cfg = RunConfig(env=EnvConfig(obs_mode="bev_semantic" if semantic else "bev_rgb",
                                   action_mode="discrete" if discrete else "continuous",
-                                  ego_anchor_x_frac=W["anchor"][0], ego_anchor_y_frac=W["anchor"][1]),
+                                  ego_anchor_x_frac=W["anchor"][0], ego_anchor_y_frac=W["anchor"][1],
+                                  size=W.get("size", 128)),
                     num_envs=N, seed=rank)
     envs = make_env(cfg, scenes=scenes, autoreset="next_step", device=local, ring_slots=ring_slots,
                     raw_rgb=not semantic, host_infos=True)
@@ -497,7 +511,7 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
                              "no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_source,
-                         "kernel": "k_render", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "k_render" if W.get("size", 128) == 128 else "k_render_any", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "written_bytes_per_launch_estimate": written_est,
                          "kernel_ms": render_avg, "sim_kernel_ms": move_avg, "judge_kernel_ms": judge_avg,
                          "judge_note": "k_judge runs on a side stream concurrently with k_render",
@@ -534,7 +548,7 @@ def run_ours(args):
     main = run_workload(ctx, args.workload, args, with_cpu_baseline=(ctx.world == 1 and not args.no_cpu_baseline))
     extras = []
     if args.workload == "c2" and not args.no_extras:
-        for name in ("c3", "c4", "c5"):
+        for name in ("c3", "c4", "c5", "f4"):
             # every rank must take the same decision: the budget is checked on rank 0's clock
             flag = ctx.torch.tensor([1.0 if time.time() - t_start < args.extras_budget else 0.0], device=ctx.dev)
             if ctx.world > 1:

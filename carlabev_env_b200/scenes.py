@@ -887,16 +887,28 @@ def _build_chunk(args):
     size = args[3] if len(args) > 3 else 128
     from .vector_env import load_town01_map
 
+    skip_invalid = args[4] if len(args) > 4 else False
     cls = load_town01_map(size)
-    return [build_scene(r, cls_map=cls, pad=pad, max_vehicles=max_vehicles) for r in requests]
+    out = []
+    for r in requests:
+        try:
+            out.append(build_scene(r, cls_map=cls, pad=pad, max_vehicles=max_vehicles))
+        except RuntimeError as ex:
+            # "Failed to reset into a valid initial state after N attempts": what CarlaBEV.reset raises for this seed
+            if not skip_invalid or "valid initial state" not in str(ex):
+                raise
+            out.append(None)
+    return out
 
 
 def build_pool(requests: list[dict], pad: int = 182, max_vehicles: int = 50, workers: int | None = None,
-               size: int = 128) -> list[dict]:
+               size: int = 128, skip_invalid: bool = False) -> list[dict]:
     """Reset-option dicts -> pool entries, on `workers` host processes (default: one per core, serial for small
     pools).  Scene generation is host work by design (the device steps scenes, it does not build them).
     `size` = EnvConfig.size: the generators keep their 128-scale coordinates at every size (the reference hard-codes
     map_size=128, scene_generator.py:65-76), only the spawn validation reads the map of that scale.
+    `skip_invalid`: requests whose reset the reference itself gives up on (RuntimeError after max_reset_attempts) come
+    back as None instead of raising (pools for the other map scales, where many seeds spawn the ego off the road).
 
     The workers are plain child interpreters running this module (`python -m carlabev_env_b200.scenes --worker`),
     fed and read through files: nothing of the caller's `__main__` is re-imported, so this is safe to call from any
@@ -911,7 +923,7 @@ def build_pool(requests: list[dict], pad: int = 182, max_vehicles: int = 50, wor
     workers = min(os.cpu_count() or 1, 32) if workers is None else workers
     workers = min(workers, max(1, n // 16))
     if workers <= 1:
-        return _build_chunk((requests, pad, max_vehicles, size))
+        return _build_chunk((requests, pad, max_vehicles, size, skip_invalid))
     chunks = [list(range(w, n, workers)) for w in range(workers)]
     pkg_parent = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
@@ -923,7 +935,7 @@ def build_pool(requests: list[dict], pad: int = 182, max_vehicles: int = 50, wor
         for w, c in enumerate(chunks):
             req, res = os.path.join(tmp, f"req{w}.pkl"), os.path.join(tmp, f"res{w}.pkl")
             with open(req, "wb") as f:
-                pickle.dump(([requests[i] for i in c], pad, max_vehicles, size), f)
+                pickle.dump(([requests[i] for i in c], pad, max_vehicles, size, skip_invalid), f)
             procs.append((c, res, subprocess.Popen([sys.executable, "-m", "carlabev_env_b200.scenes", "--worker", req, res],
                                                    env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)))
         errors = []

@@ -333,8 +333,11 @@ def test_rdm_and_red_light_pools_discrete_parity():
     eng.close()
 
 
-def test_raw_rgb_lookahead_dense_traffic():
-    """BASELINE configs[4] shape: raw (128, 128, 3) uint8 frames, lookahead_75 camera, 50 vehicles, continuous."""
+@pytest.mark.parametrize("variant", ["plain", "fov_masked", "generic_rotate", "keep_frame"])
+def test_raw_rgb_lookahead_dense_traffic(variant):
+    """BASELINE configs[4] shape: raw (128, 128, 3) uint8 frames, lookahead_75 camera, 50 vehicles, continuous.  The raw
+    frames leave the rotate loop in registers (no frame in shared memory): the corner mask, the ego square, the
+    range-tested rotate (debug flag 1) and the debug copy of the palette frame all live in that loop."""
     import torch
 
     from carlabev_env_b200 import engine as E
@@ -346,8 +349,17 @@ def test_raw_rgb_lookahead_dense_traffic():
     eng = E.Engine(n, obs_mode=E.OBS_RGB, action_mode=E.ACTION_CONTINUOUS, max_actors=50, anchor=(0.5, 0.75))
     eng.upload_map(load_map())
     eng.upload_pool(pack_pool(scenes))
-    oracles = [OracleEnv(load_map(), obs_mode="bev_raw", frame_stack=1, action_mode="continuous", anchor=(0.5, 0.75))
-               for _ in range(n)]
+    masked = variant == "fov_masked"
+    if masked:
+        from carlabev_env_b200.fovmask import corner_mask
+
+        eng.upload_fov_mask(corner_mask(128, 0.5))
+    if variant == "generic_rotate":
+        eng.set_debug_flags(1)
+    if variant == "keep_frame":
+        eng.keep_fov(True)
+    oracles = [OracleEnv(load_map(), obs_mode="bev_raw", frame_stack=1, action_mode="continuous", anchor=(0.5, 0.75),
+                         fov_masked=masked) for _ in range(n)]
     obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
     assert obs.shape == (n, 128, 128, 3) and obs.dtype == np.uint8
     for i in range(n):
@@ -370,6 +382,11 @@ def test_raw_rgb_lookahead_dense_traffic():
             assert abs(r - rew[i]) < 1e-9 and te == term[i], (t, i)
             assert np.array_equal(obs[i], o[0]), (t, i, "rgb frame")   # bar: within 1 LSB; we get exact
             alive[i] = not te
+        if variant == "keep_frame":
+            from oracle import raster
+
+            fr = eng.fov().cpu().numpy()
+            assert all(np.array_equal(raster.PALETTE[fr[i]], obs[i]) for i in range(n)), (t, "palette frame")
     eng.close()
 
 

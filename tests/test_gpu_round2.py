@@ -315,14 +315,15 @@ def test_make_env_at_other_map_scales(size, seeds):
         envs = make_env(RunConfig(env=env_cfg, num_envs=n), ring_budget_bytes=64 << 20, to_numpy=True, raw_rgb=raw)
         assert envs.single_observation_space.shape == ((size, size, 3) if raw else (24, 96, 96))
         opts = dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100))
-        oracles = [OracleEnv(cls, action_mode="continuous", size=size, obs_mode="bev_raw" if raw else "bev_semantic")
-                   for _ in range(n)]
+        oracles = [OracleEnv(cls, action_mode="continuous", size=size, obs_mode="bev_raw" if raw else "bev_semantic",
+                             frame_stack=1 if raw else 4) for _ in range(n)]
+        frame = (lambda o: o[0]) if raw else (lambda o: o)  # the raw mode has no frame stack
         want, scenes = [], []
         for i, sd in enumerate(seeds):  # SyncVectorEnv hands every env the same options: one reset per seed, masked
             mask = np.ones(n, bool) if i == 0 else np.arange(n) == i   # the first reset covers every env
             obs, _ = envs.reset(options={**opts, "scene_seed": sd, "reset_mask": mask})
             scenes.append(S.build_scene({**opts, "scene_seed": sd}, cls_map=cls, pad=envs.pad))
-            want.append(oracles[i].reset(scenes[i]))
+            want.append(frame(oracles[i].reset(scenes[i])))
         assert np.array_equal(np.asarray(obs), np.stack(want)), "reset observations"
         rng = np.random.default_rng(size)
         episodes = 0
@@ -332,11 +333,11 @@ def test_make_env_at_other_map_scales(size, seeds):
             obs, rew, term, trunc = np.asarray(obs), np.asarray(rew), np.asarray(term), np.asarray(trunc)
             for i in range(n):
                 o, r, te, tr, _ = oracles[i].step(a[i])
-                assert np.array_equal(obs[i], o), (size, raw, t, i)
+                assert np.array_equal(obs[i], frame(o)), (size, raw, t, i)
                 assert abs(r - rew[i]) <= 1e-9 and te == term[i] and tr == trunc[i], (size, raw, t, i)
                 if te or tr:  # masked reset of the finished env, as a SyncVectorEnv caller does
                     episodes += 1
                     obs_r, _ = envs.reset(options={**opts, "scene_seed": seeds[i], "reset_mask": np.arange(n) == i})
-                    assert np.array_equal(np.asarray(obs_r)[i], oracles[i].reset(scenes[i])), (size, raw, t, i, "reset")
+                    assert np.array_equal(np.asarray(obs_r)[i], frame(oracles[i].reset(scenes[i]))), (size, raw, t, i, "reset")
         assert episodes >= 1
         envs.close()

@@ -62,7 +62,7 @@ def si(d, key):
 
 
 summary = {}
-for stem in ("prof_c2", "prof_c3", "prof_c5", "prof_variants"):
+for stem in ("prof_c2", "prof_c3", "prof_c5", "prof_variants", "prof_f4"):
     p = os.path.join(src, f"{stem}_raw.csv")
     if not os.path.exists(p):
         continue
