@@ -125,7 +125,8 @@ int build_tensor_map(cbev_engine* e) {
                          (cuuint32_t)(which ? e->any_box_h : CBEV_TILE_H)};  // sim.cu:compute_view
     CUresult r = ((EncodeTiledFn)fn)(reinterpret_cast<CUtensorMap*>(which ? e->tmap_any : e->tmap),
                                      CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, e->map, dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     which ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       cbev_set_error("cuTensorMapEncodeTiled failed with CUresult %d (map %dx%d, box %dx%d)", (int)r, e->map_w, e->map_h,
@@ -274,7 +275,8 @@ static void linear_area_table(int ssize, int dsize, std::vector<int32_t>& ofs, s
   }
 }
 
-// area:     rs_tab = [nx, ny, xoff[ow+1], yoff[oh+1], xsi[nx], ysi[ny], xalpha[nx], yalpha[ny]]
+// area:     rs_tab = [nx, ny, xoff[ow+1], yoff[oh+1], xsi[nx], ysi[ny], xalpha[nx], yalpha[ny],
+//                     fxlo[ow], fxhi[ow], fylo[oh], fyhi[oh]]  (first / last source column and row of every output)
 // bilinear: rs_tab = [0, 0, xofs[ow], yofs[oh], xa0[ow], xa1[ow], yb0[oh], yb1[oh]]
 static int build_resize_tables(cbev_engine* e) {
   const int S = e->cfg.fov_size, oh = e->cfg.obs_h, ow = e->cfg.obs_w;
@@ -306,6 +308,10 @@ static int build_resize_tables(cbev_engine* e) {
   tab.insert(tab.end(), ys.begin(), ys.end());
   for (float a : xa) { int32_t b; memcpy(&b, &a, 4); tab.push_back(b); }
   for (float a : ya) { int32_t b; memcpy(&b, &a, 4); tab.push_back(b); }
+  for (int d = 0; d < ow; ++d) tab.push_back(xs[xo[d]]);
+  for (int d = 0; d < ow; ++d) tab.push_back(xs[xo[d + 1] - 1]);
+  for (int d = 0; d < oh; ++d) tab.push_back(ys[yo[d]]);
+  for (int d = 0; d < oh; ++d) tab.push_back(ys[yo[d + 1] - 1]);
   e->rs_words = (int32_t)tab.size();
   return dev_upload(&e->rs_tab, tab.data(), tab.size());
 }

@@ -595,24 +595,31 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
 // EnvConfig.size in {64, 128, 256} (hero.py:14-17, world.py:38-49; the view, the crop and
 // the map scale with it) and any EnvConfig.obs_size.  Same pipeline as k_render without its 128 / 96 specialisations:
 //   * the fetch window (<= ceil(S * sqrt 2) + 2 px on a side, 365 px at S = 256) exceeds one TMA box (<= 256 per
-//     dimension), so it lands as `nbx` column strips of CBEV_ANY_BOX_W bytes x `nby` row boxes, all on one mbarrier;
-//     window pixel (x, y) lives at s_tile[((x >> 7) * tile_h + y) * 128 + (x & 127)];
-//   * the rotate is pygame's range-tested per-pixel walk; the frame is stored row-major;
-//   * cv2.resize(INTER_AREA): copy / 2x2 integer path / float32 area tables when shrinking, and OpenCV's 8-bit
-//     bilinear kernel on area-mode coefficients when an axis enlarges (size 64 -> 96).
-// One CTA per env: 256 threads (S <= 128), 1024 threads and ~215 KB of shared memory at S = 256 (one CTA per SM).
+//     dimension), so it lands as `nbx` column strips of CBEV_ANY_BOX_W = 128 bytes x `nby` row boxes, all on one
+//     mbarrier.  The tensor map uses the 128-byte TMA swizzle (16-byte chunk ^= row & 7): with a dense 128-byte pitch
+//     every row would start in bank 0 and a heading along a map axis would put the 32 byte-gathers of an instruction
+//     into one bank; swizzled, the 16-px x 8-row warp patches of the rotate are conflict-free or 2-way.
+//     Window byte (x, y) lives at ((x >> 7) * tile_h + y) * 128 + (x & 127), XOR (y & 7) << 4;
+//   * the frame is stored with a pitch of S + 16 bytes (an odd number of 16-byte chunks: rows rotate through the banks);
+//   * cv2.resize(INTER_AREA): copy / 2x2 integer path / float32 area tables when shrinking -- with a shortcut for
+//     outputs whose whole source footprint is one colour (the weights sum to 1 within 1e-6, so the result is that
+//     colour exactly) -- and OpenCV's 8-bit bilinear kernel on area-mode coefficients when an axis enlarges (64 -> 96).
+// One CTA per env: 256 threads (S <= 128), 1024 threads and ~220 KB of shared memory at S = 256 (one CTA per SM).
 template <int OBS_MODE, int CHANNELS>
 __global__ void __launch_bounds__(1024, 1)
 k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [tile strips | re-used as the OH x OW output bytes] [frame S x S] [tables] [mbar] [draw list] [resize tables]
+  extern __shared__ uint8_t smem_raw[];
+  // layout: [tile strips (1024-byte aligned: swizzle period) | re-used as the OH x OW output bytes] [frame S x (S + 16)]
+  //         [tables] [mbar] [draw list] [resize tables]
+  uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = P.fov, NT = blockDim.x;
+  const int FP = S + 16;  // frame pitch
   constexpr int BW = CBEV_ANY_BOX_W;
   const int tile_h = P.box_h * P.nby;
   const int tile_bytes = BW * P.nbx * tile_h;
   uint8_t* const s_tile = smem;
   uint8_t* const s_fov = smem + P.region_bytes;
-  uint32_t* s_rg = (uint32_t*)(s_fov + S * S);
+  uint32_t* s_rg = (uint32_t*)(s_fov + S * FP);
   uint32_t* s_b = s_rg + 16;
   uint32_t* s_key = s_b + 16;
   int32_t* s_desc = (int32_t*)(s_key + 16);
@@ -623,6 +630,7 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
 
   const int env = P.order != nullptr ? P.order[P.env_lo + blockIdx.x] : P.env_lo + blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
   if (blockIdx.x == 0 && tid < 2 && P.order_cnt != nullptr) P.order_cnt[tid] = 0;
   const int32_t* d = P.desc + (size_t)env * CBEV_DESC_WORDS;
   const int flags = d[RD_FLAGS];
@@ -655,12 +663,10 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
   mbar_wait(s_bar, 0);
   const int shift = s_desc[RD_OX] & 15;
   const int xmax = BW * P.nbx - 1, ymax = tile_h - 1;
-  // window pixel (x, y) -> byte offset in the strips (clamped: a degenerate view can point outside the window)
-  auto tile_off = [&](int x, int y) {
-    x = min(max(x + shift, 0), xmax);
-    y = min(max(y, 0), ymax);
-    return ((x >> 7) * tile_h + y) * BW + (x & (BW - 1));
-  };
+  // window pixel (x, y), x already shifted by the alignment slack -> byte offset in the swizzled strips
+  auto tile_raw = [&](int x, int y) { return (((x >> 7) * tile_h + y) * BW + (x & (BW - 1))) ^ ((y & 7) << 4); };
+  // the same, clamped: a degenerate view can point outside the window
+  auto tile_off = [&](int x, int y) { return tile_raw(min(max(x + shift, 0), xmax), min(max(y, 0), ymax)); };
   trace_mark(P, env, 1);
 
   // ---- 2. draw list, in order: one rect per thread inside a run of equal colour (k_render) ----
@@ -683,7 +689,6 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
   trace_mark(P, env, 2);
 
   // ---- 3. rotate + compose + ego square -> S x S palette-index frame (fov.py:84-94) ----
-  uint32_t* fov32 = (uint32_t*)s_fov;
   {
     const int mode = s_desc[RD_MODE], turns = s_desc[RD_TURNS];
     const int nx = s_desc[RD_NX], ny = s_desc[RD_NY];
@@ -693,42 +698,69 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
     const int crop = P.crop;
     const int lim = (crop << 16) - 1;
     const uint32_t bg = (uint32_t)s_desc[RD_BG];
-    const int fx = s_desc[RD_FX], fy = s_desc[RD_FY];
-    const int wq = S >> 2;  // words per frame row
-    for (int u = tid; u < S * wq; u += NT) {
-      const int oy = u / wq, ox0 = (u - oy * wq) * 4;
-      const int ryp = oy - top;
-      const bool row_in = ryp >= 0 && ryp < ny;
-      const int bx = rax + isin * (rcy - ryp);
-      const int by = ray - icos * (rcy - ryp);
-      uint32_t packed = 0;
+    const int fx = s_desc[RD_FX] - shift, fy = s_desc[RD_FY];  // crop pixel (sx, sy) = window byte (sx - fx, sy - fy)
+    // As in k_render: when the four view corners lie inside the rotated surface and inside the source range, every
+    // pixel does (both conditions are linear in (x, y)) and the per-pixel range tests and clamps fall away.
+    bool fast = left <= 0 && top <= 0 && left + nx >= S && top + ny >= S && !(P.pad0 & 1) && mode == 1;
+    if (fast) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int rxp = ox0 + k - left;
-        uint32_t v = CBEV_PAL_BLACK;
-        if (row_in && rxp >= 0 && rxp < nx) {
-          if (mode == 0) {
-            int sx, sy;
-            if (turns == 0) { sx = rxp; sy = ryp; }
-            else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
-            else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
-            else { sx = ryp; sy = crop - 1 - rxp; }
-            v = s_tile[tile_off(sx - fx, sy - fy)];
-          } else {
-            const int dx = bx + rxp * icos, dy = by + rxp * isin;
-            if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
-            else v = s_tile[tile_off((dx >> 16) - fx, (dy >> 16) - fy)];
-          }
-        }
-        packed |= v << (8 * k);
+      for (int c = 0; c < 4; ++c) {
+        const int rxp = ((c & 1) ? S - 1 : 0) - left, ryp = ((c & 2) ? S - 1 : 0) - top;
+        const int dx = rax + isin * (rcy - ryp) + rxp * icos, dy = ray - icos * (rcy - ryp) + rxp * isin;
+        fast = fast && dx >= 0 && dy >= 0 && dx <= lim && dy <= lim;
       }
-      fov32[u] = packed;
+    }
+    // a warp covers 16-px x 8-row patches (lane = 4 px of one row), as in k_render
+    const int lx = lane & 3, ly = lane >> 2;
+    const int pw = S >> 4, pw_log = 31 - __clz(pw);  // patches per row (a power of two)
+    const int npatch = pw * (S >> 3);
+    for (int p = warp; p < npatch; p += nwarps) {
+      const int oy = (p >> pw_log) * 8 + ly, ox0 = (p & (pw - 1)) * 16 + lx * 4;
+      const int ryp = oy - top;
+      uint32_t packed = 0;
+      if (fast) {
+        int dx = rax + isin * (rcy - ryp) + (ox0 - left) * icos;
+        int dy = ray - icos * (rcy - ryp) + (ox0 - left) * isin;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          packed |= (uint32_t)s_tile[tile_raw((dx >> 16) - fx, (dy >> 16) - fy)] << (8 * k);
+          dx += icos;
+          dy += isin;
+        }
+      } else {
+        const bool row_in = ryp >= 0 && ryp < ny;
+        const int bx = rax + isin * (rcy - ryp);
+        const int by = ray - icos * (rcy - ryp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rxp = ox0 + k - left;
+          uint32_t v = CBEV_PAL_BLACK;
+          if (row_in && rxp >= 0 && rxp < nx) {
+            if (mode == 0) {
+              int sx, sy;
+              if (turns == 0) { sx = rxp; sy = ryp; }
+              else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
+              else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
+              else { sx = ryp; sy = crop - 1 - rxp; }
+              v = s_tile[tile_off(sx - s_desc[RD_FX], sy - fy)];
+            } else {
+              const int dx = bx + rxp * icos, dy = by + rxp * isin;
+              if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
+              else v = s_tile[tile_off((dx >> 16) - s_desc[RD_FX], (dy >> 16) - fy)];
+            }
+          }
+          packed |= v << (8 * k);
+        }
+      }
+      *(uint32_t*)(s_fov + oy * FP + ox0) = packed;
     }
     __syncthreads();
     if (P.fov_mask != nullptr) {  // apply_mask (fov.py:96-99) before the ego is drawn
+      const int wq = S >> 2, wq_log = 31 - __clz(wq);
       for (int u = tid; u < S * wq; u += NT) {
         const uint32_t mk = ((const uint32_t*)P.fov_mask)[u];
-        fov32[u] = (fov32[u] & ~mk) | ((CBEV_PAL_BLACK * 0x01010101u) & mk);
+        uint32_t* px = (uint32_t*)(s_fov + (u >> wq_log) * FP) + (u & (wq - 1));
+        *px = (*px & ~mk) | ((CBEV_PAL_BLACK * 0x01010101u) & mk);
       }
       __syncthreads();
     }
@@ -736,14 +768,15 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
     const int hw = P.hero_w;
     if (tid < hw * hw) {
       const int x = P.anchor_x - (hw >> 1) + tid % hw, y = P.anchor_y - (hw >> 1) + tid / hw;
-      if (x >= 0 && x < S && y >= 0 && y < S) s_fov[y * S + x] = CBEV_PAL_BLACK;
+      if (x >= 0 && x < S && y >= 0 && y < S) s_fov[y * FP + x] = CBEV_PAL_BLACK;
     }
   }
   __syncthreads();
   trace_mark(P, env, 3);
+  const int cq = S >> 4, cq_log = 31 - __clz(cq);  // 16-byte chunks per frame row
   if (P.fov_out != nullptr) {
     uint4* dst = (uint4*)(P.fov_out + (size_t)env * S * S);
-    for (int u = tid; u < S * S / 16; u += NT) dst[u] = ((const uint4*)s_fov)[u];
+    for (int u = tid; u < S * cq; u += NT) dst[u] = *(const uint4*)(s_fov + (u >> cq_log) * FP + ((u & (cq - 1)) << 4));
   }
 
   const int F = P.frame_stack;
@@ -752,8 +785,8 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
   if (OBS_MODE == CBEV_OBS_RGB) {
     // raw render(): (S, S, 3) uint8; 16 pixels -> 48 bytes = three 16-byte stores per thread
     uint8_t* dst = (uint8_t*)P.ring + (size_t)env * P.ring_slots * P.frame_bytes + (size_t)P.head * P.frame_bytes;
-    for (int u = tid; u < S * S / 16; u += NT) {
-      const uint4 p16 = ((const uint4*)s_fov)[u];
+    for (int u = tid; u < S * cq; u += NT) {
+      const uint4 p16 = *(const uint4*)(s_fov + (u >> cq_log) * FP + ((u & (cq - 1)) << 4));
       uint32_t o[12];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -788,38 +821,70 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
     const int32_t* lyo = lxo + OW;
     const int32_t* lxa = lyo + OH;       // [2][OW]
     const int32_t* lyb = lxa + 2 * OW;   // [2][OH]
-    for (int o = tid; o < OH * OW; o += NT) {
-      const int dy = o / OW, dx = o - dy * OW;
-      uint32_t key;
-      if (rs_mode == CBEV_RS_COPY) {
-        key = s_key[s_fov[dy * S + dx]];
-      } else if (rs_mode == CBEV_RS_HALF) {
-        // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
-        const uint8_t* q0 = s_fov + (2 * dy) * S + 2 * dx;
-        const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[S], c3 = q0[S + 1];
-        const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
-        const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
-        key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
-      } else if (rs_mode == CBEV_RS_LINEAR) {
-        // HResizeLinear: int32 rows = S0 * a0 + S1 * a1; VResizeLinear: ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2
-        const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
-        const int a0 = lxa[dx], a1 = lxa[OW + dx], b0 = lyb[dy], b1 = lyb[OH + dy];
-        const uint32_t k00 = s_key[s_fov[sy0 * S + sx0]], k01 = s_key[s_fov[sy0 * S + sx1]],
-                       k10 = s_key[s_fov[sy1 * S + sx0]], k11 = s_key[s_fov[sy1 * S + sx1]];
-        key = 0;
+    // (dy, dx) of output o = tid + i * NT without a division per output
+    const int qN = NT / OW, rN = NT - qN * OW;
+    if (rs_mode == CBEV_RS_TABLE) {
+      // Pass A: an output whose whole source footprint is one colour resolves to that colour (sixteen independent
+      // loads, no arithmetic); the others are queued.  Pass B works the queue off with the float32 tables, all lanes
+      // busy (as the 4x4-block two-pass resize of k_render does for 128 -> 96).
+      const int32_t* fxlo = (const int32_t*)(yal + nyt);
+      const int32_t* fxhi = fxlo + OW;
+      const int32_t* fylo = fxhi + OW;
+      const int32_t* fyhi = fylo + OH;
+      uint16_t* s_list = (uint16_t*)(s_out + ((OH * OW + 15) & ~15));
+      int* s_count = (int*)(s_bar + 1);
+      if (tid == 0) *s_count = 0;
+      __syncthreads();
+      int dy = tid / OW, dx = tid - dy * OW;
+      for (int o0 = 0; o0 < OH * OW; o0 += NT) {  // uniform trip count: the queue is filled with warp ballots
+        const int o = o0 + tid;
+        const bool valid = o < OH * OW;
+        bool uni = true;
+        uint32_t c0 = 0;
+        if (valid) {
+          const int xl = fxlo[dx], xh = fxhi[dx], yl = fylo[dy], yh = fyhi[dy];
+          if (xh - xl < 4 && yh - yl < 4) {
+            // footprint of <= 4 x 4: per row one 4-byte window starting at column xl (two aligned words, funnel
+            // shift), compared with the first pixel's colour under a mask of the footprint's width
+            const int sh8 = (xl & 3) * 8, wlo = xl >> 2, whi = xh >> 2;
+            const uint32_t msk = 0xffffffffu >> (8 * (3 - (xh - xl)));
+            uint32_t diff = 0, c4 = 0;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const int r0 = (int)((k00 >> (8 * ch)) & 255u) * a0 + (int)((k01 >> (8 * ch)) & 255u) * a1;
-          const int r1 = (int)((k10 >> (8 * ch)) & 255u) * a0 + (int)((k11 >> (8 * ch)) & 255u) * a1;
-          const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-          key |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t* row = (const uint32_t*)(s_fov + min(yl + i, yh) * FP);
+              const uint32_t win = __funnelshift_r(row[wlo], row[whi], sh8);
+              if (i == 0) { c0 = win & 255u; c4 = c0 * 0x01010101u; }
+              diff |= (win ^ c4) & msk;
+            }
+            uni = diff == 0;
+          } else {
+            c0 = s_fov[yl * FP + xl];
+            for (int yy = yl; yy <= yh; ++yy)
+              for (int xx = xl; xx <= xh; ++xx) uni = uni && s_fov[yy * FP + xx] == c0;
+          }
+          if (uni) s_out[o] = (uint8_t)classify_key<OBS_MODE>(s_key[c0], s_key, s_cm);
         }
-      } else {
+        const unsigned mixed = __ballot_sync(0xffffffffu, valid && !uni);
+        if (mixed) {
+          int pos = 0;
+          if (lane == 0) pos = atomicAdd(s_count, __popc(mixed));
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (valid && !uni) s_list[pos + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)o;
+        }
+        dy += qN;
+        dx += rN;
+        if (dx >= OW) { dx -= OW; ++dy; }
+      }
+      __syncthreads();
+      const int nmixed = *s_count;
+      for (int idx = tid; idx < nmixed; idx += NT) {
+        const int o = s_list[idx];
+        const int oy = o / OW, ox = o - oy * OW;
         // ResizeArea_Invoker: buf = sum_x S * alpha (from 0, in table order); sum = sum_y beta * buf; float32, no FMA
         float sr = 0.f, sg = 0.f, sb = 0.f;
-        const int y0 = yoff[dy], y1 = yoff[dy + 1], x0 = xoff[dx], x1 = xoff[dx + 1];
+        const int y0 = yoff[oy], y1 = yoff[oy + 1], x0 = xoff[ox], x1 = xoff[ox + 1];
         for (int j = y0; j < y1; ++j) {
-          const uint8_t* srow = s_fov + ysi[j] * S;
+          const uint8_t* srow = s_fov + ysi[j] * FP;
           float br = 0.f, bg = 0.f, bb = 0.f;
           for (int k = x0; k < x1; ++k) {
             const uint32_t kk = s_key[srow[xsi[k]]];
@@ -835,9 +900,42 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
         }
         const int R = min(max(__float2int_rn(sr), 0), 255), G = min(max(__float2int_rn(sg), 0), 255),
                   B = min(max(__float2int_rn(sb), 0), 255);
-        key = (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
+        s_out[o] = (uint8_t)classify_key<OBS_MODE>((uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16), s_key, s_cm);
       }
-      s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
+    } else {
+      int dy = tid / OW, dx = tid - dy * OW;
+      for (int o = tid; o < OH * OW; o += NT) {
+        uint32_t key;
+        if (rs_mode == CBEV_RS_COPY) {
+          key = s_key[s_fov[dy * FP + dx]];
+        } else if (rs_mode == CBEV_RS_HALF) {
+          // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
+          const uint8_t* q0 = s_fov + (2 * dy) * FP + 2 * dx;
+          const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[FP], c3 = q0[FP + 1];
+          const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
+          const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
+          key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
+        } else {
+          // CBEV_RS_LINEAR.  HResizeLinear: int32 rows = S0 * a0 + S1 * a1;
+          // VResizeLinear: ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2
+          const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
+          const int a0 = lxa[dx], a1 = lxa[OW + dx], b0 = lyb[dy], b1 = lyb[OH + dy];
+          const uint32_t k00 = s_key[s_fov[sy0 * FP + sx0]], k01 = s_key[s_fov[sy0 * FP + sx1]],
+                         k10 = s_key[s_fov[sy1 * FP + sx0]], k11 = s_key[s_fov[sy1 * FP + sx1]];
+          key = 0;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const int r0 = (int)((k00 >> (8 * ch)) & 255u) * a0 + (int)((k01 >> (8 * ch)) & 255u) * a1;
+            const int r1 = (int)((k10 >> (8 * ch)) & 255u) * a0 + (int)((k11 >> (8 * ch)) & 255u) * a1;
+            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            key |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
+          }
+        }
+        s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
+        dy += qN;
+        dx += rN;
+        if (dx >= OW) { dx -= OW; ++dy; }
+      }
     }
   }
   __syncthreads();
@@ -1009,11 +1107,12 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   const size_t rects_bytes = (size_t)((e->max_rects * CBEV_RECT_WORDS + 3) & ~3) * 4;
   const size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16 + rects_bytes;
   size_t region = (size_t)CBEV_ANY_BOX_W * P.nbx * P.box_h * P.nby;
-  const size_t out_bytes = ((size_t)e->cfg.obs_h * e->cfg.obs_w + 15) & ~(size_t)15;
+  // output bytes + the worklist of mixed outputs (uint16 each) of the two-pass table resize
+  const size_t out_bytes = (((size_t)e->cfg.obs_h * e->cfg.obs_w + 15) & ~(size_t)15) + 2 * (size_t)e->cfg.obs_h * e->cfg.obs_w + 16;
   if (e->cfg.obs_mode != CBEV_OBS_RGB && out_bytes > region) region = out_bytes;
-  P.region_bytes = (int32_t)region;
-  const size_t smem_any = region + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + rects_bytes +
-                          (size_t)e->rs_words * 4;
+  P.region_bytes = (int32_t)region;  // a multiple of 1024 (strips) or of 16 (output bytes)
+  const size_t smem_any = 1024 /* alignment of the swizzled strips */ + region + (size_t)S * (S + 16) + 3 * 16 * 4 +
+                          CBEV_DESC_WORDS * 4 + 16 + 16 + rects_bytes + (size_t)e->rs_words * 4;
   if (any && smem_any > 227 * 1024) {
     cbev_set_error("k_render_any needs %zu bytes of shared memory (max_rects %d): over the 227 KB of one CTA", smem_any,
                    e->max_rects);
