@@ -201,7 +201,8 @@ def _ref_staged():
 def _cpu_worker_reference(args):
     """The UNMODIFIED reference (staged copy under oracle/_ref, oracle/make_ref.py) on the pygame / gymnasium shims:
     make_env(RunConfig(num_envs=1)) stepped through its own SyncVectorEnv, masked reset on termination."""
-    wid, steps, seed = args
+    wid, steps, seed = args[:3]
+    workload = args[3] if len(args) > 3 else "c2"
     os.environ["CARLABEV_REFERENCE_ROOT"] = os.path.join(ROOT, "oracle", "_ref")
     from oracle.ref_loader import load_reference
 
@@ -209,17 +210,32 @@ def _cpu_worker_reference(args):
     from CarlaBEV.config import EnvConfig, RunConfig
     from CarlaBEV.envs import make_env
 
-    envs = make_env(RunConfig(env=EnvConfig(render_mode="rgb_array", action_mode="continuous"), num_envs=1))
+    f4 = workload == "f4"  # row f4: EnvConfig.size = 256, rdm with 12 vehicles, discrete9 actions
+    envs = make_env(RunConfig(env=EnvConfig(render_mode="rgb_array", size=256) if f4 else
+                              EnvConfig(render_mode="rgb_array", action_mode="continuous"), num_envs=1))
     rng = np.random.default_rng(seed + wid)
     mask = np.array([True])
     k = wid * 100003
     t_reset = t_step = 0.0
+
+    def do_reset():
+        nonlocal k
+        while True:
+            opts = (dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100), scene_seed=k) if f4 else
+                    dict(scene="lead_brake", level=1 + k % 3, scene_seed=k))
+            try:
+                envs.reset(options=dict(opts, reset_mask=mask))
+                return
+            except RuntimeError:  # size 256: a seed the reference cannot reset ("hero_on_obstacle"): take the next one
+                k += 1
+
     t0 = time.perf_counter()
-    envs.reset(options=dict(scene="lead_brake", level=1 + k % 3, scene_seed=k, reset_mask=mask))
+    do_reset()
     t_reset += time.perf_counter() - t0
     n = n_reset = 0
     for _ in range(steps):
-        a = np.array([[rng.uniform(0, 1), rng.uniform(-1, 1), rng.uniform(0, 1)]], dtype=np.float32)
+        a = (np.array([int(rng.integers(0, 9))]) if f4 else
+             np.array([[rng.uniform(0, 1), rng.uniform(-1, 1), rng.uniform(0, 1)]], dtype=np.float32))
         t0 = time.perf_counter()
         _, _, term, trunc, _ = envs.step(a)
         t_step += time.perf_counter() - t0
@@ -228,7 +244,7 @@ def _cpu_worker_reference(args):
             k += 1
             n_reset += 1
             t0 = time.perf_counter()
-            envs.reset(options=dict(scene="lead_brake", level=1 + k % 3, scene_seed=k, reset_mask=mask))
+            do_reset()
             t_reset += time.perf_counter() - t0
     return n, t_step, t_reset, n_reset
 
@@ -261,7 +277,7 @@ def _cpu_worker_port(args):
     return n, t_step, t_reset, k
 
 
-def cpu_baseline(steps_per_env=1500, max_workers=None):
+def cpu_baseline(steps_per_env=1500, max_workers=None, workload="c2"):
     """The reference's CPU path on all host cores: one single-env process per core (AsyncVectorEnv-style pool),
     step-only throughput = steps / slowest worker's time inside step(); reset time is reported separately."""
     import multiprocessing as mp
@@ -269,11 +285,13 @@ def cpu_baseline(steps_per_env=1500, max_workers=None):
     cores = os.cpu_count() or 1
     workers = min(cores, max_workers or 64)
     staged = _ref_staged()
+    if workload != "c2" and not staged:
+        return None  # the oracle port is only wired for the bench line's workload
     fn = _cpu_worker_reference if staged else _cpu_worker_port
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(workers) as pool:
-        res = pool.map(fn, [(w, steps_per_env, 1234) for w in range(workers)])
+        res = pool.map(fn, [(w, steps_per_env, 1234, workload) for w in range(workers)])
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
@@ -285,8 +303,10 @@ def cpu_baseline(steps_per_env=1500, max_workers=None):
             "oracle/ (NumPy port of the reference step incl. render/resize/masks/stack; no staged reference found)")
     return {"value": total / slowest, "unit": UNIT, "cores": workers, "kind": "reference-on-shims" if staged else "port",
             "reset_seconds_mean": reset_s / max(resets, 1), "resets": resets,
-            "sample": f"{workers} worker processes x 1 env x {steps_per_env} steps of the configs[1] workload (lead_brake, "
-                      f"continuous actions, 6-class F=4) through {what}; throughput = steps / slowest worker's time "
+            "sample": f"{workers} worker processes x 1 env x {steps_per_env} steps of the " +
+                      ("row-f4 workload (EnvConfig.size=256, rdm with 12 vehicles, discrete9, 6-class F=4)" if workload == "f4"
+                       else "configs[1] workload (lead_brake, continuous actions, 6-class F=4)") +
+                      f" through {what}; throughput = steps / slowest worker's time "
                       f"inside step() ({slowest:.1f} s; resets excluded and reported as reset_seconds_mean; wall incl. "
                       f"process spawn {wall:.1f} s); host has {cores} cores"}
 
@@ -536,6 +556,11 @@ def run_workload(ctx, name, args, with_cpu_baseline=False):
         }
         if with_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(steps_per_env=args.cpu_steps)
+        elif name == "f4" and world == 1 and not args.no_cpu_baseline:
+            # the other map scale has no published number anywhere: time the reference's own path beside it (short sample)
+            cb = cpu_baseline(steps_per_env=max(100, args.cpu_steps // 5), workload="f4")
+            if cb is not None:
+                res["cpu_baseline"] = cb
     envs.close()
     del envs, eng, acts_dev
     torch.cuda.empty_cache()

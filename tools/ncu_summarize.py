@@ -88,8 +88,18 @@ for stem, wl, cmd in (("prof_c2", "c2", "bench.py --workload c2 --steps 8 --warm
         tr = sum(si(d, 'dram__bytes_write.sum') + si(d, 'dram__bytes_read.sum') for d in rr) / len(rr)
         traffic[wl] = {"dram_bytes_per_launch": tr, "launches": len(rr),
                        "source": f"profiles/{tag}_{stem}_ncu_full.json: ncu --set full --clock-control none, {cmd}"}
+for stem, wl, cmd in (("prof_f4", "f4", "bench.py --workload f4 --steps 4 --warmup 12 --pool 128 (launches 12-13 of k_render_any)"),):
+    rr = [d for d in summary.get(stem, []) if d["kernel"].startswith("k_render")]
+    if rr:
+        tr = sum(si(d, 'dram__bytes_write.sum') + si(d, 'dram__bytes_read.sum') for d in rr) / len(rr)
+        traffic[wl] = {"dram_bytes_per_launch": tr, "launches": len(rr),
+                       "source": f"profiles/{tag}_{stem}_ncu_full.json: ncu --set full --clock-control none, {cmd}"}
 if traffic:
-    json.dump(traffic, open("profiles/render_traffic.json", "w"), indent=1)
+    old = {}
+    if os.path.exists("profiles/render_traffic.json"):
+        old = json.load(open("profiles/render_traffic.json"))
+    old.update(traffic)  # workloads not re-captured in this pass keep their entry
+    json.dump(old, open("profiles/render_traffic.json", "w"), indent=1)
 
 lp = os.path.join(src, "launches_c2.csv")
 if os.path.exists(lp):
