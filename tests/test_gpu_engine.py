@@ -335,9 +335,8 @@ def test_rdm_and_red_light_pools_discrete_parity():
 
 @pytest.mark.parametrize("variant", ["plain", "fov_masked", "generic_rotate", "keep_frame"])
 def test_raw_rgb_lookahead_dense_traffic(variant):
-    """BASELINE configs[4] shape: raw (128, 128, 3) uint8 frames, lookahead_75 camera, 50 vehicles, continuous.  The raw
-    frames leave the rotate loop in registers (no frame in shared memory): the corner mask, the ego square, the
-    range-tested rotate (debug flag 1) and the debug copy of the palette frame all live in that loop."""
+    """BASELINE configs[4] shape: raw (128, 128, 3) uint8 frames, lookahead_75 camera, 50 vehicles, continuous.  Variants:
+    the corner mask, the range-tested rotate (debug flag 1) and the debug copy of the palette frame on the RGB path."""
     import torch
 
     from carlabev_env_b200 import engine as E
