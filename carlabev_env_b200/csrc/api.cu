@@ -287,6 +287,11 @@ static int build_resize_tables(cbev_engine* e) {
     std::vector<int32_t> xo, xa0, xa1, yo, yb0, yb1, tab(2, 0);
     linear_area_table(S, ow, xo, xa0, xa1);
     linear_area_table(S, oh, yo, yb0, yb1);
+    // tab[0] = 1: every pair of taps sums to 2048, so four equal texels give their own colour (k_render_any's shortcut)
+    bool unit = true;
+    for (size_t i = 0; i < xa0.size(); ++i) unit = unit && xa0[i] + xa1[i] == 2048;
+    for (size_t i = 0; i < yb0.size(); ++i) unit = unit && yb0[i] + yb1[i] == 2048;
+    tab[0] = unit ? 1 : 0;
     for (auto* v : {&xo, &yo, &xa0, &xa1, &yb0, &yb1}) tab.insert(tab.end(), v->begin(), v->end());
     e->rs_words = (int32_t)tab.size();
     return dev_upload(&e->rs_tab, tab.data(), tab.size());

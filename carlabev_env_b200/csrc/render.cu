@@ -95,7 +95,8 @@ struct RenderParams {
   int32_t N, env_lo, fov, crop, anchor_x, anchor_y;
   int32_t frame_stack, ring_slots, head, mirror;  // mirror = slot offset (L - F + 1)
   int64_t frame_bytes;
-  int32_t pad0, pad1;
+  int32_t pad0;   // debug flags
+  int32_t blk83;  // k_render_any: the 8:3 block shortcut is on (separate output bytes + block flags behind the tables)
   const int32_t* desc;
   const uint32_t* rects;
   const int32_t* order;       // CTA -> env (heavy envs first), or null
@@ -608,10 +609,12 @@ k_render(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode
 template <int OBS_MODE, int CHANNELS>
 __global__ void __launch_bounds__(1024, 1)
 k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_mode) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // layout: [tile strips (1024-byte aligned: swizzle period) | re-used as the OH x OW output bytes] [frame S x (S + 16)]
   //         [tables] [mbar] [draw list] [resize tables]
-  uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // (the alignment is declared, not fixed up at run time, so that the tile's address folds into the gathers' LDS)
+  uint8_t* const smem = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();
   const int S = P.fov, NT = blockDim.x;
   const int FP = S + 16;  // frame pitch
   constexpr int BW = CBEV_ANY_BOX_W;
@@ -625,8 +628,14 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
   int32_t* s_desc = (int32_t*)(s_key + 16);
   uint64_t* s_bar = (uint64_t*)(s_desc + CBEV_DESC_WORDS);
   uint8_t* s_cm = (uint8_t*)(s_bar + 2);
-  uint32_t* s_rects = (uint32_t*)(s_cm + 16);
+  uint8_t* s_cmu = s_cm + 16;  // palette index -> output byte of a single-colour footprint (= classify_key of its colour)
+  float4* s_palf = (float4*)(s_cmu + 16);  // palette index -> (R, G, B) as float32, for the area sums
+  uint32_t* s_rects = (uint32_t*)(s_palf + 16);
   int32_t* s_tab = (int32_t*)(s_rects + ((P.max_rects * CBEV_RECT_WORDS + 3) & ~3));
+  // 8:3 block shortcut (P.blk83, below): one flag byte per 8 x 8 source block and output bytes of their own, because
+  // they are written while the rotate still reads the tile
+  uint8_t* s_bflag = (uint8_t*)(s_tab + P.rs_words);
+  uint8_t* s_out_sep = s_bflag + ((((S >> 3) * (S >> 3)) + 15) & ~15);
 
   const int env = P.order != nullptr ? P.order[P.env_lo + blockIdx.x] : P.env_lo + blockIdx.x;
   const int tid = threadIdx.x;
@@ -660,6 +669,11 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
   }
   for (int u = tid; u < P.rs_words; u += NT) s_tab[u] = P.rs_tab[u];
   __syncthreads();
+  if (OBS_MODE != CBEV_OBS_RGB && tid < CBEV_PAL_COUNT) {
+    const uint32_t kk = s_key[tid];
+    s_cmu[tid] = (uint8_t)classify_key<OBS_MODE>(kk, s_key, s_cm);
+    s_palf[tid] = make_float4((float)(kk & 255u), (float)((kk >> 8) & 255u), (float)(kk >> 16), 0.f);
+  }
   mbar_wait(s_bar, 0);
   const int shift = s_desc[RD_OX] & 15;
   const int xmax = BW * P.nbx - 1, ymax = tile_h - 1;
@@ -714,45 +728,96 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
     const int lx = lane & 3, ly = lane >> 2;
     const int pw = S >> 4, pw_log = 31 - __clz(pw);  // patches per row (a power of two)
     const int npatch = pw * (S >> 3);
-    for (int p = warp; p < npatch; p += nwarps) {
+    // 8:3 block shortcut (S : obs = 8 : 3 on both axes, e.g. 256 -> 96): every 8 x 8 source block is exactly the
+    // footprint of a 3 x 3 output block, and a patch is two such blocks.  A block whose 64 texels are one colour gives
+    // nine outputs of that colour (the area weights sum to 1 within 1e-6) straight from the rotate's registers: it is
+    // never stored to the frame nor visited by the resize.  The other blocks -- and those under the ego square, which
+    // is drawn into the frame afterwards -- are flagged and take the table resize below.
+    const bool blk83 = OBS_MODE != CBEV_OBS_RGB && P.blk83 != 0;
+    // blocks under the ego square [eg0, eg0 + hero_w) on both axes, as inclusive block ranges
+    const int eg0x = P.anchor_x - (P.hero_w >> 1), eg0y = P.anchor_y - (P.hero_w >> 1);
+    const int ebx0 = max(eg0x, 0) >> 3, ebxn = (min(eg0x + P.hero_w, S) - 1 >> 3) - ebx0;
+    const int eby0 = max(eg0y, 0) >> 3, ebyn = (min(eg0y + P.hero_w, S) - 1 >> 3) - eby0;
+    // this lane's share of a single-colour block: output (i, j) of its 3 x 3 for the first nine lanes of the block
+    const int local = ly * 2 + (lx & 1), loc_i = (local * 11) >> 5;
+    const int loc_out = loc_i * P.obs_w + (local - 3 * loc_i) + 3 * (lx >> 1);
+    const unsigned mine = (lane & 2) ? 0xccccccccu : 0x33333333u;  // the 16 lanes of this lane's block
+    // window byte of texel (x, y): strip (x >> 7) of tile_h rows of 128 bytes, 16-byte chunk ^= row & 7
+    const int strip_step = tile_h * BW - BW;
+    auto gather_fast = [&](int p) {
       const int oy = (p >> pw_log) * 8 + ly, ox0 = (p & (pw - 1)) * 16 + lx * 4;
       const int ryp = oy - top;
+      // the window origin is folded into the 16.16 start values: (d >> 16) - f == (d - (f << 16)) >> 16
+      int dx = rax + isin * (rcy - ryp) + (ox0 - left) * icos - (fx << 16);
+      int dy = ray - icos * (rcy - ryp) + (ox0 - left) * isin - (fy << 16);
       uint32_t packed = 0;
-      if (fast) {
-        int dx = rax + isin * (rcy - ryp) + (ox0 - left) * icos;
-        int dy = ray - icos * (rcy - ryp) + (ox0 - left) * isin;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          packed |= (uint32_t)s_tile[tile_raw((dx >> 16) - fx, (dy >> 16) - fy)] << (8 * k);
-          dx += icos;
-          dy += isin;
-        }
-      } else {
-        const bool row_in = ryp >= 0 && ryp < ny;
-        const int bx = rax + isin * (rcy - ryp);
-        const int by = ray - icos * (rcy - ryp);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int rxp = ox0 + k - left;
-          uint32_t v = CBEV_PAL_BLACK;
-          if (row_in && rxp >= 0 && rxp < nx) {
-            if (mode == 0) {
-              int sx, sy;
-              if (turns == 0) { sx = rxp; sy = ryp; }
-              else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
-              else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
-              else { sx = ryp; sy = crop - 1 - rxp; }
-              v = s_tile[tile_off(sx - s_desc[RD_FX], sy - fy)];
-            } else {
-              const int dx = bx + rxp * icos, dy = by + rxp * isin;
-              if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
-              else v = s_tile[tile_off((dx >> 16) - s_desc[RD_FX], (dy >> 16) - fy)];
-            }
-          }
-          packed |= v << (8 * k);
-        }
+      for (int k = 0; k < 4; ++k) {
+        const int x = dx >> 16, y = dy >> 16;
+        packed |= (uint32_t)s_tile[(y * BW + (x >> 7) * strip_step + x) ^ ((y << 4) & 0x70)] << (8 * k);
+        dx += icos;
+        dy += isin;
       }
-      *(uint32_t*)(s_fov + oy * FP + ox0) = packed;
+      return packed;
+    };
+    auto gather_generic = [&](int p) {
+      const int oy = (p >> pw_log) * 8 + ly, ox0 = (p & (pw - 1)) * 16 + lx * 4;
+      const int ryp = oy - top;
+      const bool row_in = ryp >= 0 && ryp < ny;
+      const int bx = rax + isin * (rcy - ryp);
+      const int by = ray - icos * (rcy - ryp);
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rxp = ox0 + k - left;
+        uint32_t v = CBEV_PAL_BLACK;
+        if (row_in && rxp >= 0 && rxp < nx) {
+          if (mode == 0) {
+            int sx, sy;
+            if (turns == 0) { sx = rxp; sy = ryp; }
+            else if (turns == 1) { sx = crop - 1 - ryp; sy = rxp; }
+            else if (turns == 2) { sx = crop - 1 - rxp; sy = crop - 1 - ryp; }
+            else { sx = ryp; sy = crop - 1 - rxp; }
+            v = s_tile[tile_off(sx - s_desc[RD_FX], sy - fy)];
+          } else {
+            const int dx = bx + rxp * icos, dy = by + rxp * isin;
+            if (dx < 0 || dy < 0 || dx > lim || dy > lim) v = bg;
+            else v = s_tile[tile_off((dx >> 16) - s_desc[RD_FX], (dy >> 16) - fy)];
+          }
+        }
+        packed |= v << (8 * k);
+      }
+      return packed;
+    };
+    // where the four texels of a lane go: the frame, unless their 8 x 8 block is one colour (shortcut above)
+    auto finish = [&](int p, uint32_t packed) {
+      const int oy = (p >> pw_log) * 8 + ly, ox0 = (p & (pw - 1)) * 16 + lx * 4;
+      bool keep = true;
+      if (blk83) {
+        const uint32_t c = __shfl_sync(0xffffffffu, packed, lane & 2) & 255u;  // first texel of this lane's block
+        const unsigned agree = __ballot_sync(0xffffffffu, packed == c * 0x01010101u);
+        const int pxp = p & (pw - 1), by = p >> pw_log, bx = 2 * pxp + (lx >> 1);  // block index = 2 p + (lx >> 1)
+        const bool ego = (unsigned)(bx - ebx0) <= (unsigned)ebxn && (unsigned)(by - eby0) <= (unsigned)ebyn;
+        const bool uni = (agree & mine) == mine && !ego;
+        keep = !uni;
+        if (local == 0) s_bflag[2 * p + (lx >> 1)] = uni ? 0 : 1;
+        if (uni && local < 9) s_out_sep[3 * by * P.obs_w + 6 * pxp + loc_out] = s_cmu[c];
+      }
+      if (keep) *(uint32_t*)(s_fov + oy * FP + ox0) = packed;
+    };
+    if (fast) {
+      // four patches per iteration: all sixteen gathers of a lane are issued before the first of them is consumed
+      // (npatch / nwarps is 4 at S = 64 and 16 at S = 128 / 256)
+#pragma unroll 1
+      for (int p = warp; p < npatch; p += 4 * nwarps) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pk[g] = gather_fast(p + g * nwarps);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) finish(p + g * nwarps, pk[g]);
+      }
+    } else {
+      for (int p = warp; p < npatch; p += nwarps) finish(p, gather_generic(p));
     }
     __syncthreads();
     if (P.fov_mask != nullptr) {  // apply_mask (fov.py:96-99) before the ego is drawn
@@ -805,7 +870,9 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
 
   // ---- 4. cv2.resize(INTER_AREA) (ResizeObservation, envs/__init__.py:62) + colour equality / gray level ----
   const int OH = P.obs_h, OW = P.obs_w;
-  uint8_t* s_out = smem;  // the tile is dead
+  const bool blk83 = P.blk83 != 0;
+  uint8_t* const s_out = blk83 ? s_out_sep : smem;  // the tile is dead
+  uint8_t* const s_scratch = blk83 ? smem : smem + ((OH * OW + 15) & ~15);  // work lists, in the dead tile
   {
     const int rs_mode = P.rs_mode == CBEV_RS_FAST96 ? CBEV_RS_TABLE : P.rs_mode;
     // area tables: [nx, ny, xoff[OW+1], yoff[OH+1], xsi[nx], ysi[ny], xalpha[nx], yalpha[ny]]
@@ -831,17 +898,15 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
       const int32_t* fxhi = fxlo + OW;
       const int32_t* fylo = fxhi + OW;
       const int32_t* fyhi = fylo + OH;
-      uint16_t* s_list = (uint16_t*)(s_out + ((OH * OW + 15) & ~15));
-      int* s_count = (int*)(s_bar + 1);
-      if (tid == 0) *s_count = 0;
+      uint16_t* s_list = (uint16_t*)s_scratch;
+      int* s_count = (int*)(s_bar + 1);  // [0] mixed outputs, [1] flagged blocks
+      if (tid < 2) s_count[tid] = 0;
       __syncthreads();
-      int dy = tid / OW, dx = tid - dy * OW;
-      for (int o0 = 0; o0 < OH * OW; o0 += NT) {  // uniform trip count: the queue is filled with warp ballots
-        const int o = o0 + tid;
-        const bool valid = o < OH * OW;
+      // one output: single-colour footprint -> s_cmu, otherwise onto the list (warp-aggregated; call it converged)
+      auto pass_a = [&](bool valid, int o, int dx, int dy) {
         bool uni = true;
-        uint32_t c0 = 0;
         if (valid) {
+          uint32_t c0 = 0;
           const int xl = fxlo[dx], xh = fxhi[dx], yl = fylo[dy], yh = fyhi[dy];
           if (xh - xl < 4 && yh - yl < 4) {
             // footprint of <= 4 x 4: per row one 4-byte window starting at column xl (two aligned words, funnel
@@ -862,7 +927,7 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
             for (int yy = yl; yy <= yh; ++yy)
               for (int xx = xl; xx <= xh; ++xx) uni = uni && s_fov[yy * FP + xx] == c0;
           }
-          if (uni) s_out[o] = (uint8_t)classify_key<OBS_MODE>(s_key[c0], s_key, s_cm);
+          if (uni) s_out[o] = s_cmu[c0];
         }
         const unsigned mixed = __ballot_sync(0xffffffffu, valid && !uni);
         if (mixed) {
@@ -871,9 +936,46 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
           pos = __shfl_sync(0xffffffffu, pos, 0);
           if (valid && !uni) s_list[pos + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)o;
         }
-        dy += qN;
-        dx += rN;
-        if (dx >= OW) { dx -= OW; ++dy; }
+      };
+      if (blk83) {
+        // the flagged blocks, compacted; then their nine outputs each
+        uint16_t* s_blist = s_list + OH * OW;
+        const int nblk = (S >> 3) * (S >> 3), nbw = S >> 3, nbw_log = 31 - __clz(nbw);
+        for (int b0 = 0; b0 < nblk; b0 += NT) {
+          const int b = b0 + tid;
+          const bool flagged = b < nblk && s_bflag[b] != 0;
+          const unsigned m = __ballot_sync(0xffffffffu, flagged);
+          if (m) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(s_count + 1, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (flagged) s_blist[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)b;
+          }
+        }
+        __syncthreads();
+        const int n9 = s_count[1] * 9;
+        for (int i0 = 0; i0 < n9; i0 += NT) {
+          const int idx = i0 + tid;
+          const bool valid = idx < n9;
+          int o = 0, dx = 0, dy = 0;
+          if (valid) {
+            const int q = idx / 9, sub = idx - 9 * q, blk = s_blist[q];
+            const int by = blk >> nbw_log, bx = blk & (nbw - 1), i = (sub * 11) >> 5;
+            dy = 3 * by + i;
+            dx = 3 * bx + (sub - 3 * i);
+            o = dy * OW + dx;
+          }
+          pass_a(valid, o, dx, dy);
+        }
+      } else {
+        int dy = tid / OW, dx = tid - dy * OW;
+        for (int o0 = 0; o0 < OH * OW; o0 += NT) {  // uniform trip count: the queue is filled with warp ballots
+          const int o = o0 + tid;
+          pass_a(o < OH * OW, o, dx, dy);
+          dy += qN;
+          dx += rN;
+          if (dx >= OW) { dx -= OW; ++dy; }
+        }
       }
       __syncthreads();
       const int nmixed = *s_count;
@@ -883,6 +985,34 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
         // ResizeArea_Invoker: buf = sum_x S * alpha (from 0, in table order); sum = sum_y beta * buf; float32, no FMA
         float sr = 0.f, sg = 0.f, sb = 0.f;
         const int y0 = yoff[oy], y1 = yoff[oy + 1], x0 = xoff[ox], x1 = xoff[ox + 1];
+        if (x1 - x0 <= 4 && y1 - y0 <= 4) {
+          // footprint of <= 4 x 4 consecutive texels (every shrink ratio below 3, and 8 : 3): the rows come as the
+          // 4-byte windows of pass A, the sums are unrolled; a tap beyond the footprint has weight +0.0f, and
+          // x + (+0.0f) = x exactly, so the padded sums are OpenCV's sums
+          const int xl = xsi[x0], sh8 = (xl & 3) * 8, wlo = xl >> 2, whi = (xl + (x1 - x0) - 1) >> 2;
+          float ax[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ax[k] = x0 + k < x1 ? xal[x0 + k] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (y0 + j < y1) {
+              const uint32_t* row = (const uint32_t*)(s_fov + ysi[y0 + j] * FP);
+              const uint32_t win = __funnelshift_r(row[wlo], row[whi], sh8);
+              float br = 0.f, bg = 0.f, bb = 0.f;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 c = s_palf[(win >> (8 * k)) & 255u];
+                br = __fadd_rn(br, __fmul_rn(c.x, ax[k]));
+                bg = __fadd_rn(bg, __fmul_rn(c.y, ax[k]));
+                bb = __fadd_rn(bb, __fmul_rn(c.z, ax[k]));
+              }
+              const float beta = yal[y0 + j];
+              sr = __fadd_rn(sr, __fmul_rn(beta, br));
+              sg = __fadd_rn(sg, __fmul_rn(beta, bg));
+              sb = __fadd_rn(sb, __fmul_rn(beta, bb));
+            }
+          }
+        } else
         for (int j = y0; j < y1; ++j) {
           const uint8_t* srow = s_fov + ysi[j] * FP;
           float br = 0.f, bg = 0.f, bb = 0.f;
@@ -902,16 +1032,22 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
                   B = min(max(__float2int_rn(sb), 0), 255);
         s_out[o] = (uint8_t)classify_key<OBS_MODE>((uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16), s_key, s_cm);
       }
+      if (P.trace != nullptr && tid == 0)  // work-list sizes for tools/render_trace_any.py: flagged blocks, mixed outputs
+        P.trace[(size_t)env * 8 + 7] = (unsigned)s_count[1] | ((unsigned long long)(unsigned)nmixed << 32);
     } else {
       int dy = tid / OW, dx = tid - dy * OW;
       for (int o = tid; o < OH * OW; o += NT) {
-        uint32_t key;
+        // taps of one colour give that colour exactly in every mode ((4c + 2) >> 2 = c; the bilinear kernel: below),
+        // and its output byte is tabulated
+        uint32_t key = 0;
+        int same = -1;
         if (rs_mode == CBEV_RS_COPY) {
-          key = s_key[s_fov[dy * FP + dx]];
+          same = s_fov[dy * FP + dx];
         } else if (rs_mode == CBEV_RS_HALF) {
           // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
           const uint8_t* q0 = s_fov + (2 * dy) * FP + 2 * dx;
           const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[FP], c3 = q0[FP + 1];
+          if (c0 == c1 && c0 == c2 && c0 == c3) same = (int)c0;
           const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
           const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
           key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
@@ -920,8 +1056,12 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
           // VResizeLinear: ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2
           const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
           const int a0 = lxa[dx], a1 = lxa[OW + dx], b0 = lyb[dy], b1 = lyb[OH + dy];
-          const uint32_t k00 = s_key[s_fov[sy0 * FP + sx0]], k01 = s_key[s_fov[sy0 * FP + sx1]],
-                         k10 = s_key[s_fov[sy1 * FP + sx0]], k11 = s_key[s_fov[sy1 * FP + sx1]];
+          const uint32_t i00 = s_fov[sy0 * FP + sx0], i01 = s_fov[sy0 * FP + sx1], i10 = s_fov[sy1 * FP + sx0],
+                         i11 = s_fov[sy1 * FP + sx1];
+          // s_tab[0] = 1: every tap pair sums to 2048 (api.cu checks), and then four equal taps c give
+          // floor(b0 c / 512) + floor(b1 c / 512) in {4c - 1, 4c}, + 2 >> 2 = c
+          if (s_tab[0] == 1 && i00 == i01 && i00 == i10 && i00 == i11) same = (int)i00;
+          const uint32_t k00 = s_key[i00], k01 = s_key[i01], k10 = s_key[i10], k11 = s_key[i11];
           key = 0;
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
@@ -931,7 +1071,7 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
             key |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
           }
         }
-        s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
+        s_out[o] = same >= 0 ? s_cmu[same] : (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
         dy += qN;
         dx += rN;
         if (dx >= OW) { dx -= OW; ++dy; }
@@ -1090,7 +1230,6 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   P.ring = e->ring;
   const int S = P.fov;
   const size_t tile = (size_t)CBEV_TILE_W * CBEV_TILE_H;  // >= 96*96 + 2*12288 (staging)
-  P.pad1 = 0;
   P.pad0 = e->debug_flags;  // bit0: force the generic (range-tested) rotate path
   P.obs_h = e->cfg.obs_h;
   P.obs_w = e->cfg.obs_w;
@@ -1109,10 +1248,21 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   size_t region = (size_t)CBEV_ANY_BOX_W * P.nbx * P.box_h * P.nby;
   // output bytes + the worklist of mixed outputs (uint16 each) of the two-pass table resize
   const size_t out_bytes = (((size_t)e->cfg.obs_h * e->cfg.obs_w + 15) & ~(size_t)15) + 2 * (size_t)e->cfg.obs_h * e->cfg.obs_w + 16;
-  if (e->cfg.obs_mode != CBEV_OBS_RGB && out_bytes > region) region = out_bytes;
+  // 8:3 block shortcut of k_render_any (256 -> 96, 128 -> 48, 64 -> 24): needs the whole-frame passes off (corner mask,
+  // debug copy of the frame); debug flag 512 switches it off (A/B probe)
+  const size_t nblk = (size_t)(S / 8) * (S / 8);
+  P.blk83 = e->cfg.obs_mode != CBEV_OBS_RGB && e->rs_mode == CBEV_RS_TABLE && 3 * S == 8 * e->cfg.obs_w &&
+            3 * S == 8 * e->cfg.obs_h && e->fov_mask == nullptr && !e->keep_fov && !(e->debug_flags & 512);
+  if (e->cfg.obs_mode != CBEV_OBS_RGB && out_bytes + 2 * nblk > region) region = (out_bytes + 2 * nblk + 15) & ~(size_t)15;
   P.region_bytes = (int32_t)region;  // a multiple of 1024 (strips) or of 16 (output bytes)
-  const size_t smem_any = 1024 /* alignment of the swizzled strips */ + region + (size_t)S * (S + 16) + 3 * 16 * 4 +
-                          CBEV_DESC_WORDS * 4 + 16 + 16 + rects_bytes + (size_t)e->rs_words * 4;
+  size_t sep_bytes = P.blk83 ? ((nblk + 15) & ~(size_t)15) + (((size_t)e->cfg.obs_h * e->cfg.obs_w + 15) & ~(size_t)15) : 0;
+  size_t smem_any = region + (size_t)S * (S + 16) + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 + 16 * 16 + rects_bytes +
+                    (size_t)e->rs_words * 4;
+  if (smem_any + sep_bytes > 227 * 1024) {  // a long draw list at size 256: no room for the shortcut's own output bytes
+    P.blk83 = 0;
+    sep_bytes = 0;
+  }
+  smem_any += sep_bytes;
   if (any && smem_any > 227 * 1024) {
     cbev_set_error("k_render_any needs %zu bytes of shared memory (max_rects %d): over the 227 KB of one CTA", smem_any,
                    e->max_rects);

@@ -667,12 +667,14 @@ def test_frame_recorder_env0(tmp_path):
 @pytest.mark.parametrize("obs_size,mode", [((84, 84), "semantic"), ((64, 64), "semantic"), ((128, 128), "semantic"),
                                            ((112, 100), "semantic"), ((84, 84), "gray"), ((64, 64), "gray"),
                                            ((48, 64), "gray"), ((32, 32), "semantic"), ((160, 160), "semantic"),
-                                           ((96, 144), "gray"), ((144, 96), "semantic")])
+                                           ((96, 144), "gray"), ((144, 96), "semantic"), ((48, 48), "semantic"),
+                                           ((48, 48), "gray")])
 def test_other_observation_sizes(obs_size, mode):
     """EnvConfig.obs_size other than (96, 96): ResizeObservation through OpenCV's area tables (float32, OpenCV's
     accumulation order), its 2x2 integer path for (64, 64), the plain copy for (128, 128), and its 8-bit bilinear
     kernel on area-mode coefficients as soon as one axis enlarges -- bit-exact masks /
-    gray levels against the oracle (itself pinned on cv2 for these sizes)."""
+    gray levels against the oracle (itself pinned on cv2 for these sizes).  (48, 48) is the 8 : 3 ratio: single-colour
+    8 x 8 blocks leave from the registers of the rotate (k_render_any's block shortcut)."""
     import torch
 
     from carlabev_env_b200 import engine as E

@@ -341,3 +341,41 @@ def test_make_env_at_other_map_scales(size, seeds):
                     assert np.array_equal(np.asarray(obs_r)[i], frame(oracles[i].reset(scenes[i]))), (size, raw, t, i, "reset")
         assert episodes >= 1
         envs.close()
+
+
+@pytest.mark.parametrize("size,obs_size", [(256, (96, 96)), (64, (24, 24))])
+def test_block_shortcut_equals_table_resize(size, obs_size):
+    """k_render_any's 8 : 3 block shortcut (single-colour 8 x 8 source blocks resolved in the rotate's registers) against
+    the same kernel with the shortcut off (debug flag 512: every output through the table resize, which the goldens and
+    the oracle tests pin): 96 envs, 40 steps, device auto-reset -- identical stacked masks, whatever the heading."""
+    import numpy as np
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.config import ACTION_PROFILES
+    from carlabev_env_b200.pool import pack_pool
+    from carlabev_env_b200.scenes import build_pool
+    from golden_util import load_map
+
+    pad = {64: 91, 256: 363}[size]
+    scenes = [s for s in build_pool([dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100), scene_seed=i)
+                                     for i in range(24)], pad=pad, size=size, skip_invalid=True) if s is not None]
+    assert len(scenes) >= 8
+    n = 96
+    out = []
+    for flags in (0, 512):
+        eng = E.Engine(n, action_mode=E.ACTION_DISCRETE, discrete_table=ACTION_PROFILES["discrete9_v1"]["discrete_actions"],
+                       max_actors=16, autoreset=E.AUTORESET_NEXT_STEP, ring_slots=8, size=size, obs_size=obs_size)
+        eng.upload_map(load_map(size))
+        eng.upload_pool(pack_pool(scenes))
+        eng.set_debug_flags(flags)
+        frames = [eng.reset(torch.arange(n, dtype=torch.int32) % len(scenes)).clone()]
+        g = torch.Generator(device="cuda")
+        g.manual_seed(7)
+        for _ in range(40):
+            eng.step(torch.randint(0, 9, (n,), device="cuda", generator=g))
+            frames.append(eng.obs().clone())
+        out.append(torch.stack(frames).cpu().numpy())
+        eng.close()
+    assert out[0].shape == (41, n, 24, *obs_size)
+    assert out[0].any() and np.array_equal(out[0], out[1])

@@ -28,3 +28,5 @@ if __name__ == "__main__":
     names = ["tma wait", "draw list", "rotate", "resize", "stores"]
     print(f"size {size}, {N} envs: span {(t[:, 5].max() - t0) / 1e3:.1f} us; CTA life mean {life.mean():.1f} p10 {np.percentile(life, 10):.1f} p90 {np.percentile(life, 90):.1f} us")
     print("   phase means (us): " + ", ".join(f"{n} {ph[:, i].mean():.2f} (p90 {np.percentile(ph[:, i], 90):.2f})" for i, n in enumerate(names)))
+    wl = tr[:, 7]
+    print(f"   work lists (table resize): flagged 8x8 blocks {(wl & 0xffffffff).mean():.0f} of {(size // 8) ** 2}, mixed outputs {(wl >> 32).mean():.0f} of 9216")
