@@ -1035,34 +1035,66 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
       if (P.trace != nullptr && tid == 0)  // work-list sizes for tools/render_trace_any.py: flagged blocks, mixed outputs
         P.trace[(size_t)env * 8 + 7] = (unsigned)s_count[1] | ((unsigned long long)(unsigned)nmixed << 32);
     } else {
+      // copy / exact halving / enlarging: taps of one colour give that colour exactly in every mode ((4c + 2) >> 2 = c;
+      // the bilinear kernel: below) and its output byte is tabulated -- pass A; the outputs with mixed taps are queued
+      // with warp ballots and pass B computes them with all lanes busy
+      uint16_t* s_list = (uint16_t*)s_scratch;
+      int* s_count = (int*)(s_bar + 1);
+      if (tid == 0) s_count[0] = 0;
+      __syncthreads();
+      const bool unit_taps = s_tab[0] == 1;  // bilinear: every tap pair sums to 2048 (api.cu checks)
       int dy = tid / OW, dx = tid - dy * OW;
-      for (int o = tid; o < OH * OW; o += NT) {
-        // taps of one colour give that colour exactly in every mode ((4c + 2) >> 2 = c; the bilinear kernel: below),
-        // and its output byte is tabulated
-        uint32_t key = 0;
+      for (int o0 = 0; o0 < OH * OW; o0 += NT) {  // uniform trip count
+        const int o = o0 + tid;
+        const bool valid = o < OH * OW;
         int same = -1;
-        if (rs_mode == CBEV_RS_COPY) {
-          same = s_fov[dy * FP + dx];
-        } else if (rs_mode == CBEV_RS_HALF) {
+        if (valid) {
+          if (rs_mode == CBEV_RS_COPY) {
+            same = s_fov[dy * FP + dx];
+          } else if (rs_mode == CBEV_RS_HALF) {
+            const uint8_t* q0 = s_fov + (2 * dy) * FP + 2 * dx;
+            const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[FP], c3 = q0[FP + 1];
+            if (c0 == c1 && c0 == c2 && c0 == c3) same = (int)c0;
+          } else {
+            // four equal taps c: floor(b0 c / 512) + floor(b1 c / 512) is 4c - 1 or 4c, and (that + 2) >> 2 = c
+            const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
+            const uint32_t i00 = s_fov[sy0 * FP + sx0], i01 = s_fov[sy0 * FP + sx1], i10 = s_fov[sy1 * FP + sx0],
+                           i11 = s_fov[sy1 * FP + sx1];
+            if (unit_taps && i00 == i01 && i00 == i10 && i00 == i11) same = (int)i00;
+          }
+          if (same >= 0) s_out[o] = s_cmu[same];
+        }
+        const unsigned mixed = __ballot_sync(0xffffffffu, valid && same < 0);
+        if (mixed) {
+          int pos = 0;
+          if (lane == 0) pos = atomicAdd(s_count, __popc(mixed));
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (valid && same < 0) s_list[pos + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)o;
+        }
+        dy += qN;
+        dx += rN;
+        if (dx >= OW) { dx -= OW; ++dy; }
+      }
+      __syncthreads();
+      const int nmixed = s_count[0];
+      for (int idx = tid; idx < nmixed; idx += NT) {
+        const int o = s_list[idx];
+        const int oy = o / OW, ox = o - oy * OW;
+        uint32_t key = 0;
+        if (rs_mode == CBEV_RS_HALF) {
           // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
-          const uint8_t* q0 = s_fov + (2 * dy) * FP + 2 * dx;
+          const uint8_t* q0 = s_fov + (2 * oy) * FP + 2 * ox;
           const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[FP], c3 = q0[FP + 1];
-          if (c0 == c1 && c0 == c2 && c0 == c3) same = (int)c0;
           const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
           const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
           key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
         } else {
           // CBEV_RS_LINEAR.  HResizeLinear: int32 rows = S0 * a0 + S1 * a1;
           // VResizeLinear: ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2
-          const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
-          const int a0 = lxa[dx], a1 = lxa[OW + dx], b0 = lyb[dy], b1 = lyb[OH + dy];
-          const uint32_t i00 = s_fov[sy0 * FP + sx0], i01 = s_fov[sy0 * FP + sx1], i10 = s_fov[sy1 * FP + sx0],
-                         i11 = s_fov[sy1 * FP + sx1];
-          // s_tab[0] = 1: every tap pair sums to 2048 (api.cu checks), and then four equal taps c give
-          // floor(b0 c / 512) + floor(b1 c / 512) in {4c - 1, 4c}, + 2 >> 2 = c
-          if (s_tab[0] == 1 && i00 == i01 && i00 == i10 && i00 == i11) same = (int)i00;
-          const uint32_t k00 = s_key[i00], k01 = s_key[i01], k10 = s_key[i10], k11 = s_key[i11];
-          key = 0;
+          const int sx0 = lxo[ox], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[oy], sy1 = min(sy0 + 1, S - 1);
+          const int a0 = lxa[ox], a1 = lxa[OW + ox], b0 = lyb[oy], b1 = lyb[OH + oy];
+          const uint32_t k00 = s_key[s_fov[sy0 * FP + sx0]], k01 = s_key[s_fov[sy0 * FP + sx1]],
+                         k10 = s_key[s_fov[sy1 * FP + sx0]], k11 = s_key[s_fov[sy1 * FP + sx1]];
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
             const int r0 = (int)((k00 >> (8 * ch)) & 255u) * a0 + (int)((k01 >> (8 * ch)) & 255u) * a1;
@@ -1071,11 +1103,9 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
             key |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
           }
         }
-        s_out[o] = same >= 0 ? s_cmu[same] : (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
-        dy += qN;
-        dx += rN;
-        if (dx >= OW) { dx -= OW; ++dy; }
+        s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
       }
+      if (P.trace != nullptr && tid == 0) P.trace[(size_t)env * 8 + 7] = (unsigned long long)(unsigned)nmixed << 32;
     }
   }
   __syncthreads();

@@ -1,5 +1,5 @@
 # validation with the driver's own commands + ncu evidence for k_render_any (row f4)
-O=gpurun_out/r3z
+O=gpurun_out/r4z
 mkdir -p $O
 timeout 1800 python -m pytest tests -x -q -m gpu > $O/pytest.log 2>&1; echo "pytest rc $?"; grep -E "^E  " $O/pytest.log | head; tail -3 $O/pytest.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $O/smoke.log 2>&1; echo "smoke rc $?"; tail -1 $O/smoke.log
@@ -14,7 +14,7 @@ python - <<'PY'
 import json
 for f in ('bench_20','bench_default'):
     try:
-        d=json.loads(open(f'gpurun_out/r3z/{f}.json').read().strip().splitlines()[-1]); r=d['roofline']
+        d=json.loads(open(f'gpurun_out/r4z/{f}.json').read().strip().splitlines()[-1]); r=d['roofline']
         print(f, 'val %.3e'%d['value'], 'ms %.4f'%d['ms_per_step'], 'frac %.3f step %.3f'%(r['frac'],r['step_frac']), 'e2e %.3e venv %.3e'%(d['e2e']['value'], d['e2e_vector_env']['value']), 'clocks', d['clocks'])
         for w in d.get('extra_workloads',[]): print('   ', w['name'], '%.3e'%w.get('value',0), 'frac', w.get('roofline',{}).get('frac'), w.get('skipped'), w.get('error'), (w.get('cpu_baseline') or {}).get('value'))
         if d.get('cpu_baseline'): print('    cpu', d['cpu_baseline']['value'], d['cpu_baseline']['kind'])
