@@ -343,11 +343,12 @@ def test_make_env_at_other_map_scales(size, seeds):
         envs.close()
 
 
-@pytest.mark.parametrize("size,obs_size", [(256, (96, 96)), (64, (24, 24))])
-def test_block_shortcut_equals_table_resize(size, obs_size):
+@pytest.mark.parametrize("size,obs_size,rotate", [(256, (96, 96), 0), (64, (24, 24), 0), (256, (96, 96), 1)])
+def test_block_shortcut_equals_table_resize(size, obs_size, rotate):
     """k_render_any's 8 : 3 block shortcut (single-colour 8 x 8 source blocks resolved in the rotate's registers) against
     the same kernel with the shortcut off (debug flag 512: every output through the table resize, which the goldens and
-    the oracle tests pin): 96 envs, 40 steps, device auto-reset -- identical stacked masks, whatever the heading."""
+    the oracle tests pin): 96 envs, 40 steps, device auto-reset -- identical stacked masks, whatever the heading
+    (`rotate` = 1: through the range-tested rotate, debug flag 1)."""
     import numpy as np
     import torch
 
@@ -363,7 +364,7 @@ def test_block_shortcut_equals_table_resize(size, obs_size):
     assert len(scenes) >= 8
     n = 96
     out = []
-    for flags in (0, 512):
+    for flags in (rotate, rotate | 512):
         eng = E.Engine(n, action_mode=E.ACTION_DISCRETE, discrete_table=ACTION_PROFILES["discrete9_v1"]["discrete_actions"],
                        max_actors=16, autoreset=E.AUTORESET_NEXT_STEP, ring_slots=8, size=size, obs_size=obs_size)
         eng.upload_map(load_map(size))
