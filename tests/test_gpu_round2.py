@@ -343,9 +343,12 @@ def test_make_env_at_other_map_scales(size, seeds):
         envs.close()
 
 
-@pytest.mark.parametrize("size,obs_size,rotate", [(256, (96, 96), 0), (64, (24, 24), 0), (256, (96, 96), 1)])
+@pytest.mark.parametrize("size,obs_size,rotate", [(256, (96, 96), 0), (64, (24, 24), 0), (256, (96, 96), 1),
+                                                  (128, (84, 84), 0), (256, (84, 84), 0), (128, (100, 72), 1),
+                                                  (128, (16, 24), 0)])
 def test_block_shortcut_equals_table_resize(size, obs_size, rotate):
-    """k_render_any's 8 : 3 block shortcut (single-colour 8 x 8 source blocks resolved in the rotate's registers) against
+    """k_render_any's 8 : 3 block shortcut (single-colour 8 x 8 source blocks resolved in the rotate's registers) and, at
+    the other ratios, its separable single-colour test (vertical uniformity per 4-texel word, then one window) against
     the same kernel with the shortcut off (debug flag 512: every output through the table resize, which the goldens and
     the oracle tests pin): 96 envs, 40 steps, device auto-reset -- identical stacked masks, whatever the heading
     (`rotate` = 1: through the range-tested rotate, debug flag 1)."""
@@ -358,7 +361,7 @@ def test_block_shortcut_equals_table_resize(size, obs_size, rotate):
     from carlabev_env_b200.scenes import build_pool
     from golden_util import load_map
 
-    pad = {64: 91, 256: 363}[size]
+    pad = {64: 91, 128: 182, 256: 363}[size]
     scenes = [s for s in build_pool([dict(scene="rdm", num_vehicles=12, route_dist_range=(30, 100), scene_seed=i)
                                      for i in range(24)], pad=pad, size=size, skip_invalid=True) if s is not None]
     assert len(scenes) >= 8
