@@ -727,7 +727,7 @@ int cbev_reset(cbev_handle e, const uint8_t* mask_dev, const int32_t* scene_ids_
   if (e->head < 0) e->head = F - 1;
   cbev_launch_reset(e, mask_dev, scene_ids_dev, s);
   if ((rc = debug_sync("k_reset", s))) return rc;
-  if (cbev_launch_render(e, e->head, F > 1 ? L - F + 1 : 0, 0, e->N, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
+  if (cbev_launch_render(e, e->head, F > 1 ? L - F + 1 : 0, 0, e->N, s)) return CBEV_ERR_CUDA;  // cbev_launch_render says why
   if ((rc = debug_sync("k_render (reset frame)", s))) return rc;
   CU_TRY(cudaGetLastError());
   e->was_reset = true;
@@ -807,7 +807,7 @@ int cbev_step_ex(cbev_handle e, const void* actions_dev, const cbev_step_out* ou
     e->host_copy_pending = true;
   }
   CU_TRY(cudaEventRecord(e->ev_judge, js));
-  if (cbev_launch_render(e, head, mirror, 0, e->N, s)) { cbev_set_error("render launch failed"); return CBEV_ERR_CUDA; }
+  if (cbev_launch_render(e, head, mirror, 0, e->N, s)) return CBEV_ERR_CUDA;  // cbev_launch_render says why
   if (prof) { cudaEventRecord(pe[2], s); e->prof_n += 1; }
   if ((rc = debug_sync("k_render", s))) return rc;
   CU_TRY(cudaStreamWaitEvent(s, e->ev_judge, 0));  // join (covers the host copies too)

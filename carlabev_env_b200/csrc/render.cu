@@ -97,6 +97,7 @@ struct RenderParams {
   int64_t frame_bytes;
   int32_t pad0;   // debug flags
   int32_t blk83;  // k_render_any: the 8:3 block shortcut is on (separate output bytes + block flags behind the tables)
+  int32_t list_cap;  // k_render_any: entries of the mixed-output work list; the resize runs in bands of that many outputs
   const int32_t* desc;
   const uint32_t* rects;
   const int32_t* order;       // CTA -> env (heavy envs first), or null
@@ -937,6 +938,17 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
           if (valid && !uni) s_list[pos + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)o;
         }
       };
+      // (without the block shortcut the outputs go in bands of P.list_cap: the work list of a band always fits the dead
+      //  tile, whatever the observation size -- one band for everything up to about 150 x 150 at size 128)
+      const int total = OH * OW, band = blk83 ? total : min(total, P.list_cap);
+      int nmixed_all = 0;
+      for (int b0 = 0; b0 < total; b0 += band) {
+      const int b1 = min(b0 + band, total);
+      if (b0 > 0) {  // pass B of the previous band is done before its list is reused
+        __syncthreads();
+        if (tid == 0) s_count[0] = 0;
+        __syncthreads();
+      }
       if (blk83) {
         // the flagged blocks, compacted; then their nine outputs each
         uint16_t* s_blist = s_list + OH * OW;
@@ -968,10 +980,10 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
           pass_a(valid, o, dx, dy);
         }
       } else {
-        int dy = tid / OW, dx = tid - dy * OW;
-        for (int o0 = 0; o0 < OH * OW; o0 += NT) {  // uniform trip count: the queue is filled with warp ballots
+        int dy = (b0 + tid) / OW, dx = (b0 + tid) - dy * OW;
+        for (int o0 = b0; o0 < b1; o0 += NT) {  // uniform trip count: the queue is filled with warp ballots
           const int o = o0 + tid;
-          pass_a(o < OH * OW, o, dx, dy);
+          pass_a(o < b1, o, dx, dy);
           dy += qN;
           dx += rN;
           if (dx >= OW) { dx -= OW; ++dy; }
@@ -979,6 +991,7 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
       }
       __syncthreads();
       const int nmixed = *s_count;
+      nmixed_all += nmixed;
       for (int idx = tid; idx < nmixed; idx += NT) {
         const int o = s_list[idx];
         const int oy = o / OW, ox = o - oy * OW;
@@ -1032,8 +1045,9 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
                   B = min(max(__float2int_rn(sb), 0), 255);
         s_out[o] = (uint8_t)classify_key<OBS_MODE>((uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16), s_key, s_cm);
       }
+      }  // bands
       if (P.trace != nullptr && tid == 0)  // work-list sizes for tools/render_trace_any.py: flagged blocks, mixed outputs
-        P.trace[(size_t)env * 8 + 7] = (unsigned)s_count[1] | ((unsigned long long)(unsigned)nmixed << 32);
+        P.trace[(size_t)env * 8 + 7] = (unsigned)s_count[1] | ((unsigned long long)(unsigned)nmixed_all << 32);
     } else {
       // copy / exact halving / enlarging: taps of one colour give that colour exactly in every mode ((4c + 2) >> 2 = c;
       // the bilinear kernel: below) and its output byte is tabulated -- pass A; the outputs with mixed taps are queued
@@ -1043,10 +1057,19 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
       if (tid == 0) s_count[0] = 0;
       __syncthreads();
       const bool unit_taps = s_tab[0] == 1;  // bilinear: every tap pair sums to 2048 (api.cu checks)
-      int dy = tid / OW, dx = tid - dy * OW;
-      for (int o0 = 0; o0 < OH * OW; o0 += NT) {  // uniform trip count
+      const int total = OH * OW, band = min(total, P.list_cap);  // bands: see the table resize
+      int nmixed_all = 0;
+      for (int b0 = 0; b0 < total; b0 += band) {
+      const int b1 = min(b0 + band, total);
+      if (b0 > 0) {
+        __syncthreads();
+        if (tid == 0) s_count[0] = 0;
+        __syncthreads();
+      }
+      int dy = (b0 + tid) / OW, dx = (b0 + tid) - dy * OW;
+      for (int o0 = b0; o0 < b1; o0 += NT) {  // uniform trip count
         const int o = o0 + tid;
-        const bool valid = o < OH * OW;
+        const bool valid = o < b1;
         int same = -1;
         if (valid) {
           if (rs_mode == CBEV_RS_COPY) {
@@ -1077,6 +1100,7 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
       }
       __syncthreads();
       const int nmixed = s_count[0];
+      nmixed_all += nmixed;
       for (int idx = tid; idx < nmixed; idx += NT) {
         const int o = s_list[idx];
         const int oy = o / OW, ox = o - oy * OW;
@@ -1105,7 +1129,8 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
         }
         s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
       }
-      if (P.trace != nullptr && tid == 0) P.trace[(size_t)env * 8 + 7] = (unsigned long long)(unsigned)nmixed << 32;
+      }  // bands
+      if (P.trace != nullptr && tid == 0) P.trace[(size_t)env * 8 + 7] = (unsigned long long)(unsigned)nmixed_all << 32;
     }
   }
   __syncthreads();
@@ -1212,7 +1237,10 @@ int launch(cbev_engine* e, const RenderParams& P, size_t smem, size_t smem_any, 
   if (any) {
     auto kern = k_render_any<MODE, CH>;
     if (!attr_done[dev][1]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 1;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cbev_set_error("k_render_any: cannot opt in to 227 KB of dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+      }
       attr_done[dev][1] = true;
     }
     kern<<<P.N, P.fov > 128 ? 1024 : 256, smem_any, s>>>(P, *reinterpret_cast<const CUtensorMap*>(e->tmap_any),
@@ -1221,7 +1249,10 @@ int launch(cbev_engine* e, const RenderParams& P, size_t smem, size_t smem_any, 
   }
   auto kern = k_render<MODE, CH>;
   if (!attr_done[dev][0]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+      cbev_set_error("k_render: cannot opt in to 100 KB of dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return 1;
+    }
     attr_done[dev][0] = true;
   }
   kern<<<P.N, RT, smem, s>>>(P, *reinterpret_cast<const CUtensorMap*>(e->tmap), e->cfg.mask_mode);
@@ -1276,15 +1307,22 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
   const size_t rects_bytes = (size_t)((e->max_rects * CBEV_RECT_WORDS + 3) & ~3) * 4;
   const size_t smem = tile + (size_t)S * S + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 * 16 + 16 + rects_bytes;
   size_t region = (size_t)CBEV_ANY_BOX_W * P.nbx * P.box_h * P.nby;
-  // output bytes + the worklist of mixed outputs (uint16 each) of the two-pass table resize
-  const size_t out_bytes = (((size_t)e->cfg.obs_h * e->cfg.obs_w + 15) & ~(size_t)15) + 2 * (size_t)e->cfg.obs_h * e->cfg.obs_w + 16;
+  // output bytes + the work list of mixed outputs (uint16 each) of the two-pass resize.  The list need not hold every
+  // output: the resize runs in bands of list_cap outputs (>= 4096, or all of them when they are fewer)
+  const size_t ohw = (size_t)e->cfg.obs_h * e->cfg.obs_w, ohw16 = (ohw + 15) & ~(size_t)15;
+  const size_t out_bytes = ohw16 + 2 * (ohw < 4096 ? ohw : 4096) + 16;
   // 8:3 block shortcut of k_render_any (256 -> 96, 128 -> 48, 64 -> 24): needs the whole-frame passes off (corner mask,
   // debug copy of the frame); debug flag 512 switches it off (A/B probe)
   const size_t nblk = (size_t)(S / 8) * (S / 8);
   P.blk83 = e->cfg.obs_mode != CBEV_OBS_RGB && e->rs_mode == CBEV_RS_TABLE && 3 * S == 8 * e->cfg.obs_w &&
             3 * S == 8 * e->cfg.obs_h && e->fov_mask == nullptr && !e->keep_fov && !(e->debug_flags & 512);
-  if (e->cfg.obs_mode != CBEV_OBS_RGB && out_bytes + 2 * nblk > region) region = (out_bytes + 2 * nblk + 15) & ~(size_t)15;
+  if (P.blk83 && 2 * ohw + 2 * nblk + 16 > region) P.blk83 = 0;  // (its lists: nine outputs per flagged block + the blocks)
+  if (e->cfg.obs_mode != CBEV_OBS_RGB && out_bytes > region) region = out_bytes;
   P.region_bytes = (int32_t)region;  // a multiple of 1024 (strips) or of 16 (output bytes)
+  {
+    const size_t room = region > ohw16 + 16 ? (region - ohw16 - 16) / 2 : 0;
+    P.list_cap = (int32_t)(room < ohw ? room : ohw);
+  }
   size_t sep_bytes = P.blk83 ? ((nblk + 15) & ~(size_t)15) + (((size_t)e->cfg.obs_h * e->cfg.obs_w + 15) & ~(size_t)15) : 0;
   size_t smem_any = region + (size_t)S * (S + 16) + 3 * 16 * 4 + CBEV_DESC_WORDS * 4 + 16 + 16 + 16 + 16 * 16 + rects_bytes +
                     (size_t)e->rs_words * 4;
@@ -1309,7 +1347,7 @@ int cbev_launch_render(cbev_engine* e, int32_t head, int32_t mirror, int lo, int
       case 5: rc = launch<CBEV_OBS_SEMANTIC, 5>(e, P, smem, smem_any, any, s); break;
       case 6: rc = launch<CBEV_OBS_SEMANTIC, 6>(e, P, smem, smem_any, any, s); break;
       case 7: rc = launch<CBEV_OBS_SEMANTIC, 7>(e, P, smem, smem_any, any, s); break;
-      default: rc = 1;
+      default: cbev_set_error("no raster kernel for %d mask channels", e->channels); rc = 1;
     }
   }
   if (rc == 0) e->launches += 1;

@@ -383,3 +383,50 @@ def test_block_shortcut_equals_table_resize(size, obs_size, rotate):
         eng.close()
     assert out[0].shape == (41, n, 24, *obs_size)
     assert out[0].any() and np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("size,obs_size,mode", [(256, (256, 256), "semantic"), (256, (200, 200), "gray"),
+                                                (256, (128, 128), "semantic"), (256, (64, 64), "gray"),
+                                                (64, (24, 24), "semantic")])
+def test_large_and_small_observations_at_other_map_scales(size, obs_size, mode):
+    """Observation sizes whose work list of mixed outputs cannot hold every output next to the output bytes in the dead
+    tile (size 256 with 200 x 200 or the 256 x 256 copy: the resize runs in bands), the halving and quartering of the
+    256-px view, and the 8 : 3 block shortcut at size 64 -- against the oracle (resize branches pinned on cv2 in
+    tests/test_oracle_contracts.py)."""
+    import numpy as np
+    import torch
+
+    from carlabev_env_b200 import engine as E
+    from carlabev_env_b200.pool import pack_pool
+    from carlabev_env_b200.scenes import build_pool
+    from golden_util import load_map
+    from oracle.env import OracleEnv
+
+    pad = {64: 91, 256: 363}[size]
+    cls = load_map(size)
+    scenes = [s for s in build_pool([dict(scene="rdm", num_vehicles=10, route_dist_range=(30, 100), scene_seed=i)
+                                     for i in range(16)], pad=pad, size=size, skip_invalid=True) if s is not None][:5]
+    n = len(scenes)
+    assert n >= 3
+    gray = mode == "gray"
+    eng = E.Engine(n, action_mode=E.ACTION_CONTINUOUS, max_actors=16, ring_budget_bytes=256 << 20, size=size,
+                   obs_size=obs_size, obs_mode=E.OBS_GRAY if gray else E.OBS_SEMANTIC, frame_stack=2)
+    eng.upload_map(cls)
+    eng.upload_pool(pack_pool(scenes))
+    oracles = [OracleEnv(cls, action_mode="continuous", size=size, obs_size=obs_size, frame_stack=2,
+                         obs_mode="bev_rgb" if gray else "bev_semantic") for _ in range(n)]
+    obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(obs[i], oracles[i].reset(scenes[i])), (i, "reset")
+    rng = np.random.default_rng(size + obs_size[0])
+    alive = np.ones(n, bool)
+    for t in range(16):
+        a = np.stack([rng.uniform(0.3, 1, n), rng.uniform(-0.5, 0.5, n), rng.uniform(0, 0.2, n)], axis=1).astype(np.float32)
+        eng.step(torch.from_numpy(a).cuda())
+        obs = eng.obs().cpu().numpy()
+        for i in range(n):
+            if alive[i]:
+                o, _, te, tr, _ = oracles[i].step(a[i])
+                assert np.array_equal(obs[i], o), (t, i)
+                alive[i] = not (te or tr)
+    eng.close()

@@ -209,3 +209,19 @@ def test_engine_fuzz_with_pursuit_driving(seed):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "0 mismatching rounds" in r.stdout
+
+
+@pytest.mark.parametrize("seed", [21])
+def test_engine_fuzz_across_map_scales_and_observation_sizes(seed):
+    """The same fuzzer drawing EnvConfig.size from {64, 128, 256} and the observation size from a list: k_render_any's
+    block shortcut, its table / halving / copy / bilinear resizes and the scale factor of the sim kernels against the
+    oracle (pinned on reference goldens at every scale and on cv2 for every resize branch)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz.py"), "5", str(seed), "100", "1"], cwd=root,
+                       capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 mismatching rounds" in r.stdout

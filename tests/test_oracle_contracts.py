@@ -49,6 +49,7 @@ def test_area_resize_any_obs_size_matches_cv2(size):
 
 
 @pytest.mark.parametrize("view,size", [(256, (96, 96)), (256, (128, 128)), (256, (84, 84)), (256, (64, 96)), (256, (100, 60)),
+                                       (256, (256, 256)), (256, (200, 200)), (256, (64, 64)), (64, (24, 24)),
                                        (64, (96, 96)), (64, (84, 84)), (64, (128, 128)), (64, (64, 64)), (64, (32, 32)),
                                        (64, (48, 96)), (64, (96, 48)), (64, (72, 100)), (64, (65, 65))])
 def test_resize_from_other_view_sizes_matches_cv2(view, size):

@@ -1,5 +1,6 @@
 """Engine vs oracle under random configurations with route-pursuit driving (long episodes, success / checkpoint
-endings).  Run on the B200 box:  python tools/gpu_fuzz.py [n_rounds] [seed] [steps]
+endings).  Run on the B200 box:  python tools/gpu_fuzz.py [n_rounds] [seed] [steps] [scales]
+`scales` = 1 also draws EnvConfig.size from {64, 128, 256} and the observation size from a list (k_render_any).
 Same comparison as tests/test_gpu_engine.py::test_random_configurations_against_the_oracle, more of it."""
 import sys
 
@@ -23,7 +24,7 @@ def main():
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 300
-    cls = load_map()
+    scales = len(sys.argv) > 4 and sys.argv[4] == "1"
     bad = compared = 0
     endings = {}
     for rd in range(rounds):
@@ -34,26 +35,41 @@ def main():
         anchor = (0.5, 0.75) if rng.random() < 0.4 else (0.5, 0.5)
         fov_masked, gray = bool(rng.random() < 0.3), bool(rng.random() < 0.25)
         frame_stack = int(rng.choice([3, 4, 4, 5]))
-        pad = 230 if anchor[1] == 0.75 else 182
+        size, obs_size = 128, (96, 96)
+        if scales:
+            size = int(rng.choice([64, 128, 128, 256]))
+            sizes = {64: [(96, 96), (96, 96), (24, 24), (64, 64), (32, 32), (48, 40)],
+                     128: [(96, 96), (84, 84), (64, 64), (48, 48), (128, 128), (112, 100), (160, 160), (36, 36)],
+                     256: [(96, 96), (96, 96), (84, 84), (128, 128), (64, 64), (256, 256), (100, 60)]}[size]
+            obs_size = sizes[int(rng.integers(0, len(sizes)))]
+        cls = load_map(size)
+        m = size - 1
+        ax, ay = int(round(m * anchor[0])), int(round(m * anchor[1]))
+        pad = max(size, int(np.ceil(2.0 * np.hypot(max(ax, m - ax), max(ay, m - ay)))))  # vector_env.py:_crop_size
         reqs = [dict(scene="rdm", num_vehicles=int(rng.integers(0, 12)), route_dist_range=[30, 90],
-                     scene_seed=int(rng.integers(0, 10**6))) for _ in range(8)]
-        reqs += [dict(scene="lead_brake", level=int(rng.integers(1, 4)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
-        reqs += [dict(scene="jaywalk", level=int(rng.integers(1, 5)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
-        reqs += [dict(scene="red_light_runner", scene_seed=int(rng.integers(0, 10**6))) for _ in range(2)]
-        scenes = [S.build_scene(r, cls_map=cls, pad=pad) for r in reqs]
+                     scene_seed=int(rng.integers(0, 10**6))) for _ in range(8 if size == 128 else 20)]
+        if size == 128:  # the scripted scenarios exist at the 128 scale only (quirk C-11)
+            reqs += [dict(scene="lead_brake", level=int(rng.integers(1, 4)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
+            reqs += [dict(scene="jaywalk", level=int(rng.integers(1, 5)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
+            reqs += [dict(scene="red_light_runner", scene_seed=int(rng.integers(0, 10**6))) for _ in range(2)]
+            scenes = [S.build_scene(r, cls_map=cls, pad=pad) for r in reqs]
+        else:
+            scenes = [sc for sc in S.build_pool(reqs, pad=pad, size=size, skip_invalid=True, workers=1) if sc is not None][:12]
+            reqs = [dict(size=size, n=len(scenes))]
         n = len(scenes)
         table = ACTION_PROFILES[profile].get("discrete_actions")
         eng = E.Engine(n, obs_mode=E.OBS_GRAY if gray else E.OBS_SEMANTIC, mask_mode=mask, frame_stack=frame_stack,
                        action_mode=E.ACTION_CONTINUOUS if continuous else E.ACTION_DISCRETE, discrete_table=table,
                        reward_mode=E.REWARD_SHAPING if reward == "shaping" else E.REWARD_CARL, anchor=anchor,
-                       max_actors=16, ring_budget_bytes=64 << 20)
+                       max_actors=16, ring_budget_bytes=64 << 20, size=size, obs_size=obs_size)
         eng.upload_map(cls)
         eng.upload_pool(pack_pool(scenes))
         if fov_masked:
-            eng.upload_fov_mask(corner_mask(128, 0.5))
+            eng.upload_fov_mask(corner_mask(size, 0.5))
         oracles = [OracleEnv(cls, obs_mode="bev_gray" if gray else "bev_semantic", semantic_mask_ch=mask,
                              action_mode="continuous" if continuous else "discrete", action_profile=profile,
-                             reward_mode=reward, anchor=anchor, fov_masked=fov_masked, frame_stack=frame_stack)
+                             reward_mode=reward, anchor=anchor, fov_masked=fov_masked, frame_stack=frame_stack,
+                             size=size, obs_size=obs_size)
                    for _ in range(n)]
         obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
         what = None
@@ -99,7 +115,9 @@ def main():
         if what:
             bad += 1
             print("MISMATCH", what, dict(profile=profile, reward=reward, mask=mask, anchor=anchor, fov_masked=fov_masked,
-                                         gray=gray, frame_stack=frame_stack), reqs)
+                                         gray=gray, frame_stack=frame_stack, size=size, obs_size=obs_size), reqs)
+        elif scales:
+            print(f"round {rd}: size {size} obs {obs_size} mask {mask} gray {gray} fov_masked {fov_masked} anchor {anchor}: ok", flush=True)
     print(f"endings (cause id -> count): {endings}")
     print(f"{rounds} rounds, {compared} env-steps compared, {bad} mismatching rounds")
     return 1 if bad else 0
