@@ -19,6 +19,7 @@ def main():
     from carlabev_env_b200.config import ACTION_PROFILES
     from carlabev_env_b200.fovmask import corner_mask
     from carlabev_env_b200.pool import pack_pool
+    from oracle import raster
     from oracle.env import OracleEnv
 
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 4
@@ -35,17 +36,18 @@ def main():
         anchor = (0.5, 0.75) if rng.random() < 0.4 else (0.5, 0.5)
         fov_masked, gray = bool(rng.random() < 0.3), bool(rng.random() < 0.25)
         frame_stack = int(rng.choice([3, 4, 4, 5]))
-        size, obs_size = 128, (96, 96)
+        size, obs_size, raw = 128, (96, 96), False
         if scales:
+            raw = bool(rng.random() < 0.2)  # raw render() frames (size, size, 3) uint8, no resize / frame stack
+            if rng.random() < 0.35:  # any camera anchor, also on a border
+                anchor = (float(rng.choice([0.0, 0.25, 0.5, 0.6, 1.0])), float(rng.choice([0.0, 0.4, 0.9, 1.0])))
             size = int(rng.choice([64, 128, 128, 256]))
             sizes = {64: [(96, 96), (96, 96), (24, 24), (64, 64), (32, 32), (48, 40)],
                      128: [(96, 96), (84, 84), (64, 64), (48, 48), (128, 128), (112, 100), (160, 160), (36, 36)],
                      256: [(96, 96), (96, 96), (84, 84), (128, 128), (64, 64), (256, 256), (100, 60)]}[size]
             obs_size = sizes[int(rng.integers(0, len(sizes)))]
         cls = load_map(size)
-        m = size - 1
-        ax, ay = int(round(m * anchor[0])), int(round(m * anchor[1]))
-        pad = max(size, int(np.ceil(2.0 * np.hypot(max(ax, m - ax), max(ay, m - ay)))))  # vector_env.py:_crop_size
+        pad = raster.FovGeometry(size, anchor[0], anchor[1]).pad  # the crop side (= vector_env.py:_crop_size)
         reqs = [dict(scene="rdm", num_vehicles=int(rng.integers(0, 12)), route_dist_range=[30, 90],
                      scene_seed=int(rng.integers(0, 10**6))) for _ in range(8 if size == 128 else 20)]
         if size == 128:  # the scripted scenarios exist at the 128 scale only (quirk C-11)
@@ -58,7 +60,10 @@ def main():
             reqs = [dict(size=size, n=len(scenes))]
         n = len(scenes)
         table = ACTION_PROFILES[profile].get("discrete_actions")
-        eng = E.Engine(n, obs_mode=E.OBS_GRAY if gray else E.OBS_SEMANTIC, mask_mode=mask, frame_stack=frame_stack,
+        if raw:
+            gray, frame_stack = False, 1
+        eng = E.Engine(n, obs_mode=E.OBS_RGB if raw else E.OBS_GRAY if gray else E.OBS_SEMANTIC, mask_mode=mask,
+                       frame_stack=frame_stack,
                        action_mode=E.ACTION_CONTINUOUS if continuous else E.ACTION_DISCRETE, discrete_table=table,
                        reward_mode=E.REWARD_SHAPING if reward == "shaping" else E.REWARD_CARL, anchor=anchor,
                        max_actors=16, ring_budget_bytes=64 << 20, size=size, obs_size=obs_size)
@@ -66,15 +71,16 @@ def main():
         eng.upload_pool(pack_pool(scenes))
         if fov_masked:
             eng.upload_fov_mask(corner_mask(size, 0.5))
-        oracles = [OracleEnv(cls, obs_mode="bev_gray" if gray else "bev_semantic", semantic_mask_ch=mask,
+        oracles = [OracleEnv(cls, obs_mode="bev_raw" if raw else "bev_gray" if gray else "bev_semantic", semantic_mask_ch=mask,
                              action_mode="continuous" if continuous else "discrete", action_profile=profile,
                              reward_mode=reward, anchor=anchor, fov_masked=fov_masked, frame_stack=frame_stack,
                              size=size, obs_size=obs_size)
                    for _ in range(n)]
         obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
         what = None
+        frame = (lambda o: o[0]) if raw else (lambda o: o)  # the raw mode has no frame stack
         for i in range(n):
-            if not np.array_equal(obs[i], oracles[i].reset(scenes[i])):
+            if not np.array_equal(obs[i], frame(oracles[i].reset(scenes[i]))):
                 what = f"reset observation of env {i}"
         alive = np.ones(n, bool)
         tab = None if continuous else np.asarray(table, dtype=np.float64)
@@ -101,7 +107,7 @@ def main():
                 o, r, te, tr, _ = oracles[i].step(a[i] if continuous else int(a[i]))
                 e = oracles[i].sim.ego
                 compared += 1
-                if not np.array_equal(obs[i], o):
+                if not np.array_equal(obs[i], frame(o)):
                     what = f"observation env {i} step {t}"
                 elif abs(r - rew[i]) > 1e-9 or te != term[i] or tr != trunc[i]:
                     what = f"reward / flags env {i} step {t}: {r} {rew[i]} {te} {term[i]}"
@@ -115,9 +121,9 @@ def main():
         if what:
             bad += 1
             print("MISMATCH", what, dict(profile=profile, reward=reward, mask=mask, anchor=anchor, fov_masked=fov_masked,
-                                         gray=gray, frame_stack=frame_stack, size=size, obs_size=obs_size), reqs)
+                                         gray=gray, frame_stack=frame_stack, size=size, obs_size=obs_size, raw=raw), reqs)
         elif scales:
-            print(f"round {rd}: size {size} obs {obs_size} mask {mask} gray {gray} fov_masked {fov_masked} anchor {anchor}: ok", flush=True)
+            print(f"round {rd}: size {size} obs {'raw' if raw else obs_size} mask {mask} gray {gray} fov_masked {fov_masked} anchor {anchor}: ok", flush=True)
     print(f"endings (cause id -> count): {endings}")
     print(f"{rounds} rounds, {compared} env-steps compared, {bad} mismatching rounds")
     return 1 if bad else 0
