@@ -960,11 +960,15 @@ def _spawn_valid(s, cls_map, pad) -> bool:
     ty = int(np.clip(_round_half_even(y), 0, h - 1))
     if cls_map[ty, tx] == 0:
         return False
-    hx, hy = _rect_left(x, pad, 4), _rect_left(y, pad, 4)
+    # the ego square follows EnvConfig.size (hero.py:14-17: int(32 / int(1024 / size)) = 2 / 4 / 8 px; the map is 8 x size
+    # wide), the scripted actors do not: the scene generator builds them with map_size = 128 at every scale
+    # (scene_generator.py:65, vehicle.py:19-24, pedestrian.py:19-24)
+    hw = 32 // (1024 // (w // 8))
+    hx, hy = _rect_left(x, pad, hw), _rect_left(y, pad, hw)
     for i, kind in enumerate(s["act_kind"]):
         size = 4 if kind == 0 else 2
         ax, ay = _rect_left(s["act_state0"][i, 0], pad, size), _rect_left(s["act_state0"][i, 1], pad, size)
-        if hx < ax + size and hy < ay + size and hx + 4 > ax and hy + 4 > ay:
+        if hx < ax + size and hy < ay + size and hx + hw > ax and hy + hw > ay:
             return False
     return True
 

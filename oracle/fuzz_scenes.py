@@ -76,13 +76,15 @@ def random_options(rng, authored=False):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    cfg = RunConfig(env=EnvConfig(render_mode="rgb_array"), num_envs=1)
+    size = int(sys.argv[3]) if len(sys.argv) > 3 else 128  # EnvConfig.size: 64 / 128 / 256
+    cfg = RunConfig(env=EnvConfig(render_mode="rgb_array", size=size), num_envs=1)
     envs = make_env(cfg)
     base = envs.envs[0].unwrapped
-    cls = load_town01_map()
+    cls = load_town01_map(size)
+    pad = {64: 91, 128: 182, 256: 363}[size]
     bad = errors = 0
     for case in range(n):
-        o = random_options(rng, authored=True)
+        o = random_options(rng, authored=size == 128)
         ref_err = got_err = None
         try:
             envs.reset(options={**o, "reset_mask": np.array([True])})
@@ -90,7 +92,7 @@ def main():
         except Exception as ex:  # noqa: BLE001
             ref_err = type(ex).__name__
         try:
-            got = S.build_scene(o, cls_map=cls)
+            got = S.build_scene(o, cls_map=cls, pad=pad)
         except Exception as ex:  # noqa: BLE001
             got_err = type(ex).__name__
         if ref_err or got_err:
@@ -108,7 +110,7 @@ def main():
         if diff:
             bad += 1
             print("MISMATCH", o, diff)
-    print(f"{n} cases, {errors} raised on both sides, {bad} mismatches")
+    print(f"size {size}: {n} cases, {errors} raised on both sides, {bad} mismatches")
     envs.close()
     return 1 if bad else 0
 

@@ -1,6 +1,7 @@
 """Fuzz the oracle's step against the UNMODIFIED reference (build container only).
 
-TEST INFRASTRUCTURE:  python oracle/fuzz_steps.py [n_episodes] [seed] [max_steps]
+TEST INFRASTRUCTURE:  python oracle/fuzz_steps.py [n_episodes] [seed] [max_steps] [pursuit|random] [scales]
+(`scales`: EnvConfig.size is drawn from {64, 128, 256}; off the 128 scale only `rdm` scenes exist, quirk C-11)
 Random env configuration (action profile, reward mode, mask channels, camera anchor, fov mask), random reset
 options (oracle/fuzz_scenes.random_options) and random actions; the reference env and OracleEnv are stepped in
 lock-step and must agree exactly on the observation, reward, flags, ego state and every actor state of every step.
@@ -48,23 +49,33 @@ def random_env(rng):
         kw["frame_stack"] = int(rng.choice([3, 5, 6]))
     if rng.random() < 0.3:
         kw["obs_size"] = tuple(int(v) for v in rng.choice([(84, 84), (64, 64), (128, 128), (112, 100), (48, 64)]))
+    if SCALES and rng.random() < 0.7:
+        kw["size"] = int(rng.choice([64, 256]))
+        if rng.random() < 0.5:
+            kw["obs_size"] = tuple(int(v) for v in rng.choice([(96, 96), (24, 24), (128, 128), (200, 200), (100, 60), (64, 64)]))
     return kw
 
 
 PURSUIT = len(sys.argv) > 4 and sys.argv[4] == "pursuit"
+SCALES = len(sys.argv) > 5 and sys.argv[5] == "scales"
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     max_steps = int(sys.argv[3]) if len(sys.argv) > 3 else 160
-    cls = load_town01_map()
+    maps = {}
     bad = steps = 0
-    causes = {}
+    causes, by_size = {}, {}
     for ep in range(n):
         kw = random_env(rng)
         o = random_options(rng)
         o.pop("route_profile", None)
+        size = kw.get("size", 128)
+        if size != 128:
+            o = {"scene": "rdm", "scene_seed": int(rng.integers(0, 1_000_000)), "num_vehicles": int(rng.integers(0, 16)),
+                 "route_dist_range": [30, 100]}
+        cls = maps.setdefault(size, load_town01_map(size))
         cfg = RunConfig(env=EnvConfig(render_mode="rgb_array", **kw), num_envs=1)
         envs = make_env(cfg)
         base = envs.envs[0].unwrapped
@@ -74,6 +85,7 @@ def main():
             envs.close()
             continue
         scene = extract_scene(base, o)
+        by_size[size] = by_size.get(size, 0) + 1
         am = kw.get("action_mode", "discrete")
         ora = OracleEnv(cls, obs_mode="bev_semantic" if kw.get("obs_mode", "bev_semantic") == "bev_semantic" else "bev_gray",
                         semantic_mask_ch=kw["semantic_mask_ch"], action_mode=am,
@@ -81,7 +93,8 @@ def main():
                         reward_mode=kw.get("reward_mode", "carl"),
                         anchor=(kw.get("ego_anchor_x_frac", 0.5), kw.get("ego_anchor_y_frac", 0.5)),
                         fov_masked=kw.get("fov_masked", False), frame_stack=kw.get("frame_stack", 4),
-                        obs_size=kw.get("obs_size", (96, 96)), temporal_fusion_mode=kw.get("temporal_fusion_mode", "stack"))
+                        obs_size=kw.get("obs_size", (96, 96)), temporal_fusion_mode=kw.get("temporal_fusion_mode", "stack"),
+                        size=size)
         o0 = ora.reset(scene)
         what = None
         if not np.array_equal(np.asarray(obs[0]), o0):
@@ -135,7 +148,7 @@ def main():
             bad += 1
             print("MISMATCH", what, kw, o)
         envs.close()
-    print(f"endings: {causes}")
+    print(f"endings: {causes}; episodes per EnvConfig.size: {by_size}")
     print(f"{n} episodes, {steps} steps compared, {bad} mismatching episodes")
     return 1 if bad else 0
 

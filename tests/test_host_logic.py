@@ -289,6 +289,21 @@ def test_rdm_generation_at_other_map_scales(case, size, crop, bad_seed):
                           cls_map=cls, pad=crop)
 
 
+def test_spawn_validation_uses_the_ego_square_of_the_map_scale():
+    """At EnvConfig.size = 256 the ego rect of Scene.spawn_validation_info is 8 x 8 (hero.py:14-17) while the scripted
+    vehicles stay 4 x 4 (the scene generator builds them with map_size = 128).  Seed found by oracle/fuzz_scenes.py at
+    size 256: the first attempt spawns the ego 4 px from a vehicle -- overlapping only with the 8-px square -- so the
+    reference retries; the expected state below was recorded from the unmodified reference in the build container."""
+    from carlabev_env_b200 import scenes as S
+
+    got = S.build_scene(dict(scene="rdm", scene_seed=597423, num_vehicles=7, route_dist_range=[57, 117],
+                             ego_target_speed=7.927187443575018), cls_map=load_map(256), pad=363)
+    assert np.allclose(got["ego_state0"][:3], [384.97902097902096, 1090.0, 0.0], rtol=0, atol=1e-9)
+    same = S.build_scene(dict(scene="rdm", scene_seed=597423, num_vehicles=7, route_dist_range=[57, 117],
+                              ego_target_speed=7.927187443575018), cls_map=load_map(128), pad=182)
+    assert np.allclose(same["ego_state0"][:3], [305.7552447552448, 894.2377622377622, 1.9464718232739]), "the 128 scale is untouched"
+
+
 def test_red_light_generation_matches_reference_snapshots():
     """Everything but the adversary's start jitter (unseeded in the reference, quirk C-10) is reproduced."""
     from carlabev_env_b200 import scenes as S
