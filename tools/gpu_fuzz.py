@@ -37,7 +37,14 @@ def main():
         fov_masked, gray = bool(rng.random() < 0.3), bool(rng.random() < 0.25)
         frame_stack = int(rng.choice([3, 4, 4, 5]))
         size, obs_size, raw = 128, (96, 96), False
+        traj, nveh_hi, fuse = 1024, 12, None
         if scales:
+            # actor stepping: trajectory tables, a table -> live hand-over inside the episode, or live stepping (with
+            # more than 8 actor slots: the 32-lane groups of k_move); temporal fusion of the vehicle channel
+            traj = int(rng.choice([1024, 1024, 40, 0]))
+            nveh_hi = int(rng.choice([12, 28]))
+            if rng.random() < 0.25 and mask != "binary":
+                fuse = str(rng.choice(["vehicle_temporal", "vehicle_weighted"]))
             raw = bool(rng.random() < 0.2)  # raw render() frames (size, size, 3) uint8, no resize / frame stack
             if rng.random() < 0.35:  # any camera anchor, also on a border
                 anchor = (float(rng.choice([0.0, 0.25, 0.5, 0.6, 1.0])), float(rng.choice([0.0, 0.4, 0.9, 1.0])))
@@ -48,7 +55,7 @@ def main():
             obs_size = sizes[int(rng.integers(0, len(sizes)))]
         cls = load_map(size)
         pad = raster.FovGeometry(size, anchor[0], anchor[1]).pad  # the crop side (= vector_env.py:_crop_size)
-        reqs = [dict(scene="rdm", num_vehicles=int(rng.integers(0, 12)), route_dist_range=[30, 90],
+        reqs = [dict(scene="rdm", num_vehicles=int(rng.integers(0, nveh_hi)), route_dist_range=[30, 90],
                      scene_seed=int(rng.integers(0, 10**6))) for _ in range(8 if size == 128 else 20)]
         if size == 128:  # the scripted scenarios exist at the 128 scale only (quirk C-11)
             reqs += [dict(scene="lead_brake", level=int(rng.integers(1, 4)), scene_seed=int(rng.integers(0, 10**6))) for _ in range(3)]
@@ -61,12 +68,15 @@ def main():
         n = len(scenes)
         table = ACTION_PROFILES[profile].get("discrete_actions")
         if raw:
-            gray, frame_stack = False, 1
+            gray, frame_stack, fuse = False, 1, None
+        if gray:
+            fuse = None
         eng = E.Engine(n, obs_mode=E.OBS_RGB if raw else E.OBS_GRAY if gray else E.OBS_SEMANTIC, mask_mode=mask,
                        frame_stack=frame_stack,
                        action_mode=E.ACTION_CONTINUOUS if continuous else E.ACTION_DISCRETE, discrete_table=table,
                        reward_mode=E.REWARD_SHAPING if reward == "shaping" else E.REWARD_CARL, anchor=anchor,
-                       max_actors=16, ring_budget_bytes=64 << 20, size=size, obs_size=obs_size)
+                       max_actors=16 if nveh_hi <= 12 else 32, ring_budget_bytes=64 << 20, size=size, obs_size=obs_size,
+                       trajectory_steps=traj)
         eng.upload_map(cls)
         eng.upload_pool(pack_pool(scenes))
         if fov_masked:
@@ -74,9 +84,10 @@ def main():
         oracles = [OracleEnv(cls, obs_mode="bev_raw" if raw else "bev_gray" if gray else "bev_semantic", semantic_mask_ch=mask,
                              action_mode="continuous" if continuous else "discrete", action_profile=profile,
                              reward_mode=reward, anchor=anchor, fov_masked=fov_masked, frame_stack=frame_stack,
-                             size=size, obs_size=obs_size)
+                             size=size, obs_size=obs_size, temporal_fusion_mode=fuse or "stack")
                    for _ in range(n)]
-        obs = eng.reset(torch.arange(n, dtype=torch.int32)).cpu().numpy()
+        obs = eng.reset(torch.arange(n, dtype=torch.int32))
+        obs = (eng.fuse(fuse) if fuse else obs).cpu().numpy()
         what = None
         frame = (lambda o: o[0]) if raw else (lambda o: o)  # the raw mode has no frame stack
         for i in range(n):
@@ -98,7 +109,7 @@ def main():
                 acts.append(np.clip(want, [0, -1, 0], [1, 1, 1]) if continuous else int(np.argmin(((tab - want) ** 2).sum(1))))
             a = np.asarray(acts, dtype=np.float32 if continuous else np.int64)
             eng.step(torch.from_numpy(a).cuda())
-            obs, rew = eng.obs().cpu().numpy(), eng.reward.cpu().numpy()
+            obs, rew = (eng.fuse(fuse) if fuse else eng.obs()).cpu().numpy(), eng.reward.cpu().numpy()
             term, trunc = eng.terminated.cpu().numpy().astype(bool), eng.truncated.cpu().numpy().astype(bool)
             hero = eng.hero.cpu().numpy()
             for i in range(n):
@@ -121,9 +132,10 @@ def main():
         if what:
             bad += 1
             print("MISMATCH", what, dict(profile=profile, reward=reward, mask=mask, anchor=anchor, fov_masked=fov_masked,
-                                         gray=gray, frame_stack=frame_stack, size=size, obs_size=obs_size, raw=raw), reqs)
+                                         gray=gray, frame_stack=frame_stack, size=size, obs_size=obs_size, raw=raw, traj=traj, fuse=fuse,
+                                         nveh_hi=nveh_hi), reqs)
         elif scales:
-            print(f"round {rd}: size {size} obs {'raw' if raw else obs_size} mask {mask} gray {gray} fov_masked {fov_masked} anchor {anchor}: ok", flush=True)
+            print(f"round {rd}: size {size} obs {'raw' if raw else obs_size} mask {mask} gray {gray} fov_masked {fov_masked} anchor {anchor} tables {traj} fusion {fuse} vehicles < {nveh_hi}: ok", flush=True)
     print(f"endings (cause id -> count): {endings}")
     print(f"{rounds} rounds, {compared} env-steps compared, {bad} mismatching rounds")
     return 1 if bad else 0
