@@ -439,11 +439,15 @@ SG_HD bool generate_scene(int kind, int level, int64_t scene_seed, const double*
       tx = tx < 0 ? 0 : (tx > map_w - 1 ? map_w - 1 : tx);
       ty = ty < 0 ? 0 : (ty > map_h - 1 ? map_h - 1 : ty);
       if (map[(size_t)ty * map_w + tx] == 0) ok = false;
-      const int hx = rect_left(x, pad, 4), hy = rect_left(y, pad, 4);
+      // the ego square follows the map scale (hero.py:14-17: 2 / 4 / 8 px at EnvConfig.size 64 / 128 / 256; the map is
+      // 8 x size wide), the scripted actors are built with map_size = 128 at every scale (scene_generator.py:65)
+      const int msize = map_w >= 8 ? map_w / 8 : 128, mscale = msize <= 1024 ? 1024 / msize : 1;
+      const int hw = 32 / mscale > 0 ? 32 / mscale : 1;
+      const int hx = rect_left(x, pad, hw), hy = rect_left(y, pad, hw);
       for (int a = 0; a < out.n_actors && ok; ++a) {
         const int size = out.actors[a].kind == 0 ? 4 : 2;
         const int ax = rect_left(out.actors[a].state0[0], pad, size), ay = rect_left(out.actors[a].state0[1], pad, size);
-        if (hx < ax + size && hy < ay + size && hx + 4 > ax && hy + 4 > ay) ok = false;
+        if (hx < ax + size && hy < ay + size && hx + hw > ax && hy + hw > ay) ok = false;
       }
     }
     if (ok) return true;

@@ -963,7 +963,7 @@ def _spawn_valid(s, cls_map, pad) -> bool:
     # the ego square follows EnvConfig.size (hero.py:14-17: int(32 / int(1024 / size)) = 2 / 4 / 8 px; the map is 8 x size
     # wide), the scripted actors do not: the scene generator builds them with map_size = 128 at every scale
     # (scene_generator.py:65, vehicle.py:19-24, pedestrian.py:19-24)
-    hw = 32 // (1024 // (w // 8))
+    hw = max(1, 32 // max(1, 1024 // max(1, w // 8)))
     hx, hy = _rect_left(x, pad, hw), _rect_left(y, pad, hw)
     for i, kind in enumerate(s["act_kind"]):
         size = 4 if kind == 0 else 2
