@@ -943,108 +943,108 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
       const int total = OH * OW, band = blk83 ? total : min(total, P.list_cap);
       int nmixed_all = 0;
       for (int b0 = 0; b0 < total; b0 += band) {
-      const int b1 = min(b0 + band, total);
-      if (b0 > 0) {  // pass B of the previous band is done before its list is reused
-        __syncthreads();
-        if (tid == 0) s_count[0] = 0;
-        __syncthreads();
-      }
-      if (blk83) {
-        // the flagged blocks, compacted; then their nine outputs each
-        uint16_t* s_blist = s_list + OH * OW;
-        const int nblk = (S >> 3) * (S >> 3), nbw = S >> 3, nbw_log = 31 - __clz(nbw);
-        for (int b0 = 0; b0 < nblk; b0 += NT) {
-          const int b = b0 + tid;
-          const bool flagged = b < nblk && s_bflag[b] != 0;
-          const unsigned m = __ballot_sync(0xffffffffu, flagged);
-          if (m) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(s_count + 1, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (flagged) s_blist[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)b;
-          }
+        const int b1 = min(b0 + band, total);
+        if (b0 > 0) {  // pass B of the previous band is done before its list is reused
+          __syncthreads();
+          if (tid == 0) s_count[0] = 0;
+          __syncthreads();
         }
-        __syncthreads();
-        const int n9 = s_count[1] * 9;
-        for (int i0 = 0; i0 < n9; i0 += NT) {
-          const int idx = i0 + tid;
-          const bool valid = idx < n9;
-          int o = 0, dx = 0, dy = 0;
-          if (valid) {
-            const int q = idx / 9, sub = idx - 9 * q, blk = s_blist[q];
-            const int by = blk >> nbw_log, bx = blk & (nbw - 1), i = (sub * 11) >> 5;
-            dy = 3 * by + i;
-            dx = 3 * bx + (sub - 3 * i);
-            o = dy * OW + dx;
-          }
-          pass_a(valid, o, dx, dy);
-        }
-      } else {
-        int dy = (b0 + tid) / OW, dx = (b0 + tid) - dy * OW;
-        for (int o0 = b0; o0 < b1; o0 += NT) {  // uniform trip count: the queue is filled with warp ballots
-          const int o = o0 + tid;
-          pass_a(o < b1, o, dx, dy);
-          dy += qN;
-          dx += rN;
-          if (dx >= OW) { dx -= OW; ++dy; }
-        }
-      }
-      __syncthreads();
-      const int nmixed = *s_count;
-      nmixed_all += nmixed;
-      for (int idx = tid; idx < nmixed; idx += NT) {
-        const int o = s_list[idx];
-        const int oy = o / OW, ox = o - oy * OW;
-        // ResizeArea_Invoker: buf = sum_x S * alpha (from 0, in table order); sum = sum_y beta * buf; float32, no FMA
-        float sr = 0.f, sg = 0.f, sb = 0.f;
-        const int y0 = yoff[oy], y1 = yoff[oy + 1], x0 = xoff[ox], x1 = xoff[ox + 1];
-        if (x1 - x0 <= 4 && y1 - y0 <= 4) {
-          // footprint of <= 4 x 4 consecutive texels (every shrink ratio below 3, and 8 : 3): the rows come as the
-          // 4-byte windows of pass A, the sums are unrolled; a tap beyond the footprint has weight +0.0f, and
-          // x + (+0.0f) = x exactly, so the padded sums are OpenCV's sums
-          const int xl = xsi[x0], sh8 = (xl & 3) * 8, wlo = xl >> 2, whi = (xl + (x1 - x0) - 1) >> 2;
-          float ax[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) ax[k] = x0 + k < x1 ? xal[x0 + k] : 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (y0 + j < y1) {
-              const uint32_t* row = (const uint32_t*)(s_fov + ysi[y0 + j] * FP);
-              const uint32_t win = __funnelshift_r(row[wlo], row[whi], sh8);
-              float br = 0.f, bg = 0.f, bb = 0.f;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float4 c = s_palf[(win >> (8 * k)) & 255u];
-                br = __fadd_rn(br, __fmul_rn(c.x, ax[k]));
-                bg = __fadd_rn(bg, __fmul_rn(c.y, ax[k]));
-                bb = __fadd_rn(bb, __fmul_rn(c.z, ax[k]));
-              }
-              const float beta = yal[y0 + j];
-              sr = __fadd_rn(sr, __fmul_rn(beta, br));
-              sg = __fadd_rn(sg, __fmul_rn(beta, bg));
-              sb = __fadd_rn(sb, __fmul_rn(beta, bb));
+        if (blk83) {
+          // the flagged blocks, compacted; then their nine outputs each
+          uint16_t* s_blist = s_list + OH * OW;
+          const int nblk = (S >> 3) * (S >> 3), nbw = S >> 3, nbw_log = 31 - __clz(nbw);
+          for (int k0 = 0; k0 < nblk; k0 += NT) {
+            const int b = k0 + tid;
+            const bool flagged = b < nblk && s_bflag[b] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, flagged);
+            if (m) {
+              int pos = 0;
+              if (lane == 0) pos = atomicAdd(s_count + 1, __popc(m));
+              pos = __shfl_sync(0xffffffffu, pos, 0);
+              if (flagged) s_blist[pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)b;
             }
           }
-        } else
-        for (int j = y0; j < y1; ++j) {
-          const uint8_t* srow = s_fov + ysi[j] * FP;
-          float br = 0.f, bg = 0.f, bb = 0.f;
-          for (int k = x0; k < x1; ++k) {
-            const uint32_t kk = s_key[srow[xsi[k]]];
-            const float a = xal[k];
-            br = __fadd_rn(br, __fmul_rn((float)(kk & 255u), a));
-            bg = __fadd_rn(bg, __fmul_rn((float)((kk >> 8) & 255u), a));
-            bb = __fadd_rn(bb, __fmul_rn((float)(kk >> 16), a));
+          __syncthreads();
+          const int n9 = s_count[1] * 9;
+          for (int i0 = 0; i0 < n9; i0 += NT) {
+            const int idx = i0 + tid;
+            const bool valid = idx < n9;
+            int o = 0, dx = 0, dy = 0;
+            if (valid) {
+              const int q = idx / 9, sub = idx - 9 * q, blk = s_blist[q];
+              const int by = blk >> nbw_log, bx = blk & (nbw - 1), i = (sub * 11) >> 5;
+              dy = 3 * by + i;
+              dx = 3 * bx + (sub - 3 * i);
+              o = dy * OW + dx;
+            }
+            pass_a(valid, o, dx, dy);
           }
-          const float beta = yal[j];
-          sr = __fadd_rn(sr, __fmul_rn(beta, br));
-          sg = __fadd_rn(sg, __fmul_rn(beta, bg));
-          sb = __fadd_rn(sb, __fmul_rn(beta, bb));
+        } else {
+          int dy = (b0 + tid) / OW, dx = (b0 + tid) - dy * OW;
+          for (int o0 = b0; o0 < b1; o0 += NT) {  // uniform trip count: the queue is filled with warp ballots
+            const int o = o0 + tid;
+            pass_a(o < b1, o, dx, dy);
+            dy += qN;
+            dx += rN;
+            if (dx >= OW) { dx -= OW; ++dy; }
+          }
         }
-        const int R = min(max(__float2int_rn(sr), 0), 255), G = min(max(__float2int_rn(sg), 0), 255),
-                  B = min(max(__float2int_rn(sb), 0), 255);
-        s_out[o] = (uint8_t)classify_key<OBS_MODE>((uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16), s_key, s_cm);
-      }
+        __syncthreads();
+        const int nmixed = *s_count;
+        nmixed_all += nmixed;
+        for (int idx = tid; idx < nmixed; idx += NT) {
+          const int o = s_list[idx];
+          const int oy = o / OW, ox = o - oy * OW;
+          // ResizeArea_Invoker: buf = sum_x S * alpha (from 0, in table order); sum = sum_y beta * buf; float32, no FMA
+          float sr = 0.f, sg = 0.f, sb = 0.f;
+          const int y0 = yoff[oy], y1 = yoff[oy + 1], x0 = xoff[ox], x1 = xoff[ox + 1];
+          if (x1 - x0 <= 4 && y1 - y0 <= 4) {
+            // footprint of <= 4 x 4 consecutive texels (every shrink ratio below 3, and 8 : 3): the rows come as the
+            // 4-byte windows of pass A, the sums are unrolled; a tap beyond the footprint has weight +0.0f, and
+            // x + (+0.0f) = x exactly, so the padded sums are OpenCV's sums
+            const int xl = xsi[x0], sh8 = (xl & 3) * 8, wlo = xl >> 2, whi = (xl + (x1 - x0) - 1) >> 2;
+            float ax[4];
+  #pragma unroll
+            for (int k = 0; k < 4; ++k) ax[k] = x0 + k < x1 ? xal[x0 + k] : 0.f;
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (y0 + j < y1) {
+                const uint32_t* row = (const uint32_t*)(s_fov + ysi[y0 + j] * FP);
+                const uint32_t win = __funnelshift_r(row[wlo], row[whi], sh8);
+                float br = 0.f, bg = 0.f, bb = 0.f;
+  #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float4 c = s_palf[(win >> (8 * k)) & 255u];
+                  br = __fadd_rn(br, __fmul_rn(c.x, ax[k]));
+                  bg = __fadd_rn(bg, __fmul_rn(c.y, ax[k]));
+                  bb = __fadd_rn(bb, __fmul_rn(c.z, ax[k]));
+                }
+                const float beta = yal[y0 + j];
+                sr = __fadd_rn(sr, __fmul_rn(beta, br));
+                sg = __fadd_rn(sg, __fmul_rn(beta, bg));
+                sb = __fadd_rn(sb, __fmul_rn(beta, bb));
+              }
+            }
+          } else
+          for (int j = y0; j < y1; ++j) {
+            const uint8_t* srow = s_fov + ysi[j] * FP;
+            float br = 0.f, bg = 0.f, bb = 0.f;
+            for (int k = x0; k < x1; ++k) {
+              const uint32_t kk = s_key[srow[xsi[k]]];
+              const float a = xal[k];
+              br = __fadd_rn(br, __fmul_rn((float)(kk & 255u), a));
+              bg = __fadd_rn(bg, __fmul_rn((float)((kk >> 8) & 255u), a));
+              bb = __fadd_rn(bb, __fmul_rn((float)(kk >> 16), a));
+            }
+            const float beta = yal[j];
+            sr = __fadd_rn(sr, __fmul_rn(beta, br));
+            sg = __fadd_rn(sg, __fmul_rn(beta, bg));
+            sb = __fadd_rn(sb, __fmul_rn(beta, bb));
+          }
+          const int R = min(max(__float2int_rn(sr), 0), 255), G = min(max(__float2int_rn(sg), 0), 255),
+                    B = min(max(__float2int_rn(sb), 0), 255);
+          s_out[o] = (uint8_t)classify_key<OBS_MODE>((uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16), s_key, s_cm);
+        }
       }  // bands
       if (P.trace != nullptr && tid == 0)  // work-list sizes for tools/render_trace_any.py: flagged blocks, mixed outputs
         P.trace[(size_t)env * 8 + 7] = (unsigned)s_count[1] | ((unsigned long long)(unsigned)nmixed_all << 32);
@@ -1060,75 +1060,75 @@ k_render_any(RenderParams P, const __grid_constant__ CUtensorMap tmap, int mask_
       const int total = OH * OW, band = min(total, P.list_cap);  // bands: see the table resize
       int nmixed_all = 0;
       for (int b0 = 0; b0 < total; b0 += band) {
-      const int b1 = min(b0 + band, total);
-      if (b0 > 0) {
+        const int b1 = min(b0 + band, total);
+        if (b0 > 0) {
+          __syncthreads();
+          if (tid == 0) s_count[0] = 0;
+          __syncthreads();
+        }
+        int dy = (b0 + tid) / OW, dx = (b0 + tid) - dy * OW;
+        for (int o0 = b0; o0 < b1; o0 += NT) {  // uniform trip count
+          const int o = o0 + tid;
+          const bool valid = o < b1;
+          int same = -1;
+          if (valid) {
+            if (rs_mode == CBEV_RS_COPY) {
+              same = s_fov[dy * FP + dx];
+            } else if (rs_mode == CBEV_RS_HALF) {
+              const uint8_t* q0 = s_fov + (2 * dy) * FP + 2 * dx;
+              const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[FP], c3 = q0[FP + 1];
+              if (c0 == c1 && c0 == c2 && c0 == c3) same = (int)c0;
+            } else {
+              // four equal taps c: floor(b0 c / 512) + floor(b1 c / 512) is 4c - 1 or 4c, and (that + 2) >> 2 = c
+              const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
+              const uint32_t i00 = s_fov[sy0 * FP + sx0], i01 = s_fov[sy0 * FP + sx1], i10 = s_fov[sy1 * FP + sx0],
+                             i11 = s_fov[sy1 * FP + sx1];
+              if (unit_taps && i00 == i01 && i00 == i10 && i00 == i11) same = (int)i00;
+            }
+            if (same >= 0) s_out[o] = s_cmu[same];
+          }
+          const unsigned mixed = __ballot_sync(0xffffffffu, valid && same < 0);
+          if (mixed) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(s_count, __popc(mixed));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (valid && same < 0) s_list[pos + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)o;
+          }
+          dy += qN;
+          dx += rN;
+          if (dx >= OW) { dx -= OW; ++dy; }
+        }
         __syncthreads();
-        if (tid == 0) s_count[0] = 0;
-        __syncthreads();
-      }
-      int dy = (b0 + tid) / OW, dx = (b0 + tid) - dy * OW;
-      for (int o0 = b0; o0 < b1; o0 += NT) {  // uniform trip count
-        const int o = o0 + tid;
-        const bool valid = o < b1;
-        int same = -1;
-        if (valid) {
-          if (rs_mode == CBEV_RS_COPY) {
-            same = s_fov[dy * FP + dx];
-          } else if (rs_mode == CBEV_RS_HALF) {
-            const uint8_t* q0 = s_fov + (2 * dy) * FP + 2 * dx;
+        const int nmixed = s_count[0];
+        nmixed_all += nmixed;
+        for (int idx = tid; idx < nmixed; idx += NT) {
+          const int o = s_list[idx];
+          const int oy = o / OW, ox = o - oy * OW;
+          uint32_t key = 0;
+          if (rs_mode == CBEV_RS_HALF) {
+            // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
+            const uint8_t* q0 = s_fov + (2 * oy) * FP + 2 * ox;
             const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[FP], c3 = q0[FP + 1];
-            if (c0 == c1 && c0 == c2 && c0 == c3) same = (int)c0;
+            const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
+            const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
+            key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
           } else {
-            // four equal taps c: floor(b0 c / 512) + floor(b1 c / 512) is 4c - 1 or 4c, and (that + 2) >> 2 = c
-            const int sx0 = lxo[dx], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[dy], sy1 = min(sy0 + 1, S - 1);
-            const uint32_t i00 = s_fov[sy0 * FP + sx0], i01 = s_fov[sy0 * FP + sx1], i10 = s_fov[sy1 * FP + sx0],
-                           i11 = s_fov[sy1 * FP + sx1];
-            if (unit_taps && i00 == i01 && i00 == i10 && i00 == i11) same = (int)i00;
+            // CBEV_RS_LINEAR.  HResizeLinear: int32 rows = S0 * a0 + S1 * a1;
+            // VResizeLinear: ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2
+            const int sx0 = lxo[ox], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[oy], sy1 = min(sy0 + 1, S - 1);
+            const int a0 = lxa[ox], a1 = lxa[OW + ox], b0 = lyb[oy], b1 = lyb[OH + oy];
+            const uint32_t k00 = s_key[s_fov[sy0 * FP + sx0]], k01 = s_key[s_fov[sy0 * FP + sx1]],
+                           k10 = s_key[s_fov[sy1 * FP + sx0]], k11 = s_key[s_fov[sy1 * FP + sx1]];
+  #pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              const int r0 = (int)((k00 >> (8 * ch)) & 255u) * a0 + (int)((k01 >> (8 * ch)) & 255u) * a1;
+              const int r1 = (int)((k10 >> (8 * ch)) & 255u) * a0 + (int)((k11 >> (8 * ch)) & 255u) * a1;
+              const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+              key |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
+            }
           }
-          if (same >= 0) s_out[o] = s_cmu[same];
+          s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
         }
-        const unsigned mixed = __ballot_sync(0xffffffffu, valid && same < 0);
-        if (mixed) {
-          int pos = 0;
-          if (lane == 0) pos = atomicAdd(s_count, __popc(mixed));
-          pos = __shfl_sync(0xffffffffu, pos, 0);
-          if (valid && same < 0) s_list[pos + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)o;
-        }
-        dy += qN;
-        dx += rN;
-        if (dx >= OW) { dx -= OW; ++dy; }
-      }
-      __syncthreads();
-      const int nmixed = s_count[0];
-      nmixed_all += nmixed;
-      for (int idx = tid; idx < nmixed; idx += NT) {
-        const int o = s_list[idx];
-        const int oy = o / OW, ox = o - oy * OW;
-        uint32_t key = 0;
-        if (rs_mode == CBEV_RS_HALF) {
-          // OpenCV's 2x2 fast path for 8-bit images: (a + b + c + d + 2) >> 2 per channel
-          const uint8_t* q0 = s_fov + (2 * oy) * FP + 2 * ox;
-          const uint32_t c0 = q0[0], c1 = q0[1], c2 = q0[FP], c3 = q0[FP + 1];
-          const uint32_t rg = s_rg[c0] + s_rg[c1] + s_rg[c2] + s_rg[c3] + 0x00020002u;
-          const uint32_t b = s_b[c0] + s_b[c1] + s_b[c2] + s_b[c3] + 2u;
-          key = ((rg & 0xffffu) >> 2) | ((rg >> 18) << 8) | ((b >> 2) << 16);
-        } else {
-          // CBEV_RS_LINEAR.  HResizeLinear: int32 rows = S0 * a0 + S1 * a1;
-          // VResizeLinear: ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2 >> 2
-          const int sx0 = lxo[ox], sx1 = min(sx0 + 1, S - 1), sy0 = lyo[oy], sy1 = min(sy0 + 1, S - 1);
-          const int a0 = lxa[ox], a1 = lxa[OW + ox], b0 = lyb[oy], b1 = lyb[OH + oy];
-          const uint32_t k00 = s_key[s_fov[sy0 * FP + sx0]], k01 = s_key[s_fov[sy0 * FP + sx1]],
-                         k10 = s_key[s_fov[sy1 * FP + sx0]], k11 = s_key[s_fov[sy1 * FP + sx1]];
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const int r0 = (int)((k00 >> (8 * ch)) & 255u) * a0 + (int)((k01 >> (8 * ch)) & 255u) * a1;
-            const int r1 = (int)((k10 >> (8 * ch)) & 255u) * a0 + (int)((k11 >> (8 * ch)) & 255u) * a1;
-            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-            key |= (uint32_t)min(max(v, 0), 255) << (8 * ch);
-          }
-        }
-        s_out[o] = (uint8_t)classify_key<OBS_MODE>(key, s_key, s_cm);
-      }
       }  // bands
       if (P.trace != nullptr && tid == 0) P.trace[(size_t)env * 8 + 7] = (unsigned long long)(unsigned)nmixed_all << 32;
     }
@@ -1238,7 +1238,8 @@ int launch(cbev_engine* e, const RenderParams& P, size_t smem, size_t smem_any, 
     auto kern = k_render_any<MODE, CH>;
     if (!attr_done[dev][1]) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-        cbev_set_error("k_render_any: cannot opt in to 227 KB of dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+        cbev_set_error("k_render_any: cannot opt in to 227 KB of dynamic shared memory: %s",
+                       cudaGetErrorString(cudaGetLastError()));
         return 1;
       }
       attr_done[dev][1] = true;
@@ -1250,7 +1251,8 @@ int launch(cbev_engine* e, const RenderParams& P, size_t smem, size_t smem_any, 
   auto kern = k_render<MODE, CH>;
   if (!attr_done[dev][0]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
-      cbev_set_error("k_render: cannot opt in to 100 KB of dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      cbev_set_error("k_render: cannot opt in to 100 KB of dynamic shared memory: %s",
+                     cudaGetErrorString(cudaGetLastError()));
       return 1;
     }
     attr_done[dev][0] = true;
